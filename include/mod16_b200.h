@@ -1,0 +1,144 @@
+/*
+ * mod16_b200 -- C ABI of the B200-native MOD16 evapotranspiration forward path.
+ *
+ * The reference (arthur-e/MOD16) is pure Python/numpy and has NO foreign-function
+ * interface; the boundary it exposes for this path is the Python callable contract
+ *
+ *     MOD16._evapotranspiration(params, *14 drivers, f_wet, tiny, r_corr_list)
+ *                                              mod16/__init__.py:196-201
+ *     MOD16._et(params, *14 drivers, ...)      mod16/__init__.py:163-168
+ *     MOD16.evapotranspiration(self, *14 drivers, f_wet, separate)
+ *                                              mod16/__init__.py:675-682
+ *
+ * and the objective loops built on `_et` (mod16/sensitivity.py:94-96,
+ * mod16/calibration.py:224-227).  The entry points below are what a binding for those
+ * calls needs: plain pointers, sizes and flag words; no Python, numpy or torch types.
+ * `mod16_b200/_abi.py` binds them with ctypes; INTEGRATION.md shows the stub a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *  - every data pointer is a DEVICE pointer (cudaMalloc / torch CUDA tensor storage)
+ *    unless the field comment says "host";
+ *  - per-step arrays are (T, N) row-major: element (t, n) of driver k lives at
+ *    ptr[t * t_stride + n * n_stride] (strides in ELEMENTS; 0 broadcasts);
+ *  - all calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL is the
+ *    legacy default stream); nothing is allocated behind the caller's back;
+ *  - return value: MOD16_OK or a negative error code; mod16_last_cuda_error() returns the
+ *    cudaError_t of the last failed CUDA call on this thread's library state.
+ */
+#ifndef MOD16_B200_H
+#define MOD16_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOD16_ABI_VERSION 1
+
+#define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
+#define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
+#define MOD16_N_DRIVERS 14 /* positional drivers of the three entry points above */
+
+/* parameter row order == MOD16.required_parameters */
+enum {
+  MOD16_P_TMIN_CLOSE = 0, MOD16_P_TMIN_OPEN, MOD16_P_VPD_OPEN, MOD16_P_VPD_CLOSE,
+  MOD16_P_GL_SH, MOD16_P_GL_WV, MOD16_P_G_CUTICULAR, MOD16_P_CSL, MOD16_P_RBL_MIN,
+  MOD16_P_RBL_MAX, MOD16_P_BETA
+};
+
+/* driver order == positional order of the reference signatures */
+enum {
+  MOD16_D_LW_NET_DAY = 0, MOD16_D_LW_NET_NIGHT, MOD16_D_SW_RAD_DAY, MOD16_D_SW_RAD_NIGHT,
+  MOD16_D_SW_ALBEDO, MOD16_D_TEMP_DAY, MOD16_D_TEMP_NIGHT, MOD16_D_TEMP_ANNUAL,
+  MOD16_D_TMIN, MOD16_D_VPD_DAY, MOD16_D_VPD_NIGHT, MOD16_D_PRESSURE, MOD16_D_FPAR,
+  MOD16_D_LAI
+};
+
+/* error codes */
+#define MOD16_OK 0
+#define MOD16_ERR_NULL (-1)     /* a required pointer is NULL */
+#define MOD16_ERR_SHAPE (-2)    /* T or N < 0, or a stride is negative */
+#define MOD16_ERR_FLAGS (-3)    /* unknown / inconsistent flag word */
+#define MOD16_ERR_CUDA (-4)     /* a CUDA call failed: see mod16_last_cuda_error() */
+#define MOD16_ERR_PARAMS (-5)   /* parameter source is inconsistent */
+#define MOD16_ERR_WORKSPACE (-6)/* workspace too small */
+
+/* flag word of mod16_forward_* ------------------------------------------------------- */
+/* semantics: which of the reference's two forward paths is reproduced */
+#define MOD16_SEM_STATIC 0x0u    /* _evapotranspiration/_et: W m-2, no clamps (:196-382) */
+#define MOD16_SEM_INSTANCE 0x1u  /* evapotranspiration(): kg m-2 s-1, clamps (:675-793) */
+#define MOD16_SEM_MASK 0xFu
+/* outputs written (each a dense (T, N) array) */
+#define MOD16_OUT_SUM 0x00u        /* out[0] = day + night                    (_et) */
+#define MOD16_OUT_DAY_NIGHT 0x10u  /* out[0] = day, out[1] = night */
+#define MOD16_OUT_COMPONENTS 0x20u /* out[0..2] = day canopy, soil, transpiration;
+                                      out[3..5] = night  (separate=True, :789-790) */
+#define MOD16_OUT_MASK 0xF0u
+/* the static path's batch-global transpiration gate `if np.any(g_surf > 0)` (:343) */
+#define MOD16_GATE_GLOBAL 0x000u     /* call-exact: optimistic pass + device-side fix-up */
+#define MOD16_GATE_ELEMENT 0x100u    /* predicate per element (a loop of scalar calls) */
+#define MOD16_GATE_OPEN 0x200u       /* always compute transpiration */
+#define MOD16_GATE_CLOSED 0x300u     /* transpiration = 0 */
+#define MOD16_GATE_OPEN_TRACK 0x400u /* GATE_OPEN, and OR the predicate into *gate_flag */
+#define MOD16_GATE_FIXUP 0x500u      /* only if *gate_flag == 0: recompute with GATE_CLOSED
+                                        (multi-GPU: all-reduce(max) the flag in between) */
+#define MOD16_GATE_MASK 0xF00u
+/* kernel selection (testing / profiling): default picks the vectorised kernel when the
+   layout allows 128-bit loads, else the strided one */
+#define MOD16_FORCE_GENERIC 0x1000u
+#define MOD16_FORCE_MIRROR 0x2000u  /* f32: op-for-op transcription instead of fast math */
+
+typedef struct mod16_driver {
+  const void* ptr;   /* device array of float / double, or NULL: use `scalar` */
+  int64_t t_stride;  /* elements between consecutive time steps (0: constant in time) */
+  int64_t n_stride;  /* elements between consecutive pixels (0: constant in space) */
+  double scalar;     /* value used when ptr == NULL */
+} mod16_driver_t;
+
+typedef struct mod16_drivers {
+  mod16_driver_t drv[MOD16_N_DRIVERS];
+  mod16_driver_t r_corr[2]; /* optional `r_corr_list` (day, night), :291-294 */
+  int32_t has_r_corr;
+  int32_t reserved;
+} mod16_drivers_t;
+
+/*
+ * Parameter source, one of
+ *  (a) pft != NULL: per-pixel land-cover code (0..12) gathers a column of `table`
+ *      (the BPLUT dict of mod16/utils.py:81-117 as a dense 11 x 13 array);
+ *  (b) arrays[k] != NULL for all k: per-pixel parameter vectors, the `(1 x N)` arrays of
+ *      the static path's `params` list (:175-178); array_stride[k] is 1, or 0 for a scalar
+ *      held in device memory;
+ *  (c) neither: one parameter set for every pixel, table[k][0].
+ */
+typedef struct mod16_params {
+  const uint8_t* pft;                         /* device, N codes, or NULL */
+  double table[MOD16_N_PARAMS][MOD16_N_PFT];  /* host values, copied at launch */
+  const void* arrays[MOD16_N_PARAMS];         /* device, float / double as the entry */
+  int64_t array_stride[MOD16_N_PARAMS];
+} mod16_params_t;
+
+typedef struct mod16_out {
+  void* out[6];       /* device (T, N) row-major, dense; see MOD16_OUT_* */
+  int32_t* gate_flag; /* device int; required by GATE_GLOBAL / OPEN_TRACK / FIXUP */
+} mod16_out_t;
+
+int mod16_abi_version(void);
+int mod16_last_cuda_error(void);
+const char* mod16_error_string(int code);
+
+/* K1 -- fused forward model over a (T, N) block of pixel-timesteps. */
+int mod16_forward_f32(const mod16_drivers_t* drivers, const mod16_params_t* params,
+                      const mod16_out_t* out, int64_t T, int64_t N, uint32_t flags,
+                      void* stream);
+int mod16_forward_f64(const mod16_drivers_t* drivers, const mod16_params_t* params,
+                      const mod16_out_t* out, int64_t T, int64_t N, uint32_t flags,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOD16_B200_H */

@@ -1,0 +1,97 @@
+'''
+ctypes binding of ``include/mod16_b200.h`` -- the only way the Python layer reaches the
+CUDA kernels.  There is no CPU fallback: if ``libmod16_b200.so`` is missing or CUDA is
+unavailable, the first call raises.
+'''
+import ctypes
+import os
+
+N_PARAMS = 11
+N_PFT = 13
+N_DRIVERS = 14
+
+# flag words (mirror include/mod16_b200.h)
+SEM_STATIC, SEM_INSTANCE = 0x0, 0x1
+OUT_SUM, OUT_DAY_NIGHT, OUT_COMPONENTS = 0x00, 0x10, 0x20
+GATE_GLOBAL, GATE_ELEMENT, GATE_OPEN, GATE_CLOSED = 0x000, 0x100, 0x200, 0x300
+GATE_OPEN_TRACK, GATE_FIXUP = 0x400, 0x500
+FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
+GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
+              'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
+
+ABI_VERSION = 1
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
+                        'libmod16_b200.so')
+
+
+class Driver(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p), ('t_stride', ctypes.c_int64),
+                ('n_stride', ctypes.c_int64), ('scalar', ctypes.c_double)]
+
+
+class Drivers(ctypes.Structure):
+    _fields_ = [('drv', Driver * N_DRIVERS), ('r_corr', Driver * 2),
+                ('has_r_corr', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [('pft', ctypes.c_void_p),
+                ('table', (ctypes.c_double * N_PFT) * N_PARAMS),
+                ('arrays', ctypes.c_void_p * N_PARAMS),
+                ('array_stride', ctypes.c_int64 * N_PARAMS)]
+
+
+class Out(ctypes.Structure):
+    _fields_ = [('out', ctypes.c_void_p * 6), ('gate_flag', ctypes.c_void_p)]
+
+
+class Mod16Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/mod16_b200.h declares; tests/test_abi_symbols.py checks the list
+# against the header and the built library
+EXPORTS = {
+    'mod16_abi_version': (ctypes.c_int, []),
+    'mod16_last_cuda_error': (ctypes.c_int, []),
+    'mod16_error_string': (ctypes.c_char_p, [ctypes.c_int]),
+    'mod16_forward_f32': (ctypes.c_int, [
+        ctypes.POINTER(Drivers), ctypes.POINTER(Params), ctypes.POINTER(Out),
+        ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p]),
+    'mod16_forward_f64': (ctypes.c_int, [
+        ctypes.POINTER(Drivers), ctypes.POINTER(Params), ctypes.POINTER(Out),
+        ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p]),
+}
+
+
+def load(path=None):
+    'Loads the shared library (once) and declares the prototypes.'
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise Mod16Error(
+            'CUDA library %s is not built; run `python -m mod16_b200.build` '
+            '(there is no CPU fallback)' % path)
+    lib = ctypes.CDLL(path)
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.mod16_abi_version() != ABI_VERSION:
+        raise Mod16Error('ABI version mismatch: library %d, binding %d' % (
+            lib.mod16_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        lib = load()
+        msg = lib.mod16_error_string(rc).decode()
+        if rc == -4:
+            msg += ' [cudaError %d]' % lib.mod16_last_cuda_error()
+        raise Mod16Error('mod16_b200: %s (code %d)' % (msg, rc))

@@ -1,0 +1,84 @@
+// Shared host/device declarations of the CUDA translation units: kernel argument blocks,
+// broadcast-aware loads, error plumbing of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mod16_b200.h"
+#include "mod16_math.cuh"
+
+namespace mod16 {
+
+// thread-local record of the last failed CUDA call (mod16_last_cuda_error())
+extern thread_local int g_last_cuda_error;
+
+#define M16_CUDA_CHECK(expr)                                   \
+  do {                                                         \
+    cudaError_t e__ = (expr);                                  \
+    if (e__ != cudaSuccess) {                                  \
+      ::mod16::g_last_cuda_error = (int)e__;                   \
+      return MOD16_ERR_CUDA;                                   \
+    }                                                          \
+  } while (0)
+
+// One broadcastable input as the kernels see it.
+template <typename R>
+struct Arr {
+  const R* ptr;      // NULL: scalar
+  int64_t ts, ns;    // element strides over time / pixels (0 broadcasts)
+  R scalar;
+  __device__ __forceinline__ R at(int64_t t, int64_t n) const {
+    return ptr ? __ldg(ptr + t * ts + n * ns) : scalar;
+  }
+};
+
+template <typename R>
+struct ForwardArgs {
+  Arr<R> drv[MOD16_N_DRIVERS];
+  Arr<R> rc[2];
+  int has_rc;
+  // parameters
+  const uint8_t* pft;
+  const R* par_arr[MOD16_N_PARAMS];
+  int64_t par_stride[MOD16_N_PARAMS];
+  int par_mode;  // 0: table column 0 for everyone, 1: gather by pft, 2: per-pixel arrays
+  double table[MOD16_N_PARAMS][MOD16_N_PFT];
+  // outputs
+  R* out[6];
+  int* gate_flag;
+  int skip_if_flag;  // fix-up launch: return at once when *gate_flag != 0
+  int track_gate;    // OR (g_surf > 0) into *gate_flag
+  int gate;          // mod16::Gate
+  int64_t T, N;
+  int t_chunk;       // time steps per block row
+};
+
+// Builds Params<R> for one pixel from the argument block.
+template <typename R, int SEM>
+__device__ __forceinline__ Params<R> load_params(const ForwardArgs<R>& a, int64_t n,
+                                                 const double (*tab)[MOD16_N_PFT]) {
+  Params<R> q;
+  double v[MOD16_N_PARAMS];
+  if (a.par_mode == 2) {
+#pragma unroll
+    for (int k = 0; k < MOD16_N_PARAMS; ++k)
+      v[k] = (double)__ldg(a.par_arr[k] + n * a.par_stride[k]);
+  } else {
+    int code = 0;
+    if (a.par_mode == 1) {
+      code = (int)__ldg(a.pft + n);
+      // numpy fancy indexing would raise on a code > 12; the kernel yields NaN parameters
+      if (code >= MOD16_N_PFT) code = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < MOD16_N_PARAMS; ++k) v[k] = tab[k][code];
+  }
+  q.tmin_close = (R)v[0]; q.tmin_open = (R)v[1]; q.vpd_open = (R)v[2];
+  q.vpd_close = (R)v[3];  q.gl_sh = (R)v[4];     q.gl_wv = (R)v[5];
+  q.g_cuticular = (R)v[6]; q.csl = (R)v[7];      q.rbl_min = (R)v[8];
+  q.rbl_max = (R)v[9];    q.beta = (R)v[10];
+  q.tann_lo = 273.15 + (SEM == SEM_STATIC ? v[1] : v[0]);
+  return q;
+}
+
+}  // namespace mod16

@@ -1,0 +1,255 @@
+'''
+Host side of K1: turns the reference's loosely typed call arguments (python scalars,
+0-d / (N,) / (1, N) / (T, N) numpy arrays or torch tensors) into the broadcast descriptors
+of ``include/mod16_b200.h`` and launches the fused CUDA forward kernel.
+
+The broadcasting contract mirrors numpy's for the shapes the reference's callers use
+(SURVEY.md H6): the result has the broadcast shape of all drivers and parameters; an
+input that is constant along time or along pixels is never materialised -- it is passed
+with a zero stride.  Inputs already resident on the GPU (torch CUDA tensors) are used in
+place; host inputs are copied to the device for the call and results are copied back.
+'''
+import ctypes
+import numpy as np
+import torch
+
+from . import _abi
+
+_TORCH_DT = {np.dtype('float32'): torch.float32, np.dtype('float64'): torch.float64}
+
+
+def _is_scalar(x):
+    if isinstance(x, (int, float, np.integer, np.floating, bool)):
+        return True
+    if isinstance(x, np.ndarray) and x.ndim == 0:
+        return True
+    if isinstance(x, torch.Tensor) and x.ndim == 0 and x.device.type == 'cpu':
+        return True
+    return False
+
+
+def _shape(x):
+    return () if _is_scalar(x) else tuple(x.shape)
+
+
+def result_dtype(values, dtype=None):
+    '''
+    float32 only when numpy's own promotion of the inputs would give float32 (python
+    scalars are weak, NEP 50); otherwise float64.  ``dtype`` overrides.
+    '''
+    if dtype is not None:
+        dt = np.dtype(dtype)
+        if dt not in _TORCH_DT:
+            raise TypeError('dtype must be float32 or float64, not %s' % dt)
+        return dt
+    kinds = []
+    for v in values:
+        if isinstance(v, (int, float, bool)):
+            continue  # weak python scalar
+        if isinstance(v, torch.Tensor):
+            kinds.append(np.dtype(str(v.dtype).replace('torch.', '')))
+        elif isinstance(v, (np.ndarray, np.generic)):
+            kinds.append(v.dtype)
+        else:
+            kinds.append(np.asarray(v).dtype)
+    if not kinds:
+        return np.dtype('float64')
+    dt = np.result_type(*kinds)
+    if dt == np.dtype('float32') or dt == np.dtype('float16'):
+        return np.dtype('float32')
+    return np.dtype('float64')
+
+
+def pick_device(values, device=None):
+    if device is not None:
+        return torch.device(device)
+    for v in values:
+        if isinstance(v, torch.Tensor) and v.device.type == 'cuda':
+            return v.device
+    if not torch.cuda.is_available():
+        raise _abi.Mod16Error(
+            'mod16_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+class _Staged(object):
+    'Keeps device copies alive for the duration of a call and fills Driver structs.'
+
+    def __init__(self, device, dtype):
+        self.device = device
+        self.np_dtype = dtype
+        self.t_dtype = _TORCH_DT[dtype]
+        self.keep = []
+
+    def tensor(self, x, dtype=None):
+        dtype = dtype or self.t_dtype
+        if isinstance(x, torch.Tensor):
+            t = x.detach()
+            if t.device != self.device or t.dtype != dtype:
+                t = t.to(device=self.device, dtype=dtype, non_blocking=True)
+        else:
+            a = np.asarray(x)
+            t = torch.from_numpy(np.ascontiguousarray(a)).to(
+                device=self.device, dtype=dtype, non_blocking=True)
+        self.keep.append(t)
+        return t
+
+    def fill(self, slot, x, T, N, ndim):
+        '''
+        Describes input ``x`` (broadcastable to the call's (T, N) view) in ``slot``.
+        '''
+        if _is_scalar(x):
+            slot.ptr = None
+            slot.t_stride = 0
+            slot.n_stride = 0
+            slot.scalar = float(x)
+            return
+        t = self.tensor(x)
+        shp = tuple(t.shape)
+        if len(self.full_shape) > 2 and len(shp) >= 2:
+            # more than two axes: leading axes fold into time; materialise the broadcast
+            t = torch.broadcast_to(t, self.full_shape).reshape(T, N)
+            self.keep.append(t)
+            shp = tuple(t.shape)
+        if len(shp) == 1:
+            shp = (1,) + shp
+            strides = (0, t.stride(0))
+        else:
+            strides = (t.stride(0), t.stride(1))
+        if any(s < 0 for s in strides):
+            t = t.contiguous()
+            self.keep.append(t)
+            strides = (t.stride(0), t.stride(1)) if t.ndim == 2 else (0, t.stride(0))
+        ts = 0 if shp[0] == 1 else strides[0]
+        ns = 0 if shp[1] == 1 else strides[1]
+        if shp[0] not in (1, T) or shp[1] not in (1, N):
+            raise ValueError('input of shape %r does not broadcast to (%d, %d)' % (
+                tuple(x.shape), T, N))
+        slot.ptr = t.data_ptr()
+        slot.t_stride = ts
+        slot.n_stride = ns
+        slot.scalar = 0.0
+
+
+def _view_2d(shape):
+    'Maps a broadcast result shape onto the kernels\' (T, N) view.'
+    if len(shape) == 0:
+        return 1, 1
+    if len(shape) == 1:
+        return 1, shape[0]
+    T = 1
+    for s in shape[:-1]:
+        T *= s
+    return T, shape[-1]
+
+
+def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static',
+                out_mode='sum', gate='global', dtype=None, r_corr_list=None, device=None,
+                stream=None, force=0, as_torch=None, gate_flag=None):
+    '''
+    Launches K1 once.
+
+    drivers : the 14 positional drivers of the reference signatures
+    params  : sequence of 11 values in ``required_parameters`` order, each a scalar or a
+              per-pixel array ((N,), (1, N)); or None when ``pft``/``table`` are given
+    pft, table : uint8 land-cover code per pixel and the dense 11 x 13 BPLUT table
+    out_mode : 'sum' | 'day_night' | 'components'
+    gate     : 'global' (reference) | 'element' | 'open' | 'closed' | 'open_track' | 'fixup'
+
+    Returns a list of 1, 2 or 6 arrays of the broadcast shape (numpy, unless an input was
+    a CUDA tensor or ``as_torch`` is set).
+    '''
+    lib = _abi.load()
+    drivers = list(drivers)
+    if len(drivers) != _abi.N_DRIVERS:
+        raise TypeError('expected 14 drivers, got %d' % len(drivers))
+    extra = list(r_corr_list) if r_corr_list is not None else []
+    plist = list(params) if params is not None else []
+    if params is not None and len(plist) != _abi.N_PARAMS:
+        raise TypeError('expected 11 parameters, got %d' % len(plist))
+    everything = drivers + extra + plist
+    np_dtype = result_dtype(everything, dtype)
+    dev = pick_device(everything + ([pft] if pft is not None else []), device)
+    if as_torch is None:
+        as_torch = any(isinstance(v, torch.Tensor) and v.device.type == 'cuda'
+                       for v in everything)
+
+    shapes = [_shape(v) for v in everything]
+    if pft is not None:
+        shapes.append(tuple(np.shape(pft)) if not isinstance(pft, torch.Tensor)
+                      else tuple(pft.shape))
+    full_shape = tuple(np.broadcast_shapes(*shapes))
+    T, N = _view_2d(full_shape)
+
+    with torch.cuda.device(dev):
+        st = _Staged(dev, np_dtype)
+        st.full_shape = full_shape
+        cd = _abi.Drivers()
+        for k, v in enumerate(drivers):
+            st.fill(cd.drv[k], v, T, N, len(full_shape))
+        cd.has_r_corr = 1 if r_corr_list is not None else 0
+        for k, v in enumerate(extra[:2]):
+            st.fill(cd.r_corr[k], v, T, N, len(full_shape))
+
+        cp = _abi.Params()
+        if pft is not None:
+            if table is None:
+                raise TypeError('`pft` needs the 11 x 13 `table`')
+            tab = np.asarray(table, np.float64)
+            if tab.shape != (_abi.N_PARAMS, _abi.N_PFT):
+                raise ValueError('table must be 11 x 13')
+            pt = st.tensor(pft, torch.uint8).reshape(-1)
+            if pt.numel() != N:
+                raise ValueError('pft must hold one code per pixel (N = %d)' % N)
+            pt = pt.contiguous()
+            st.keep.append(pt)
+            cp.pft = pt.data_ptr()
+        else:
+            tab = np.full((_abi.N_PARAMS, _abi.N_PFT), np.nan)
+            if all(_is_scalar(v) for v in plist):
+                tab[:, 0] = [float(v) for v in plist]
+            else:
+                for k, v in enumerate(plist):
+                    if _is_scalar(v):
+                        v = np.full((1,), float(v))
+                    t = st.tensor(v).reshape(-1)
+                    if t.numel() not in (1, N):
+                        raise ValueError(
+                            'parameter %d has %d values, expected 1 or N = %d' % (
+                                k, t.numel(), N))
+                    t = t.contiguous()
+                    st.keep.append(t)
+                    cp.arrays[k] = t.data_ptr()
+                    cp.array_stride[k] = 0 if t.numel() == 1 else 1
+        for i in range(_abi.N_PARAMS):
+            for j in range(_abi.N_PFT):
+                cp.table[i][j] = tab[i, j]
+
+        n_out = {'sum': 1, 'day_night': 2, 'components': 6}[out_mode]
+        flags = {'static': _abi.SEM_STATIC, 'instance': _abi.SEM_INSTANCE}[semantics]
+        flags |= {'sum': _abi.OUT_SUM, 'day_night': _abi.OUT_DAY_NIGHT,
+                  'components': _abi.OUT_COMPONENTS}[out_mode]
+        flags |= _abi.GATE_FLAGS[gate] | force
+        outs = [torch.empty((T, N), device=dev, dtype=st.t_dtype) for _ in range(n_out)]
+        co = _abi.Out()
+        for k, o in enumerate(outs):
+            co.out[k] = o.data_ptr()
+        if gate_flag is None:
+            gate_flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        co.gate_flag = gate_flag.data_ptr()
+        s = stream if stream is not None else torch.cuda.current_stream(dev)
+        handle = s.cuda_stream if hasattr(s, 'cuda_stream') else int(s)
+        fn = lib.mod16_forward_f32 if np_dtype == np.dtype('float32') else lib.mod16_forward_f64
+        _abi.check(fn(ctypes.byref(cd), ctypes.byref(cp), ctypes.byref(co), T, N, flags,
+                      ctypes.c_void_p(handle)))
+        outs = [o.reshape(full_shape) for o in outs]
+        if as_torch:
+            # staged copies must outlive the asynchronous launch on a foreign stream
+            if hasattr(s, 'cuda_stream') and s != torch.cuda.current_stream(dev):
+                for t in st.keep + outs:
+                    t.record_stream(s)
+            return outs
+        res = [o.cpu().numpy() for o in outs]  # synchronises
+        if full_shape == ():
+            res = [r[()] for r in res]
+        return res

@@ -248,7 +248,9 @@ def static_evapotranspiration(
             t_open = (1 - fw) * ((s * a_canopy) + (
                 rho * CP_AIR * fpar * (vpd / r_ad)))              # :344-345
             t_open = t_open / (s + gamma * (1 + (1 / g_canopy) / r_ad))  # :346
-        if gate == 'global':
+        if gate == 'global' or i == 1:
+            # at night g_surf == 0, so the reference's gate is never open there;
+            #   the extension modes below only concern the day half
             t = t_open if np.any(g_surf > 0) else 0               # :343-348
         elif gate == 'element':
             t = np.where(g_surf > 0, t_open, 0)

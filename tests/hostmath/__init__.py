@@ -1,0 +1,74 @@
+'''
+TEST HARNESS ONLY: builds tests/hostmath/hostmath.cpp (the kernels' per-element math,
+compiled for the host) and exposes it through ctypes.  Used by the `-m "not gpu"` tests to
+check the device math against the oracle where no GPU exists.  Never imported by the
+product package.
+'''
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, '_build', 'libhostmath.so')
+SRC = os.path.join(HERE, 'hostmath.cpp')
+CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), 'mod16_b200', 'csrc')
+
+
+def build():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh')]
+    if os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
+        return SO
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    fast = os.path.exists(os.path.join(CSRC, 'mod16_fast.cuh'))
+    cmd = ['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-ffp-contract=off',
+           '-o', SO, SRC] + (['-DHM_WITH_FAST'] if fast else [])
+    subprocess.run(cmd, check=True)
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+    return _lib
+
+
+def _flat(arrs, dtype):
+    b = np.broadcast_arrays(*[np.asarray(a, dtype=dtype) for a in arrs])
+    shape = b[0].shape
+    return np.ascontiguousarray(np.stack([x.ravel() for x in b])), shape
+
+
+def forward(params, drivers, semantics='static', gate='global', dtype=np.float64,
+            r_corr_list=None, fast=False):
+    '''
+    Evaluates the kernel math on the host.  Returns dict(day=(canopy, soil, trans),
+    night=(...), g_pos=bool array) with arrays of the broadcast shape.
+    '''
+    allv, shape = _flat(list(drivers) + list(params) +
+                        (list(r_corr_list) if r_corr_list is not None else []), dtype)
+    n = allv.shape[1]
+    drv = np.ascontiguousarray(allv[:14])
+    par = np.ascontiguousarray(allv[14:25])
+    rc = np.ascontiguousarray(allv[25:27]) if r_corr_list is not None else np.zeros((2, 1), dtype)
+    out = np.empty((6, n), dtype)
+    gpos = np.empty(n, np.uint8)
+    sem = {'static': 0, 'instance': 1}[semantics]
+    g = {'open': 0, 'global': 0, 'element': 1, 'closed': 2}[gate]
+    suffix = 'f64' if dtype == np.float64 else 'f32'
+    name = ('hm_fast_' if fast else 'hm_forward_') + suffix
+    fn = getattr(lib(), name)
+    fn.restype = None
+    fn(ctypes.c_int(sem), ctypes.c_int(g), drv.ctypes.data_as(ctypes.c_void_p),
+       par.ctypes.data_as(ctypes.c_void_p), rc.ctypes.data_as(ctypes.c_void_p),
+       ctypes.c_int(1 if r_corr_list is not None else 0), ctypes.c_int64(n),
+       out.ctypes.data_as(ctypes.c_void_p), gpos.ctypes.data_as(ctypes.c_void_p))
+    out = out.reshape((6,) + shape)
+    gpos = gpos.reshape(shape).astype(bool)
+    if semantics == 'static' and gate == 'global' and not gpos.any():
+        out[2] = 0  # the batch-global gate is closed (:343-348)
+    return dict(day=(out[0], out[1], out[2]), night=(out[3], out[4], out[5]), g_pos=gpos)

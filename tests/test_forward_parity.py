@@ -1,0 +1,235 @@
+'''
+GPU parity tests of K1 (the fused forward kernel) through the drop-in Python API, which
+calls the C ABI.  Compared with the oracle on the same seeded inputs and with the golden
+vectors frozen from the reference.
+'''
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import parity
+from mod16_b200 import MOD16, _abi, synthetic, utils
+from mod16_b200.models import MOD16Collection61
+from oracle import mod16_oracle as orc
+
+pytestmark = pytest.mark.gpu
+NAMES = list(synthetic.DRIVER_NAMES)
+BPLUT7 = [-8., 8.8, 650., 4400., .02, .02, 1e-5, .0055, 60., 95., 250.]
+
+
+def as_f64(drv):
+    return [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
+
+
+def test_unit_test_scalars_like_the_reference(cuda_lib):
+    'Reads like /root/reference/tests/tests.py:64-90.'
+    params = dict(gl_sh=0.01, gl_wv=0.01, g_cuticular=1e-5, tmin_close=-8, tmin_open=8,
+                  vpd_open=650, vpd_close=3000, rbl_min=60, rbl_max=90, csl=2.4e-3,
+                  beta=250)
+    vec = [params[p] for p in MOD16.required_parameters]
+    drv = [-50, -30, 150, 0, 0.3, 293, 290, 285, 285, 1000, 500, 100e3, 0.5, 1.5]
+    _et = MOD16._et(vec, *drv)
+    _day, _night = MOD16._evapotranspiration(vec, *drv)
+    model = MOD16(params)
+    _day2, _night2 = model.evapotranspiration(*drv)
+    assert round(float(_et), 2) == 40.94
+    assert round(float(_day + _night), 2) == 40.94
+    assert round(float(_day2 * orc.lhv(293) + _night2 * orc.lhv(290)), 1) == 41.0
+    with pytest.raises(KeyError):
+        MOD16({'gl_sh': 1})
+
+
+def test_verify_inline_arrays(cuda_lib, golden_dir):
+    z = np.load(os.path.join(golden_dir, 'verify.npz'))
+    lw_d, lw_n, sw_d, sw_n, alb, tann, fc, vpd_n = z['scalars']
+    a = (lw_d, lw_n, sw_d, sw_n, alb, z['temp'], z['temp'], tann, z['tmin'], z['vpd_day'],
+         z['vpd_day'], z['pressure'], fc, z['lai'])
+    model = MOD16Collection61(7)
+    assert [getattr(model, k) for k in MOD16.required_parameters] == list(z['params'])
+    day, night = model.evapotranspiration(*a, f_wet=np.array((0, 0.4, 0.8)), separate=True)
+    for h, (hn, got) in enumerate((('day', day), ('night', night))):
+        for c, cn in enumerate(('canopy', 'soil', 'trans')):
+            parity.assert_parity(got[c], z['inst_%s_%s' % (hn, cn)], np.float64,
+                                 parity.MASS_SCALE, what='%s %s' % (hn, cn))
+    b = a[:10] + (vpd_n,) + a[11:]
+    d, n = MOD16._evapotranspiration(list(z['params']), *b, f_wet=np.array((0, 0.4, 0.8)))
+    parity.assert_parity(d, z['static_day'], np.float64, what='static day')
+    parity.assert_parity(n, z['static_night'], np.float64, what='static night')
+    nb = MOD16Collection61(12).evapotranspiration(  # same model the notebook scalar uses
+        -50, -30, 150, 0, 0.3, 293, 285, 285, 285, 1000, 500, 1e5, 0.5, 1.5)
+    ref = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, z['notebook_params']))) \
+        .evapotranspiration(-50, -30, 150, 0, 0.3, 293, 285, 285, 285, 1000, 500, 1e5, 0.5, 1.5)
+    parity.assert_parity(nb[0], ref[0], np.float64, parity.MASS_SCALE)
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_divergence_and_nan_tables(cuda_lib, golden_dir, dtype):
+    'SURVEY.md 8(a): every case as its own call (scalar semantics => element gate).'
+    z = np.load(os.path.join(golden_dir, 'tables.npz'))
+    vec = list(z['params'])
+    drv = [z['drivers'][:, i].astype(dtype) for i in range(14)]
+    ref = z
+    if dtype == np.float32:  # the reference evaluated on the float32-rounded inputs
+        with np.errstate(all='ignore'):
+            d, n = orc.static_evapotranspiration(vec, *as_f64(drv), gate='element')
+            sep = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, vec))) \
+                .evapotranspiration(*as_f64(drv), separate=True)
+        ref = dict(static_day=d, static_night=n)
+        for h, hn in enumerate(('day', 'night')):
+            for c, cn in enumerate(('canopy', 'soil', 'trans')):
+                ref['inst_%s_%s' % (hn, cn)] = sep[h][c]
+    d, n = MOD16._evapotranspiration(vec, *drv, gate='element', dtype=dtype)
+    parity.assert_parity(d, ref['static_day'], dtype, what='static day')
+    parity.assert_parity(n, ref['static_night'], dtype, what='static night')
+    day, night = MOD16(dict(zip(MOD16.required_parameters, vec))).evapotranspiration(
+        *drv, separate=True, dtype=dtype)
+    for hn, got in (('day', day), ('night', night)):
+        for c, cn in enumerate(('canopy', 'soil', 'trans')):
+            parity.assert_parity(got[c], ref['inst_%s_%s' % (hn, cn)], dtype,
+                                 parity.MASS_SCALE, what='inst %s %s' % (hn, cn))
+
+
+def test_global_gate_is_call_exact(cuda_lib, golden_dir):
+    z = np.load(os.path.join(golden_dir, 'tables.npz'))
+    vec = list(z['params'])
+    base = [np.float64(v) for v in z['drivers'][0]]
+    for key in ('closed', 'open', ):
+        drv = list(base)
+        drv[NAMES.index('tmin')] = z['gate_%s_tmin' % key]
+        got = MOD16._et(vec, *drv)
+        parity.assert_parity(got, np.broadcast_to(z['gate_%s_et' % key], got.shape),
+                             np.float64, what='gate ' + key)
+    drv[NAMES.index('tmin')] = np.array([np.nan, np.nan])
+    got = MOD16._et(vec, *drv)
+    parity.assert_parity(got, np.broadcast_to(z['gate_nan_et'], got.shape), np.float64,
+                         what='gate nan')
+
+
+@pytest.mark.parametrize('name', ['rand_phys_f64', 'rand_phys_fill_f64',
+                                  'rand_stress_fill_f64', 'rand_phys_f32',
+                                  'rand_stress_fill_f32'])
+def test_random_golden_fixtures(cuda_lib, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + '.npz'))
+    dtype = np.float32 if name.endswith('f32') else np.float64
+    drv = [z['drv_' + k] if 'drv_' + k in z else 0 for k in NAMES]
+    pft = z['pft']
+    vec = [z['table'][i][pft].reshape(1, -1).astype(dtype) for i in range(11)]
+    d, n = MOD16._evapotranspiration(vec, *drv, dtype=dtype)
+    parity.assert_parity(d, z['static_day'], dtype, what='static day')
+    parity.assert_parity(n, z['static_night'], dtype, what='static night')
+    et = MOD16._et_by_pft(z['table'], pft, *drv, dtype=dtype)
+    parity.assert_parity(et, z['static_et'], dtype, what='_et by pft')
+    model = MOD16(dict(zip(MOD16.required_parameters, z['inst_params'])))
+    day, night = model.evapotranspiration(*drv, separate=True, dtype=dtype)
+    for hn, got in (('day', day), ('night', night)):
+        for c, cn in enumerate(('canopy', 'soil', 'trans')):
+            parity.assert_parity(got[c], z['inst_%s_%s' % (hn, cn)], dtype,
+                                 parity.MASS_SCALE, what='inst %s %s' % (hn, cn))
+    d2, n2 = model.evapotranspiration(*drv, dtype=dtype)
+    parity.assert_parity(d2, (z['inst_day_canopy'] + z['inst_day_soil']) + z['inst_day_trans'],
+                         dtype, parity.MASS_SCALE, what='inst day total')
+
+
+@pytest.mark.parametrize('dtype,kind,nan', [
+    (np.float64, 'physical', 0.0), (np.float64, 'stress', 0.002),
+    (np.float32, 'physical', 0.0), (np.float32, 'stress', 0.002),
+    (np.float32, 'physical', 0.002)])
+def test_medium_grid_against_oracle(cuda_lib, dtype, kind, nan):
+    'A (T, N) block big enough to exercise the vectorised layout, tails and many blocks.'
+    T, N = 37, 4 * 1031
+    d = synthetic.host_drivers(T, N, 4242, kind=kind, dtype=dtype, nan_frac=nan,
+                               fill_frac=nan)
+    drv = [d[k] for k in NAMES]
+    pft = synthetic.host_pft_map(N, 7)
+    table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51),
+                              MOD16.required_parameters, default_beta=250.0)
+    vec = [table[i][pft].reshape(1, N) for i in range(11)]
+    with np.errstate(all='ignore'):
+        ref = orc.static_et(vec, *as_f64(drv))
+    got = MOD16._et_by_pft(table, pft, *drv, dtype=dtype)
+    m = parity.assert_parity(got, ref, dtype, what='%s %s' % (kind, np.dtype(dtype).name),
+                             allow_fail=0 if dtype == np.float64 else 2)
+    print('medium grid', np.dtype(dtype).name, kind, m)
+
+
+def test_input_kinds_and_broadcasting(cuda_lib):
+    'python scalars, (N,), (1, N), (T, 1), (T, N), int16 zeros, torch CUDA tensors.'
+    T, N = 5, 64
+    d = synthetic.host_drivers(T, N, 99)
+    drv = [d[k] for k in NAMES]
+    drv[NAMES.index('sw_rad_night')] = np.zeros((T, N), np.int16)   # calibration.py:383
+    drv[NAMES.index('sw_albedo')] = d['sw_albedo'][:, :1]            # (T, 1)
+    drv[NAMES.index('pressure')] = d['pressure'].reshape(1, N)       # (1, N)
+    drv[NAMES.index('fpar')] = 0.4                                   # python scalar
+    vec = list(BPLUT7)
+    vec[4] = np.linspace(0.01, 0.04, N).reshape(1, N)                # mixed scalar/(1, N)
+    with np.errstate(all='ignore'):
+        ref = orc.static_et(vec, *drv)
+    got = MOD16._et(vec, *drv)
+    assert isinstance(got, np.ndarray) and got.shape == (T, N) and got.dtype == np.float64
+    parity.assert_parity(got, ref, np.float64, what='mixed shapes')
+    # 1-D masked vectors as sensitivity.py:179-185 builds them
+    flat = [v.ravel() if isinstance(v, np.ndarray) and v.shape == (T, N) else v for v in
+            [d[k] for k in NAMES]]
+    flat[NAMES.index('temp_annual')] = np.repeat(d['temp_annual'][None], T, 0).ravel()
+    flat[NAMES.index('pressure')] = np.repeat(d['pressure'][None], T, 0).ravel()
+    with np.errstate(all='ignore'):
+        ref1 = orc.static_et(BPLUT7, *flat)
+    got1 = MOD16._et(BPLUT7, *flat)
+    assert got1.shape == (T * N,)
+    parity.assert_parity(got1, ref1, np.float64, what='1-D')
+    # CUDA tensors in, CUDA tensor out, no host round trip
+    tdrv = [torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v
+            for v in [d[k] for k in NAMES]]
+    got2 = MOD16._et(BPLUT7, *tdrv)
+    assert isinstance(got2, torch.Tensor) and got2.is_cuda and got2.dtype == torch.float64
+    with np.errstate(all='ignore'):
+        ref2 = orc.static_et(BPLUT7, *[d[k] for k in NAMES])
+    parity.assert_parity(got2.cpu().numpy(), ref2, np.float64, what='cuda tensors')
+    # float32 inputs + python-float params => float32 compute, like numpy promotion
+    f32 = [v.astype(np.float32) if isinstance(v, np.ndarray) else v for v in [d[k] for k in NAMES]]
+    got3 = MOD16._et(BPLUT7, *f32)
+    assert got3.dtype == np.float32
+    parity.assert_parity(got3, orc.static_et(BPLUT7, *as_f64(f32)), np.float32, what='f32')
+    # non-contiguous (transposed) storage
+    tr = [np.asfortranarray(v) if isinstance(v, np.ndarray) and v.ndim == 2 else v
+          for v in [d[k] for k in NAMES]]
+    parity.assert_parity(MOD16._et(BPLUT7, *tr), ref2, np.float64, what='fortran order')
+
+
+def test_empty_and_ragged(cuda_lib):
+    d = synthetic.host_drivers(3, 0, 1)
+    got = MOD16._et(BPLUT7, *[d[k] for k in NAMES])
+    assert got.shape == (3, 0)
+    for N in (1, 3, 5, 127, 129):   # not multiples of the vector width
+        d = synthetic.host_drivers(2, N, N, dtype=np.float32)
+        drv = [d[k] for k in NAMES]
+        got = MOD16._et(BPLUT7, *drv, dtype=np.float32)
+        parity.assert_parity(got, orc.static_et(BPLUT7, *as_f64(drv)), np.float32,
+                             what='N=%d' % N)
+
+
+def test_r_corr_list(cuda_lib):
+    d = synthetic.host_drivers(4, 40, 11)
+    drv = [d[k] for k in NAMES]
+    rc = [orc.r_correction(d['pressure'], d['temp_day']) * 1.1,
+          orc.r_correction(d['pressure'], d['temp_night']) * 0.9]
+    with np.errstate(all='ignore'):
+        ref = orc.static_et(BPLUT7, *drv, r_corr_list=rc)
+    parity.assert_parity(MOD16._et(BPLUT7, *drv, r_corr_list=rc), ref, np.float64)
+    f32 = [v.astype(np.float32) if isinstance(v, np.ndarray) else v for v in drv]
+    rc32 = [r.astype(np.float32) for r in rc]
+    with np.errstate(all='ignore'):
+        ref32 = orc.static_et(BPLUT7, *as_f64(f32), r_corr_list=as_f64(rc32))
+    parity.assert_parity(MOD16._et(BPLUT7, *f32, r_corr_list=rc32), ref32, np.float32)
+
+
+def test_errors_are_loud(cuda_lib):
+    with pytest.raises(TypeError):
+        MOD16._et(BPLUT7[:5], *([1.0] * 14))
+    with pytest.raises(ValueError):
+        MOD16._et(BPLUT7, *([np.zeros((2, 3))] + [np.zeros((2, 4))] * 13))
+    with pytest.raises(_abi.Mod16Error):
+        _abi.load('/nonexistent/libmod16_b200.so')
