@@ -67,11 +67,11 @@ __device__ __forceinline__ Params<R> load_params(const ForwardArgs<R>& a, int64_
     int code = 0;
     if (a.par_mode == 1) {
       code = (int)__ldg(a.pft + n);
-      // numpy fancy indexing would raise on a code > 12; the kernel yields NaN parameters
-      if (code >= MOD16_N_PFT) code = 0;
     }
+    // numpy fancy indexing would raise on a code > 12; the kernels yield NaN parameters
 #pragma unroll
-    for (int k = 0; k < MOD16_N_PARAMS; ++k) v[k] = tab[k][code];
+    for (int k = 0; k < MOD16_N_PARAMS; ++k)
+      v[k] = code < MOD16_N_PFT ? tab[k][code] : __longlong_as_double(0x7ff8000000000000LL);
   }
   q.tmin_close = (R)v[0]; q.tmin_open = (R)v[1]; q.vpd_open = (R)v[2];
   q.vpd_close = (R)v[3];  q.gl_sh = (R)v[4];     q.gl_wv = (R)v[5];

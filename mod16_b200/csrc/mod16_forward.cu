@@ -242,8 +242,7 @@ int mod16_forward_f32(const mod16_drivers_t* drivers, const mod16_params_t* para
   int rc = mod16::build_forward_args<float>(drivers, params, out, T, N, flags, a);
   if (rc != MOD16_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool fast = !(flags & (MOD16_FORCE_GENERIC | MOD16_FORCE_MIRROR)) &&
-                    mod16::fast_f32_applicable(a, flags);
+  const bool fast = !(flags & MOD16_FORCE_MIRROR) && mod16::fast_f32_applicable(a, flags);
   return mod16::run_with_gate<float>(a, flags, st, [&](mod16::ForwardArgs<float>& x) {
     return fast ? mod16::launch_fast_f32(x, flags, st)
                 : mod16::launch_strided<float>(x, flags, st);

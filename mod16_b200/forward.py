@@ -145,7 +145,7 @@ def _view_2d(shape):
 
 def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static',
                 out_mode='sum', gate='global', dtype=None, r_corr_list=None, device=None,
-                stream=None, force=0, as_torch=None, gate_flag=None):
+                stream=None, force=0, as_torch=None, gate_flag=None, out=None):
     '''
     Launches K1 once.
 
@@ -155,6 +155,8 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     pft, table : uint8 land-cover code per pixel and the dense 11 x 13 BPLUT table
     out_mode : 'sum' | 'day_night' | 'components'
     gate     : 'global' (reference) | 'element' | 'open' | 'closed' | 'open_track' | 'fixup'
+
+    out      : optional list of preallocated CUDA tensors ((T, N), contiguous) to write into
 
     Returns a list of 1, 2 or 6 arrays of the broadcast shape (numpy, unless an input was
     a CUDA tensor or ``as_torch`` is set).
@@ -230,7 +232,16 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
         flags |= {'sum': _abi.OUT_SUM, 'day_night': _abi.OUT_DAY_NIGHT,
                   'components': _abi.OUT_COMPONENTS}[out_mode]
         flags |= _abi.GATE_FLAGS[gate] | force
-        outs = [torch.empty((T, N), device=dev, dtype=st.t_dtype) for _ in range(n_out)]
+        if out is not None:
+            outs = list(out)
+            if len(outs) != n_out or any(
+                    (not o.is_cuda) or o.dtype != st.t_dtype or o.numel() != T * N
+                    or not o.is_contiguous() for o in outs):
+                raise ValueError('`out` must be %d contiguous CUDA tensors of %d elements' % (
+                    n_out, T * N))
+            as_torch = True
+        else:
+            outs = [torch.empty((T, N), device=dev, dtype=st.t_dtype) for _ in range(n_out)]
         co = _abi.Out()
         for k, o in enumerate(outs):
             co.out[k] = o.data_ptr()

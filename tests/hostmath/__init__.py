@@ -54,8 +54,12 @@ def forward(params, drivers, semantics='static', gate='global', dtype=np.float64
     n = allv.shape[1]
     drv = np.ascontiguousarray(allv[:14])
     par = np.ascontiguousarray(allv[14:25])
+    if fast:
+        # the fast path receives the BPLUT columns in double, as the kernels do
+        par = np.ascontiguousarray(np.stack([
+            np.broadcast_to(np.asarray(p, np.float64), shape).ravel() for p in params]))
     rc = np.ascontiguousarray(allv[25:27]) if r_corr_list is not None else np.zeros((2, 1), dtype)
-    out = np.empty((6, n), dtype)
+    out = np.empty((9 if fast else 6, n), dtype)
     gpos = np.empty(n, np.uint8)
     sem = {'static': 0, 'instance': 1}[semantics]
     g = {'open': 0, 'global': 0, 'element': 1, 'closed': 2}[gate]
@@ -67,8 +71,12 @@ def forward(params, drivers, semantics='static', gate='global', dtype=np.float64
        par.ctypes.data_as(ctypes.c_void_p), rc.ctypes.data_as(ctypes.c_void_p),
        ctypes.c_int(1 if r_corr_list is not None else 0), ctypes.c_int64(n),
        out.ctypes.data_as(ctypes.c_void_p), gpos.ctypes.data_as(ctypes.c_void_p))
-    out = out.reshape((6,) + shape)
+    out = out.reshape((out.shape[0],) + shape)
     gpos = gpos.reshape(shape).astype(bool)
-    if semantics == 'static' and gate == 'global' and not gpos.any():
+    closed = semantics == 'static' and gate == 'global' and not gpos.any()
+    if closed:
         out[2] = 0  # the batch-global gate is closed (:343-348)
-    return dict(day=(out[0], out[1], out[2]), night=(out[3], out[4], out[5]), g_pos=gpos)
+    res = dict(day=(out[0], out[1], out[2]), night=(out[3], out[4], out[5]), g_pos=gpos)
+    if fast and not closed:
+        res.update(tot_day=out[6], tot_night=out[7], tot=out[8])
+    return res

@@ -40,7 +40,47 @@ static void run(int sem, int gate, const R* drv, const R* par, const R* rc, int 
   }
 }
 
+#ifdef HM_WITH_FAST
+static void run_fast(int sem, int gate, const float* drv, const double* par, const float* rc,
+                     int has_rc, int64_t n, float* out, uint8_t* gpos) {
+  for (int64_t i = 0; i < n; ++i) {
+    fast::StepIn in;
+    const float* c = drv;
+    in.lw_d = c[0 * n + i]; in.lw_n = c[1 * n + i]; in.sw_d = c[2 * n + i];
+    in.sw_n = c[3 * n + i]; in.alb = c[4 * n + i];  in.t_d = c[5 * n + i];
+    in.t_n = c[6 * n + i];  in.t_ann = c[7 * n + i]; in.tmin = c[8 * n + i];
+    in.vpd_d = c[9 * n + i]; in.vpd_n = c[10 * n + i]; in.p = c[11 * n + i];
+    in.fpar = c[12 * n + i]; in.lai = c[13 * n + i];
+    in.rc_d = has_rc ? rc[i] : 0.f;
+    in.rc_n = has_rc ? rc[n + i] : 0.f;
+    double col[11];
+    for (int k = 0; k < 11; ++k) col[k] = par[k * n + i];
+    fast::PftConst pc = fast::make_pft_const(col, sem);
+    fast::PixConst px = fast::make_pix_const(in.p, in.t_ann, pc, sem);
+    fast::StepOut r;
+    bool g;
+    auto colfn = [&](int k) { return col[k]; };
+    if (sem == SEM_STATIC)
+      fast::pixel_step_fast<SEM_STATIC>(in, pc, px, colfn, has_rc != 0, gate, r, g);
+    else
+      fast::pixel_step_fast<SEM_INSTANCE>(in, pc, px, colfn, has_rc != 0, gate, r, g);
+    out[0 * n + i] = r.day.canopy;   out[1 * n + i] = r.day.soil;
+    out[2 * n + i] = r.day.trans;    out[3 * n + i] = r.night.canopy;
+    out[4 * n + i] = r.night.soil;   out[5 * n + i] = r.night.trans;
+    out[6 * n + i] = r.tot_day;      out[7 * n + i] = r.tot_night;
+    out[8 * n + i] = r.tot;
+    gpos[i] = g ? 1 : 0;
+  }
+}
+#endif
+
 extern "C" {
+#ifdef HM_WITH_FAST
+void hm_fast_f32(int sem, int gate, const float* drv, const double* par, const float* rc,
+                 int has_rc, int64_t n, float* out, uint8_t* gpos) {
+  run_fast(sem, gate, drv, par, rc, has_rc, n, out, gpos);
+}
+#endif
 void hm_forward_f64(int sem, int gate, const double* drv, const double* par, const double* rc,
                     int has_rc, int64_t n, double* out, uint8_t* gpos) {
   run<double>(sem, gate, drv, par, rc, has_rc, n, out, gpos);

@@ -92,3 +92,91 @@ def test_mirror_r_corr_list():
     hd, hn = totals(r, 'static')
     parity.assert_parity(hd, od, np.float64, what='r_corr day')
     parity.assert_parity(hn, on, np.float64, what='r_corr night')
+
+
+# ---- float32 fast path (mod16_fast.cuh): algebra, guards and NaN masks ------------------
+# On the host the MUFU approximations are replaced by libm calls, so this checks the
+# rearranged formulas and the three guards; the approximations' accuracy is covered by the
+# GPU tests.
+
+def _table():
+    from mod16_b200 import utils
+    return utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51), orc.PARAM_ORDER,
+                             default_beta=250.0)
+
+
+@pytest.mark.parametrize('kind,nan', [('physical', 0.0), ('stress', 0.0),
+                                      ('physical', 0.003), ('stress', 0.003)])
+def test_fast_f32_matches_f64_oracle(kind, nan):
+    T, N = 40, 5000
+    d = synthetic.host_drivers(T, N, 321, kind=kind, dtype=np.float32, nan_frac=nan,
+                               fill_frac=nan)
+    drv = [d[k] for k in NAMES]
+    d64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
+    table = _table()
+    pft = synthetic.host_pft_map(N, 5)
+    vec = [table[i][pft].reshape(1, N) for i in range(11)]
+    with np.errstate(all='ignore'):
+        od, on = orc.static_evapotranspiration(vec, *d64)
+    r = hostmath.forward(vec, drv, 'static', 'global', dtype=np.float32, fast=True)
+    parity.assert_parity(r['tot_day'], od, np.float32, what='fast static day')
+    parity.assert_parity(r['tot_night'], on, np.float32, what='fast static night')
+    parity.assert_parity(r['tot'], od + on, np.float32, what='fast static sum')
+    col = list(table[:, 7])
+    with np.errstate(all='ignore'):
+        sep = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, col))).evapotranspiration(
+            *d64, separate=True)
+    r = hostmath.forward(col, drv, 'instance', dtype=np.float32, fast=True)
+    for h, hn_ in enumerate(('day', 'night')):
+        for c in range(3):
+            parity.assert_parity(r[hn_][c], sep[h][c], np.float32, parity.MASS_SCALE,
+                                 what='fast instance %s %d' % (hn_, c))
+
+
+def test_fast_f32_tables(golden_dir):
+    z = np.load(os.path.join(golden_dir, 'tables.npz'))
+    vec = list(z['params'])
+    drv = [z['drivers'][:, i].astype(np.float32) for i in range(14)]
+    d64 = [v.astype(np.float64) for v in drv]
+    with np.errstate(all='ignore'):
+        od, on = orc.static_evapotranspiration(vec, *d64, gate='element')
+        sep = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, vec))).evapotranspiration(
+            *d64, separate=True)
+    r = hostmath.forward(vec, drv, 'static', 'element', dtype=np.float32, fast=True)
+    parity.assert_parity(r['tot_day'], od, np.float32, what='fast table day')
+    parity.assert_parity(r['tot_night'], on, np.float32, what='fast table night')
+    r = hostmath.forward(vec, drv, 'instance', dtype=np.float32, fast=True)
+    for h, hn_ in enumerate(('day', 'night')):
+        for c in range(3):
+            parity.assert_parity(r[hn_][c], sep[h][c], np.float32, parity.MASS_SCALE,
+                                 what='fast table inst %s %d' % (hn_, c))
+
+
+def test_fast_f32_guards_near_thresholds():
+    'Elements placed within rounding of rh = 0.7, rh = 0+ and |G| = 0.39|A| (opposite sign).'
+    rng = np.random.default_rng(8)
+    n = 20000
+    t = rng.uniform(260, 305, n).astype(np.float32)
+    es = orc.svp(t.astype(np.float64))
+    rh_target = np.where(rng.random(n) < 0.5, 0.7, 0.0) + rng.normal(0, 2e-7, n)
+    rh_target[n // 2:] = np.abs(rng.normal(0, 5e-4, n - n // 2))
+    vpd = (es * (1 - rh_target)).astype(np.float32)
+    d = synthetic.host_drivers(1, n, 5, dtype=np.float32)
+    d['temp_day'] = t[None]
+    d['temp_night'] = (t - 6)[None]
+    d['vpd_day'] = vpd[None]
+    # soil heat flux switch: cold days with positive A so that G < 0 < 0.39 A, |G| ~ 0.39|A|
+    tc = d['temp_day'].astype(np.float64) - 273.15
+    g = 4.73 * tc - 20.87
+    a_needed = np.abs(g) / 0.39 * (1 + rng.normal(0, 1e-7, g.shape))
+    d['sw_rad_day'] = np.where(g < 0, (a_needed + 40) / (1 - d['sw_albedo'].astype(np.float64)),
+                               d['sw_rad_day']).astype(np.float32)
+    d['lw_net_day'] = np.where(g < 0, -40.0, d['lw_net_day']).astype(np.float32)
+    d['temp_annual'] = np.full(n, 285.0, np.float32)
+    drv = [d[k] for k in NAMES]
+    d64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
+    with np.errstate(all='ignore'):
+        od, on = orc.static_evapotranspiration(BPLUT7, *d64)
+    r = hostmath.forward(BPLUT7, drv, 'static', 'global', dtype=np.float32, fast=True)
+    parity.assert_parity(r['tot_day'], od, np.float32, what='guards day')
+    parity.assert_parity(r['tot_night'], on, np.float32, what='guards night')
