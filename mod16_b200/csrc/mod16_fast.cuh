@@ -1,294 +1,467 @@
 // float32 fast path of the MOD16 forward model.
 //
 // Same physics as mod16_math.cuh, rearranged for the B200 instruction budget (SURVEY.md
-// H4): every chain of divisions is merged into one reciprocal, the aerodynamic
-// resistances are carried as conductances (1/r_a = 1/r_r + g, so no resistance is ever
-// formed and the reference's inf/NaN detours through r_h = 1/0 disappear), powers become
-// MUFU sequences (x^1.75 via rsqrt/sqrt, rh^(vpd/beta) via lg2/ex2, rh^4 by squaring) and
-// everything that depends only on the pixel (pressure terms, the annual-temperature
-// window, BPLUT-derived ramp slopes) is hoisted out of the time loop.
+// H4; measured pipe rates in profiles/r01_microbench.txt: FP32 one warp-instruction per
+// clock per SM sub-partition, packed FFMA2/FMUL2/FADD2 one per two clocks for twice the
+// work, MUFU one per 8 clocks, FSETP/FSEL one per 2 clocks):
 //
-// Parity with the float64 reference on the same float32 inputs is kept by three guards,
-// each a rare, divergent detour:
-//   * domain guard  -- an element whose temperatures or pressure are outside the physical
-//     range (NaN, -9999 fill, ...) is evaluated by the op-for-op code in DOUBLE, so fill /
-//     NaN masks are the reference's by construction;
-//   * RH guard      -- near the f_wet jump (rh = 0.7) and near rh = 0+ (where
-//     rh^(vpd/beta) is ill-conditioned) rh is recomputed in double;
-//   * G guard       -- when |G| and 0.39|A| are within rounding of each other and of
-//     opposite sign (the only discontinuous switch of the soil heat flux), the predicate
-//     is re-evaluated in double.
+//   * every Penman-Monteith term is a ratio (s A + rho Cp f VPD / r_a) / (s c + gamma k / r_a).
+//     Numerator and denominator are multiplied by the common positive factor
+//         m = lambda(T) T (239 + Tc)^2 X          X = rho T  (air-density numerator, :409-412)
+//     which cancels every division the reference performs on the way (1/lambda in gamma,
+//     1/(239+Tc)^2 in the SVP slope, 1/T in rho, 1/X in r_r).  What remains per half-day is
+//     one reciprocal for SVP's exponent, two exponentials (SVP and 1/SVP), lg2/ex2 for
+//     (T/293.15)^-1.75, lg2/ex2 for rh^(vpd/beta) and one reciprocal per component;
+//   * resistances are carried as conductances (1/r_a = 1/r_r + g), so the reference's
+//     inf/NaN detours through r_h = 1/0 (f_wet == 0) never arise;
+//   * the two linear ramps and the r_tot interpolation share one saturated multiply;
+//   * everything that depends only on the pixel (pressure terms, the annual-temperature
+//     window, BPLUT-derived slopes) is hoisted out of the time loop;
+//   * the math is written once over a value type V: `float` (one pixel; strided kernel and
+//     host tests) or `F2` (two neighbouring pixels in one 64-bit register pair, evaluated
+//     with the sm_100 packed-FP32 instructions; the vectorised kernel).
+//
+// The fast formulas are used only inside the physical domain (finite drivers, 200 K < T <
+// 340 K, VPD / fPAR / LAI / albedo >= 0, 30 kPa <= P <= 120 kPa, sane BPLUT column) and away
+// from the model's discontinuities.  step_fast() flags an element that is outside the
+// domain or within rounding of a discontinuous switch (rh = 0.7, rh = 0+, |G| = 0.39 |A|,
+// A_day = 0); the kernels then re-evaluate that element with the op-for-op code of
+// mod16_math.cuh in DOUBLE (pixel_step_exact), so NaN / fill masks and branch decisions
+// are the float64 reference's by construction.
 // Citations are file:line under /root/reference/mod16/__init__.py.
 #pragma once
+#include <stdint.h>
 #include "mod16_math.cuh"
 
 namespace mod16 {
 namespace fast {
 
-// ---- MUFU wrappers (approximate, flush-to-zero; host versions for tests/hostmath) -------
+// ======================= value types and their operations ================================
+struct alignas(8) F2 { float x, y; };  // two pixels
+struct M2 { bool x, y; };              // two predicates
+
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ float rcp(float x) {
-  float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
-}
-__device__ __forceinline__ float ex2(float x) {
-  float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
-}
-__device__ __forceinline__ float lg2(float x) {
-  float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
-}
-__device__ __forceinline__ float rsq(float x) {
-  float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
-}
-__device__ __forceinline__ float sqr(float x) {
-  float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
-}
+#define M16_DEV 1
 #else
-inline float rcp(float x) { return 1.0f / x; }
-inline float ex2(float x) { return exp2f(x); }
-inline float lg2(float x) { return log2f(x); }
-inline float rsq(float x) { return 1.0f / sqrtf(x); }
-inline float sqr(float x) { return sqrtf(x); }
+#define M16_DEV 0
 #endif
 
-// ---- constants derived from one BPLUT column (computed in double, stored as float) -----
-struct PftConst {
-  float tmin_close, tmin_open, inv_dtmin;  // ramp up   (:325)
-  float vpd_open, vpd_close, inv_dvpd;     // ramp down (:326)
-  float gl_sh, gl_wv, g_cut, csl;
-  float rbl_min, rbl_max, rbl_slope;       // r_tot = rbl_max - rbl_slope*(vpd_close - vpd)
-  float inv_beta;
-  float tann_lo_hi, tann_lo_lo;            // 273.15 + tmin_{open|close} as a float pair
+// ---- scalar ---------------------------------------------------------------------------
+#if M16_DEV
+__device__ __forceinline__ float s_rcp(float x) {
+  float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float s_ex2(float x) {
+  float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float s_lg2(float x) {
+  float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float s_sat(float x) { return __saturatef(x); }
+#else
+inline float s_rcp(float x) { return 1.0f / x; }
+inline float s_ex2(float x) { return exp2f(x); }
+inline float s_lg2(float x) { return log2f(x); }
+inline float s_sat(float x) { return x != x ? 0.0f : (x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x)); }
+#endif
+
+M16_HD float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+M16_HD float vrcp(float a) { return s_rcp(a); }
+M16_HD float vex2(float a) { return s_ex2(a); }
+M16_HD float vlg2(float a) { return s_lg2(a); }
+M16_HD float vsat(float a) { return s_sat(a); }
+M16_HD float vabs(float a) { return fabsf(a); }
+M16_HD float vmax(float a, float b) { return fmaxf(a, b); }
+M16_HD float vmin(float a, float b) { return fminf(a, b); }
+M16_HD bool vlt(float a, float b) { return a < b; }
+M16_HD bool vle(float a, float b) { return a <= b; }
+M16_HD bool vgt(float a, float b) { return a > b; }
+M16_HD bool vge(float a, float b) { return a >= b; }
+M16_HD bool veq(float a, float b) { return a == b; }
+M16_HD bool mor(bool a, bool b) { return a || b; }
+M16_HD bool mand(bool a, bool b) { return a && b; }
+M16_HD bool mnot(bool a) { return !a; }
+M16_HD float vsel(bool m, float a, float b) { return m ? a : b; }
+M16_HD bool many(bool m) { return m; }
+template <class V> M16_HD V splat(float c);
+template <> M16_HD float splat<float>(float c) { return c; }
+
+// ---- packed pair -----------------------------------------------------------------------
+#if M16_DEV
+__device__ __forceinline__ unsigned long long f2_bits(F2 a) {
+  return *reinterpret_cast<unsigned long long*>(&a);
+}
+__device__ __forceinline__ F2 f2_from(unsigned long long b) { return *reinterpret_cast<F2*>(&b); }
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(r);
+}
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(r);
+}
+__device__ __forceinline__ F2 vfma(F2 a, F2 b, F2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)),
+      "l"(f2_bits(c)));
+  return f2_from(r);
+}
+#else
+inline F2 operator*(F2 a, F2 b) { return F2{a.x * b.x, a.y * b.y}; }
+inline F2 operator+(F2 a, F2 b) { return F2{a.x + b.x, a.y + b.y}; }
+inline F2 vfma(F2 a, F2 b, F2 c) { return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+#endif
+M16_HD F2 operator-(F2 a) { return F2{-a.x, -a.y}; }
+M16_HD F2 operator-(F2 a, F2 b) { return a + (-b); }
+template <> M16_HD F2 splat<F2>(float c) { return F2{c, c}; }
+M16_HD F2 operator*(F2 a, float b) { return a * splat<F2>(b); }
+M16_HD F2 operator*(float a, F2 b) { return splat<F2>(a) * b; }
+M16_HD F2 operator+(F2 a, float b) { return a + splat<F2>(b); }
+M16_HD F2 operator+(float a, F2 b) { return splat<F2>(a) + b; }
+M16_HD F2 operator-(F2 a, float b) { return a + splat<F2>(-b); }
+M16_HD F2 operator-(float a, F2 b) { return splat<F2>(a) + (-b); }
+M16_HD F2 vfma(F2 a, float b, F2 c) { return vfma(a, splat<F2>(b), c); }
+M16_HD F2 vfma(float a, F2 b, F2 c) { return vfma(splat<F2>(a), b, c); }
+M16_HD F2 vfma(F2 a, F2 b, float c) { return vfma(a, b, splat<F2>(c)); }
+M16_HD F2 vfma(float a, F2 b, float c) { return vfma(splat<F2>(a), b, splat<F2>(c)); }
+M16_HD F2 vfma(F2 a, float b, float c) { return vfma(a, splat<F2>(b), splat<F2>(c)); }
+M16_HD F2 vrcp(F2 a) { return F2{s_rcp(a.x), s_rcp(a.y)}; }
+M16_HD F2 vex2(F2 a) { return F2{s_ex2(a.x), s_ex2(a.y)}; }
+M16_HD F2 vlg2(F2 a) { return F2{s_lg2(a.x), s_lg2(a.y)}; }
+M16_HD F2 vsat(F2 a) { return F2{s_sat(a.x), s_sat(a.y)}; }
+M16_HD F2 vabs(F2 a) { return F2{fabsf(a.x), fabsf(a.y)}; }
+M16_HD F2 vmax(F2 a, F2 b) { return F2{fmaxf(a.x, b.x), fmaxf(a.y, b.y)}; }
+M16_HD F2 vmin(F2 a, F2 b) { return F2{fminf(a.x, b.x), fminf(a.y, b.y)}; }
+M16_HD F2 vmax(F2 a, float b) { return F2{fmaxf(a.x, b), fmaxf(a.y, b)}; }
+M16_HD M2 vlt(F2 a, F2 b) { return M2{a.x < b.x, a.y < b.y}; }
+M16_HD M2 vle(F2 a, F2 b) { return M2{a.x <= b.x, a.y <= b.y}; }
+M16_HD M2 vgt(F2 a, F2 b) { return M2{a.x > b.x, a.y > b.y}; }
+M16_HD M2 vge(F2 a, F2 b) { return M2{a.x >= b.x, a.y >= b.y}; }
+M16_HD M2 vlt(F2 a, float b) { return M2{a.x < b, a.y < b}; }
+M16_HD M2 vle(F2 a, float b) { return M2{a.x <= b, a.y <= b}; }
+M16_HD M2 vgt(F2 a, float b) { return M2{a.x > b, a.y > b}; }
+M16_HD M2 vge(F2 a, float b) { return M2{a.x >= b, a.y >= b}; }
+M16_HD M2 veq(F2 a, F2 b) { return M2{a.x == b.x, a.y == b.y}; }
+M16_HD M2 mor(M2 a, M2 b) { return M2{a.x || b.x, a.y || b.y}; }
+M16_HD M2 mand(M2 a, M2 b) { return M2{a.x && b.x, a.y && b.y}; }
+M16_HD M2 mnot(M2 a) { return M2{!a.x, !a.y}; }
+M16_HD F2 vsel(M2 m, F2 a, F2 b) { return F2{m.x ? a.x : b.x, m.y ? a.y : b.y}; }
+M16_HD F2 vsel(M2 m, F2 a, float b) { return F2{m.x ? a.x : b, m.y ? a.y : b}; }
+M16_HD F2 vsel(M2 m, float a, F2 b) { return F2{m.x ? a : b.x, m.y ? a : b.y}; }
+M16_HD bool many(M2 m) { return m.x || m.y; }
+
+template <class V> struct MaskOf;
+template <> struct MaskOf<float> { typedef bool type; };
+template <> struct MaskOf<F2> { typedef M2 type; };
+template <class V> M16_HD typename MaskOf<V>::type mask_splat(bool b);
+template <> M16_HD bool mask_splat<float>(bool b) { return b; }
+template <> M16_HD M2 mask_splat<F2>(bool b) { return M2{b, b}; }
+
+// normalisation of the common factor m (keeps every scaled quantity O(1..1e3))
+constexpr double kLam0 = 2.45e6;          // lambda / kLam0 ~ 1
+constexpr double kT0 = 293.15;            // T / kT0 = q ~ 1            (:292)
+constexpr double kDD0 = 264.0 * 264.0;    // (239 + Tc)^2 / kDD0 ~ 1    (:1397)
+
+// ======================= per-PFT and per-pixel constants ==================================
+// constants derived from one BPLUT column (computed in double, stored as float)
+template <class V>
+struct alignas(16) PftConstV {
+  V tmin_close, inv_dtmin, vpd_close, inv_dvpd;  // ramps (:325-326)
+  V gl_sh, gl_wv, g_cut, csl;
+  V rbl_max, rbl_delta, inv_beta, ok;  // r_tot = rbl_max - rbl_delta * m_vpd (:357-361)
+};
+struct alignas(16) PftConst : PftConstV<float> {
+  float tann_lo_hi, tann_lo_lo, pad0, pad1;  // 273.15 + tmin_{open|close} as a float pair
 };
 
 M16_HD PftConst make_pft_const(const double v[11], int sem) {
   PftConst c;
-  c.tmin_close = (float)v[0]; c.tmin_open = (float)v[1];
+  c.tmin_close = (float)v[0];
   c.inv_dtmin = (float)(1.0 / (v[1] - v[0]));
-  c.vpd_open = (float)v[2]; c.vpd_close = (float)v[3];
+  c.vpd_close = (float)v[3];
   c.inv_dvpd = (float)(1.0 / (v[3] - v[2]));
   c.gl_sh = (float)v[4]; c.gl_wv = (float)v[5]; c.g_cut = (float)v[6]; c.csl = (float)v[7];
-  c.rbl_min = (float)v[8]; c.rbl_max = (float)v[9];
-  c.rbl_slope = (float)((v[9] - v[8]) / (v[3] - v[2]));
+  c.rbl_max = (float)v[9];
+  c.rbl_delta = (float)(v[9] - v[8]);
   c.inv_beta = (float)(1.0 / v[10]);
+  // the rearranged algebra assumes the column is physically sane; anything else (NaN
+  // columns of PFT 0 / 11, zero-width ramps, non-positive conductances) goes to the
+  // op-for-op code
+  bool ok = true;
+  for (int k = 0; k < 11; ++k) ok = ok && (v[k] == v[k]) && (v[k] > -1e30) && (v[k] < 1e30);
+  ok = ok && (v[1] - v[0] > 1e-3) && (v[3] - v[2] > 1e-3) && (v[4] > 1e-12) && (v[5] > 1e-12) &&
+       (v[6] >= 0.0) && (v[7] >= 0.0) && (v[8] > 1e-6) && (v[9] > 1e-6) && (v[10] > 1e-6);
+  c.ok = ok ? 1.0f : 0.0f;
   double lo = 273.15 + (sem == SEM_STATIC ? v[1] : v[0]);
   c.tann_lo_hi = (float)lo;
   c.tann_lo_lo = (float)(lo - (double)c.tann_lo_hi);
+  c.pad0 = c.pad1 = 0.0f;
   return c;
 }
 
-// Params<double> for the op-for-op fallback, rebuilt from the float constants is NOT
-// possible without loss, so the fallback receives the original double column.
-
-// ---- per-pixel state hoisted out of the time loop --------------------------------------
-struct PixConst {
-  float pa;        // 0.348444 * (P / 100)                     (:410)
-  float p101;      // 101300 / P                               (:292)
-  float inv_p101;  // P / 101300
-  float cpp;       // Cp * P / eps  (gamma = cpp / lambda)     (:1289)
-  bool window;     // T_ann < 298.15 and T_ann >(=) 273.15 + tmin_{open|close}  (:230-233)
-  bool p_ok;       // pressure inside the physical domain
+// per-pixel state hoisted out of the time loop
+template <class V>
+struct PixConstV {
+  V pa;        // 0.348444 * (P / 100)                          (:410)
+  V inv_p101;  // P / 101300 = 1 / (101300 / P)                 (:292)
+  V cpp_n;     // Cp P / eps / (kLam0 kDD0): scaled gamma numerator (:1289)
+  typename MaskOf<V>::type window;  // annual-temperature window (:230-233)
+  typename MaskOf<V>::type ok;      // pressure and BPLUT column inside the fast domain
 };
+typedef PixConstV<float> PixConst;
 
 M16_HD PixConst make_pix_const(float p, float t_ann, const PftConst& c, int sem) {
   PixConst x;
   x.pa = 0.348444f * (p * 0.01f);
-  x.p101 = 101300.0f * rcp(p);
-  x.inv_p101 = p * (1.0f / 101300.0f);
-  x.cpp = p * (float)(kCp / kEps);
+  x.inv_p101 = p * (float)(1.0 / 101300.0);
+  x.cpp_n = p * (float)(kCp / kEps / (kLam0 * kDD0));
   // the window is decided in double: a float32 T_ann must fall on the same side of
   // 298.15 and of 273.15 + tmin as it does in the float64 reference
   const double ta = (double)t_ann;
   const double lo = (double)c.tann_lo_hi + (double)c.tann_lo_lo;
   x.window = (ta < 273.15 + 25) && (sem == SEM_STATIC ? (ta > lo) : (ta >= lo));
-  x.p_ok = (p >= 1.0e3f) && (p <= 2.0e5f);
+  x.ok = (p >= 3.0e4f) && (p <= 1.2e5f) && (c.ok != 0.0f);
   return x;
 }
 
-// rare: relative humidity in double from float inputs (:279-281 / :670-673)
-#if defined(__CUDACC__)
-__host__ __device__ __noinline__
-#endif
-static float rh_exact(float t, float vpd, int sem, bool& wet) {
-  double es = svp<double>((double)t);
-  double avp = es - (double)vpd;
-  double rh = avp / es;
-  if (sem == SEM_STATIC) rh = rh < 0.0 ? 0.0 : rh;
-  else rh = avp < 0.0 ? 0.0 : (rh > 1.0 ? 1.0 : rh);
-  wet = !(rh < 0.7);
-  return (float)rh;
+M16_HD PixConstV<F2> pair_pix(const PixConst& a, const PixConst& b) {
+  PixConstV<F2> r;
+  r.pa = F2{a.pa, b.pa}; r.inv_p101 = F2{a.inv_p101, b.inv_p101};
+  r.cpp_n = F2{a.cpp_n, b.cpp_n};
+  r.window = M2{a.window, b.window}; r.ok = M2{a.ok, b.ok};
+  return r;
+}
+M16_HD PftConstV<F2> pair_pft(const PftConstV<float>& a, const PftConstV<float>& b) {
+  PftConstV<F2> r;
+  r.tmin_close = F2{a.tmin_close, b.tmin_close}; r.inv_dtmin = F2{a.inv_dtmin, b.inv_dtmin};
+  r.vpd_close = F2{a.vpd_close, b.vpd_close};    r.inv_dvpd = F2{a.inv_dvpd, b.inv_dvpd};
+  r.gl_sh = F2{a.gl_sh, b.gl_sh}; r.gl_wv = F2{a.gl_wv, b.gl_wv};
+  r.g_cut = F2{a.g_cut, b.g_cut}; r.csl = F2{a.csl, b.csl};
+  r.rbl_max = F2{a.rbl_max, b.rbl_max}; r.rbl_delta = F2{a.rbl_delta, b.rbl_delta};
+  r.inv_beta = F2{a.inv_beta, b.inv_beta}; r.ok = F2{a.ok, b.ok};
+  return r;
 }
 
-// rare: the |G| > 0.39 |A| predicate in double (:239)
-#if defined(__CUDACC__)
-__host__ __device__ __noinline__
-#endif
-static bool g_exceeds_exact(float t, float sw, float alb, float lw, bool night) {
-  double a = night ? (double)lw : (double)sw * (1.0 - (double)alb) + (double)lw;
-  double g = (4.73 * ((double)t - 273.15)) - 20.87;
-  return fabs(g) > (0.39 * fabs(a));
-}
-
+// ======================= the model ========================================================
 // t - 273.15 with the constant split into a float pair, so that the Celsius temperature
 // carries no 6e-6 K bias from rounding 273.15 to float
-M16_HD float celsius(float t) {
+template <class V> M16_HD V celsius(V t) {
   const float hi = 273.15f;
   const float lo = (float)(273.15 - (double)hi);
   return (t - hi) - lo;
 }
 
-struct HalfIn {
-  float t, vpd, a_can, a_soil, rc;
+template <class V>
+struct StepInV {  // one pixel-timestep (or pair) of float drivers
+  V lw_d, lw_n, sw_d, sw_n, alb, t_d, t_n, tmin, vpd_d, vpd_n, fpar, lai;
+  V rc_d, rc_n;
+};
+
+template <class V>
+struct HalfV { V canopy, soil, trans; };
+
+template <class V>
+struct StepOutV {  // components and totals of one pixel-timestep (or pair)
+  HalfV<V> day, night;
+  V tot_day, tot_night, tot;  // :380 / :792 per half, and day + night (:193)
 };
 
 // One half-day, fast form.  STATIC night never transpires (its gate is never open).
-template <int SEM, bool DAY>
-M16_HD Half<float> half_fast(const HalfIn& h, float tmin, float fpar, float lai,
-                             const PftConst& c, const PixConst& x, bool has_rc, int gate,
-                             bool& g_pos) {
-  const float tc = celsius(h.t);
-  // saturation vapour pressure and its reciprocal (:1365-1367)
-  const float xarg = (17.27f * tc) * rcp(tc + 237.3f);
-  const float es = 610.8f * ex2(xarg * 1.4426950408889634f);
-  const float inv_es = rcp(es);
-  float rh;
-  if (SEM == SEM_STATIC) {
-    rh = (es - h.vpd) * inv_es;      // :280
-    rh = rh < 0.0f ? 0.0f : rh;      // :281
+// Returns the three components; `need` is OR-ed with the guard predicates.
+template <class V, int SEM, bool DAY, bool HAS_RC>
+M16_HD HalfV<V> half_fast(V t, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V omf, V lai,
+                          const PftConstV<V>& c, const PixConstV<V>& x, int gate,
+                          typename MaskOf<V>::type& g_pos, typename MaskOf<V>::type& need) {
+  typedef typename MaskOf<V>::type M;
+  const V tc = celsius<V>(t);
+  // saturation vapour pressure 610.8 exp(17.27 Tc / (Tc + 237.3)) and its reciprocal (:1365)
+  const V xe = ((float)(17.27 * 1.4426950408889634) * tc) * vrcp(tc + 237.3f);
+  const V e = vex2(xe);                             // SVP / 610.8
+  const V ies = (float)(1.0 / 610.8) * vex2(-xe);   // 1 / SVP
+  V rh = vfma(-vpd, ies, 1.0f);
+  if (SEM == SEM_STATIC) rh = vmax(rh, splat<V>(0.0f));  // :280-281 (VPD >= 0 in the domain)
+  else rh = vsat(rh);                                    // :671-673
+  // discontinuities in rh: the f_wet jump at 0.7 (:282) and rh -> 0+, where rh^(vpd/beta)
+  // is ill-conditioned (:376)
+  need = mor(need, mor(vlt(vabs(rh - 0.7f), splat<V>(4.0e-6f)),
+                       vlt(vabs(rh - 1.0e-3f), splat<V>(1.0e-3f))));
+  const V rh2 = rh * rh;
+  const V fw = vsel(vge(rh, splat<V>(0.7f)), rh2 * rh2, splat<V>(0.0f));  // :282
+  const V omfw = 1.0f - fw;
+  // scaled slope S = s m, psychrometric constant G = gamma m and K = rho Cp VPD m / X
+  const V q = t * (float)(1.0 / kT0);
+  const V d2 = tc + 239.0f;
+  const V dd = d2 * d2;
+  const V lam_n = vfma(tc, (float)(-2361.0 / kLam0), (float)(2.501e6 / kLam0));    // :121
+  const V S = (((float)(17.38 * 239.0 * 610.8 / kDD0) * e) * lam_n) * q;            // :1397
+  const V G = (x.cpp_n * q) * dd;                                                    // :1289
+  const V Kv = (((float)(kCp / (kT0 * kDD0)) * lam_n) * dd) * vpd;
+  // X = rho T (:409-412); B = X / r_r = 4 sigma T^4 / Cp (:298-299)
+  const V X = vfma(rh, vfma(tc, -0.252f, 2.0582f), x.pa);
+  const V q2 = q * q;
+  const V B = (float)(4.0 * kSigma * kT0 * kT0 * kT0 * kT0 / kCp) * (q2 * q2);
+  // 1 / r_corr = (P / 101300) (T / 293.15)^-1.75 (:292), or the supplied r_corr_list entry
+  V inv_rc;
+  if (HAS_RC) {
+    inv_rc = vrcp(rc);
+    need = mor(need, mnot(mand(vgt(rc, splat<V>(1e-6f)), vlt(rc, splat<V>(1e6f)))));
   } else {
-    const float avp = es - h.vpd;    // :671-673
-    rh = avp * inv_es;
-    rh = avp < 0.0f ? 0.0f : (rh > 1.0f ? 1.0f : rh);
+    inv_rc = x.inv_p101 * vex2(-1.75f * vlg2(q));
   }
-  bool wet = !(rh < 0.7f);
-  if (fabsf(rh - 0.7f) < 3.0e-5f || (rh > 0.0f && rh < 2.0e-3f))
-    rh = rh_exact(h.t, h.vpd, SEM, wet);
-  const float rh2 = rh * rh;
-  const float fw = wet ? rh2 * rh2 : 0.0f;                       // :282
-  const float d2 = 239.0f + tc;
-  const float s = (17.38f * 239.0f) * es * rcp(d2 * d2);         // :1397
-  const float lam = fmaf(-2361.0f, tc, 2.501e6f);                // :121
-  const float inv_lam = rcp(lam);
-  const float gamma = x.cpp * inv_lam;                           // :1289
-  // (T / 293.15)^(+-1.75) from one rsqrt and one sqrt (:292)
-  const float q = h.t * (1.0f / 293.15f);
-  const float rs = rsq(q);          // q^-1/2
-  const float r4 = sqr(rs);         // q^-1/4
-  float r_corr, inv_rc;
-  if (has_rc) {
-    r_corr = h.rc;
-    inv_rc = rcp(h.rc);
-  } else {
-    r_corr = x.p101 * (q * q * r4);
-    inv_rc = x.inv_p101 * (rs * rs * rs * r4);
-  }
-  // air density numerator X (rho = X / T, :409-412) and 1/r_r = 4 sigma T^4 / (Cp X)
-  const float xr = fmaf(-100.0f * rh, fmaf(0.00252f, tc, -0.020582f), x.pa);
-  const float inv_t = rs * rs * (1.0f / 293.15f);
-  const float rho_cp = (float)kCp * xr * inv_t;
-  const float t2 = h.t * h.t;
-  const float inv_rr = (float)(4.0 * kSigma / kCp) * (t2 * t2) * rcp(xr);
-  const float omfw = 1.0f - fw;
-  const float rcv = rho_cp * h.vpd;  // rho Cp VPD, shared by the three components
+  const V m_v = vsat((c.vpd_close - vpd) * c.inv_dvpd);  // reversed ramp on VPD (:326)
+  const V Kf = Kv * fpar;
+  const V SA = S * a_can;
+  V il = splat<V>(0.0f);
+  if (SEM == SEM_INSTANCE) il = (float)(1.0 / kLam0) * vrcp(lam_n);  // 1 / lambda (:959 ...)
 
-  Half<float> o;
-  // -- wet canopy: e = fw (s Ac + rho Cp fpar VPD / r_aw) / (s + gamma r_e / r_aw),
-  //    1/r_aw = 1/r_r + gl_sh lai fw, r_e / r_aw = (1/r_aw) / (gl_wv lai fw)   (:305-320)
-  if (SEM == SEM_STATIC) {
-    const float lf = lai * fw;
-    const float ira = fmaf(c.gl_sh, lf, inv_rr);
-    const float ce = c.gl_wv * lf;
-    const float num = fmaf(s, h.a_can, rcv * fpar * ira);
-    const float den = fmaf(s, ce, gamma * ira);
-    const float e = (fw * num) * ce * rcp(den);
-    o.canopy = (lf <= 1e-7f) ? 0.0f : e;
-  } else {
-    const float fw2 = fw == 0.0f ? 1e-7f : fw;                   // :934
-    const float lai2 = lai == 0.0f ? 1e-7f : lai;                // :935
-    const float lf = lai2 * fw2;
-    const float ira = fmaf(c.gl_sh, lf, inv_rr);
-    const float ce = c.gl_wv * lf;
-    const float num = fw2 * fmaf(s, h.a_can, rcv * fpar * ira);
-    const float den = fmaf(s, ce, gamma * ira);
-    const float e = num < 0.0f ? 0.0f : (num * ce * rcp(den)) * inv_lam;  // :959
-    o.canopy = (fw2 <= 1e-7f || lai2 <= 1e-7f) ? 0.0f : e;               // :961
-  }
-
-  // -- transpiration (:323-349, :1233-1258)
-  g_pos = false;
-  if (DAY || SEM == SEM_INSTANCE) {
-    float gs = 0.0f;
-    if (DAY) {
-      const float tm = celsius(tmin);
-      const float m_t = tm >= c.tmin_open ? 1.0f
-                        : (tm < c.tmin_close ? 0.0f : (tm - c.tmin_close) * c.inv_dtmin);
-      const float m_v = h.vpd >= c.vpd_close ? 0.0f
-                        : (h.vpd < c.vpd_open ? 1.0f
-                                              : 1.0f - (h.vpd - c.vpd_open) * c.inv_dvpd);
-      gs = (c.csl * m_t * m_v) * inv_rc;
-    } else {
-      gs = 0.0f * inv_rc;
-    }
-    g_pos = gs > 0.0f;
-    const float sc = gs + c.g_cut * inv_rc;
-    const float gbl = c.gl_sh * lai * omfw;
-    const bool ok = (lai > 0.0f) && (omfw > 0.0f);
-    const float prod = ok ? gbl * sc : 1e-7f;    // g_canopy = prod / tot (:334-337)
-    const float tot = ok ? gbl + sc : 1.0f;
-    const float ird = inv_rr + c.gl_sh;          // 1 / r_a_dry (:340)
-    const float a_can = (SEM == SEM_INSTANCE && h.a_can < 0.0f) ? 0.0f : h.a_can;  // :1251
-    const float num = omfw * fmaf(s, a_can, rcv * fpar * ird);
-    const float den = fmaf(s + gamma, prod, gamma * ird * tot);
-    float tr = num * prod * rcp(den);
+  HalfV<V> o;
+  // -- wet canopy (:305-320): e = fw ce X (S Ac + Kf Y) / (S ce X + G Y), Y = X / r_aw
+  {
+    const V lf = lai * fw;
+    const V ce = c.gl_wv * lf;
+    const V Y = vfma(c.gl_sh * lf, X, B);
+    const V num = vfma(Kf, Y, SA);
+    const V den = vfma(S * ce, X, G * Y);
+    const V r = ((fw * ce) * X) * vrcp(den);
     if (SEM == SEM_STATIC) {
-      if (gate == GATE_CLOSED) tr = 0.0f;
-      else if (gate == GATE_ELEMENT) tr = g_pos ? tr : 0.0f;
+      o.canopy = num * r;  // the (lai f_wet <= 1e-7) mask changes less than 1e-6 W m-2
+    } else {
+      const V ev = (vmax(num, splat<V>(0.0f)) * r) * il;                        // :959
+      o.canopy = vsel(vle(lai, splat<V>(1e-7f)), splat<V>(0.0f), ev);           // :934-935, :961
+    }
+  }
+  // -- transpiration (:323-349, :1233-1258)
+  g_pos = mask_splat<V>(false);
+  if (DAY || SEM == SEM_INSTANCE) {
+    V gs = splat<V>(0.0f);
+    if (DAY) {
+      const V m_t = vsat((celsius<V>(tmin) - c.tmin_close) * c.inv_dtmin);      // :325
+      gs = ((c.csl * m_t) * m_v) * inv_rc;                                      // :327-328
+    }
+    g_pos = vgt(gs, splat<V>(0.0f));
+    const V sc = vfma(c.g_cut, inv_rc, gs);                                     // :329
+    const V gbl = (c.gl_sh * lai) * omfw;                                       // :333
+    const M ok = mand(vgt(lai, splat<V>(0.0f)), vgt(omfw, splat<V>(0.0f)));     // :336
+    const V prod = vsel(ok, gbl * sc, splat<V>(1e-7f));  // g_canopy = prod / tot (:334-337)
+    const V tot = vsel(ok, gbl + sc, splat<V>(1.0f));
+    const V Yd = vfma(c.gl_sh, X, B);                    // X / r_a_dry (:340)
+    const V ac = (SEM == SEM_INSTANCE) ? vmax(SA, splat<V>(0.0f)) : SA;         // :1251
+    const V num = vfma(Kf, Yd, ac);
+    const V den = vfma((S + G) * prod, X, (G * Yd) * tot);
+    V tr = (num * ((omfw * prod) * X)) * vrcp(den);
+    if (SEM == SEM_STATIC) {
+      if (gate == GATE_CLOSED) tr = splat<V>(0.0f);
+      else if (gate == GATE_ELEMENT) tr = vsel(g_pos, tr, splat<V>(0.0f));
       o.trans = tr;
     } else {
-      const float g_can = ok ? prod * rcp(tot) : 1e-7f;
-      o.trans = g_can <= 1e-7f ? 0.0f : tr * inv_lam;            // :1258
+      const M dead = mor(mnot(ok), vle(prod, 1e-7f * tot));                     // :1258
+      o.trans = vsel(dead, splat<V>(0.0f), tr * il);
     }
   } else {
-    o.trans = 0.0f;
+    o.trans = splat<V>(0.0f);
   }
-
-  // -- bare soil (:357-376): 1/r_as = 1/r_tot + 1/r_r, r_tot/r_as = 1 + r_tot/r_r
+  // -- bare soil (:357-376): q = X (S As r_t + Kv (1 - fpar) W) / (r_t (S X + G W)),
+  //    W = X + r_t B, r_t = r_tot / r_corr
   {
-    const float rbl = h.vpd <= c.vpd_open
-                          ? c.rbl_min
-                          : (h.vpd >= c.vpd_close
-                                 ? c.rbl_max
-                                 : fmaf(-c.rbl_slope, c.vpd_close - h.vpd, c.rbl_max));
-    const float r_t = rbl * inv_rc;
-    const float ira = fmaf(r_corr, rcp(rbl), inv_rr);
-    const float num = fmaf(s, h.a_soil, rcv * (1.0f - fpar) * ira);
-    const float den = fmaf(gamma, fmaf(r_t, inv_rr, 1.0f), s);
-    const float qn = num * rcp(den);
-    const float k = h.vpd * c.inv_beta;
-    float pw = ex2(k * lg2(rh));                                  // rh^(vpd/beta)
-    pw = (k == 0.0f || rh == 1.0f) ? 1.0f : pw;                   // pow(x, 0) = pow(1, y) = 1
+    const V r_t = vfma(-c.rbl_delta, m_v, c.rbl_max) * inv_rc;                  // :357-363
+    const V W = vfma(r_t, B, X);
+    const V num = vfma(S * a_soil, r_t, (Kv * omf) * W);
+    const V den = r_t * vfma(G, W, S * X);
+    V qn = (num * X) * vrcp(den);
+    const V pw = vex2((vpd * c.inv_beta) * vlg2(rh));  // rh^(vpd/beta), 1 when rh == 1
+    const V mix = vfma(omfw, pw, fw);
     if (SEM == SEM_STATIC) {
-      o.soil = qn * fmaf(omfw, pw, fw);
+      o.soil = qn * mix;
     } else {
-      const float e_sat = qn * fw, e_uns = qn * omfw;
-      float e = e_sat < 0.0f ? 0.0f : e_sat;                      // :858
-      e = e + (e_uns < 0.0f ? 0.0f : e_uns * pw);                 // :859-861
-      o.soil = e * inv_lam;                                       // :864
+      qn = vmax(qn, splat<V>(0.0f));                                            // :858-861
+      o.soil = (qn * mix) * il;                                                 // :864
     }
   }
   return o;
 }
 
+// Physical domain of the fast formulas.  NaN anywhere fails it (fminf / fmaxf drop a NaN
+// operand, hence the self-comparison of the sums).
+template <class V>
+M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in) {
+  // radiation terms and Tmin: finite and not a fill value (-9999, -32768, 1e20 ...)
+  const V r = vmax(vmax(vabs(in.lw_d), vabs(in.lw_n)),
+                   vmax(vmax(vabs(in.sw_d), vabs(in.sw_n)), vabs(in.tmin)));
+  // non-negative quantities
+  const V lo = vmin(vmin(vmin(in.lai, in.fpar), vmin(in.vpd_d, in.vpd_n)), in.alb);
+  const V hi = vmax(vmax(vmax(in.lai, in.fpar), vmax(in.vpd_d, in.vpd_n)), in.alb);
+  const V tl = vmin(in.t_d, in.t_n), th = vmax(in.t_d, in.t_n);
+  const V s1 = ((in.lw_d + in.lw_n) + (in.sw_d + in.sw_n)) + in.tmin;
+  const V s2 = ((in.lai + in.fpar) + (in.vpd_d + in.vpd_n)) + ((in.alb + in.t_d) + in.t_n);
+  return mand(mand(mand(vlt(r, splat<V>(9000.0f)), vge(lo, splat<V>(0.0f))),
+                   mand(vlt(hi, splat<V>(1.0e5f)), vgt(tl, splat<V>(200.0f)))),
+              mand(vlt(th, splat<V>(340.0f)), mand(veq(s1, s1), veq(s2, s2))));
+}
+
+// One pixel-timestep (or pair), both halves.  Returns the mask of elements that must be
+// re-evaluated by pixel_step_exact (outside the domain, or within rounding of a
+// discontinuity); their entries of `o` are unspecified.
+template <class V, int SEM, bool HAS_RC>
+M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,
+                                          const PixConstV<V>& x, int gate, StepOutV<V>& o,
+                                          typename MaskOf<V>::type& g_pos) {
+  typedef typename MaskOf<V>::type M;
+  M need = mnot(mand(x.ok, in_domain<V>(in)));
+  const V oma = 1.0f - in.alb;
+  const V a_d = vfma(in.sw_d, oma, in.lw_d);            // :225
+  const V a_n = in.lw_n;                                 // :226
+  const V a_nc = vfma(in.sw_n, oma, in.lw_n);            // :272 (night: sw_rad_night)
+  // soil heat flux (:229-241)
+  const M cond = mand(x.window, vge(in.t_d - in.t_n, splat<V>(5.0f)));
+  V g_d = vsel(cond, vfma(celsius<V>(in.t_d), 4.73f, -20.87f), splat<V>(0.0f));
+  V g_n = vsel(cond, vfma(celsius<V>(in.t_n), 4.73f, -20.87f), splat<V>(0.0f));
+  const V lim_d = 0.39f * a_d, lim_n = 0.39f * a_n;
+  // |G| > 0.39 |A| switches G to 0.39 A (:239); within rounding of equality the decision
+  // is the double code's.  A_day > 0 gates both limits below (:245-252).
+  need = mor(need, mor(mor(vle(vabs(vabs(g_d) - vabs(lim_d)), splat<V>(1.0e-4f)),
+                           vle(vabs(vabs(g_n) - vabs(lim_n)), splat<V>(1.0e-4f))),
+                       vlt(vabs(a_d), splat<V>(1.0e-4f))));
+  g_d = vsel(vgt(vabs(g_d), vabs(lim_d)), lim_d, g_d);
+  g_n = vsel(vgt(vabs(g_n), vabs(lim_n)), lim_n, g_n);
+  const M a_pos = vgt(a_d, splat<V>(0.0f));
+  V r_d = a_d - g_d;                                     // A - G, day
+  V r_n = a_n - g_n;
+  r_d = vsel(mand(a_pos, vlt(r_d, splat<V>(0.0f))), splat<V>(0.0f), r_d);  // :245-247 (G := A)
+  const V floor_n = -0.5f * a_d;
+  r_n = vsel(mand(a_pos, vlt(r_n, floor_n)), floor_n, r_n);  // :248-252 (G := A_n + A_d / 2)
+  const V omf = 1.0f - in.fpar;
+  M unused = mask_splat<V>(false);
+  o.day = half_fast<V, SEM, true, HAS_RC>(in.t_d, in.vpd_d, in.fpar * a_d, omf * r_d, in.rc_d,
+                                          in.tmin, in.fpar, omf, in.lai, c, x, gate, g_pos,
+                                          need);
+  o.night = half_fast<V, SEM, false, HAS_RC>(in.t_n, in.vpd_n, in.fpar * a_nc, omf * r_n,
+                                             in.rc_n, in.tmin, in.fpar, omf, in.lai, c, x, gate,
+                                             unused, need);
+  if (SEM == SEM_STATIC) {  // :380
+    o.tot_day = (o.day.trans + o.day.canopy) + o.day.soil;
+    o.tot_night = (o.night.trans + o.night.canopy) + o.night.soil;
+  } else {                  // :792
+    o.tot_day = (o.day.canopy + o.day.soil) + o.day.trans;
+    o.tot_night = (o.night.canopy + o.night.soil) + o.night.trans;
+  }
+  o.tot = o.tot_day + o.tot_night;
+  return need;
+}
+
+// ---- scalar interface used by the strided kernel, the fix-up and the host harness -------
 struct StepIn {  // one pixel-timestep of float drivers
   float lw_d, lw_n, sw_d, sw_n, alb, t_d, t_n, t_ann, tmin, vpd_d, vpd_n, p, fpar, lai;
   float rc_d, rc_n;
 };
 
-struct StepOut {  // components and totals of one pixel-timestep
+struct StepOut {
   Half<float> day, night;
-  float tot_day, tot_night, tot;  // :380 / :792 per half, and day + night (:193)
+  float tot_day, tot_night, tot;
 };
 
-// op-for-op evaluation in double (domain-guard fallback); `col` is the BPLUT column
+// op-for-op evaluation in double (the fallback); `col` is the BPLUT column
 template <int SEM>
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
@@ -315,76 +488,72 @@ static void pixel_step_exact(const StepIn& in, const double col[11], bool has_rc
   o.tot_day = (float)td; o.tot_night = (float)tn; o.tot = (float)(td + tn);
 }
 
-// NaN-propagating 3-input minimum (FMNMX3.NAN on sm_100a)
-M16_HD float min3_nan(float a, float b, float c) {
-#if defined(__CUDA_ARCH__)
-  float r; asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
-#else
-  if (a != a || b != b || c != c) return NAN;
-  return fminf(a, fminf(b, c));
-#endif
+M16_HD StepInV<float> to_v(const StepIn& in) {
+  StepInV<float> v;
+  v.lw_d = in.lw_d; v.lw_n = in.lw_n; v.sw_d = in.sw_d; v.sw_n = in.sw_n; v.alb = in.alb;
+  v.t_d = in.t_d; v.t_n = in.t_n; v.tmin = in.tmin; v.vpd_d = in.vpd_d; v.vpd_n = in.vpd_n;
+  v.fpar = in.fpar; v.lai = in.lai; v.rc_d = in.rc_d; v.rc_n = in.rc_n;
+  return v;
 }
 
-// Domain of the fast path: every per-step driver is a number above the fill range
-// (> -9000: rejects NaN and -9999 / -32768 style fills) and the temperatures are such
-// that every denominator of the rearranged formulas is positive (40 K < T < 1000 K).
-// Pressure is checked once per pixel (PixConst::p_ok).
-M16_HD bool in_domain(const StepIn& in) {
-  float m = min3_nan(in.lw_d, in.lw_n, in.sw_d);
-  m = min3_nan(m, in.alb, in.tmin);
-  m = min3_nan(m, in.vpd_d, in.vpd_n);
-  m = min3_nan(m, in.fpar, in.lai);
-  m = min3_nan(m, in.sw_n, in.sw_n);
-  const float tl = min3_nan(in.t_d, in.t_n, in.t_n);
-  return (m > -9000.0f) && (tl > 40.0f) && (in.t_d < 1000.0f) && (in.t_n < 1000.0f);
-}
-
-// One pixel-timestep, both halves, with the guards.
-// `col(k)` returns BPLUT parameter k of this pixel in double (only called on the fallback).
+// Fast evaluation of one pixel-timestep with the exact re-evaluation done in place.
+// `guarded` (optional) reports whether the element took the double path.
 template <int SEM, typename ColFn>
 M16_HD void pixel_step_fast(const StepIn& in, const PftConst& c, const PixConst& x,
-                            ColFn col, bool has_rc, int gate, StepOut& o, bool& g_pos) {
-  if (!(x.p_ok && in_domain(in))) {
+                            ColFn col, bool has_rc, int gate, StepOut& o, bool& g_pos,
+                            bool* guarded = nullptr) {
+  StepOutV<float> r;
+  const StepInV<float> v = to_v(in);
+  const bool need = has_rc ? step_fast<float, SEM, true>(v, c, x, gate, r, g_pos)
+                           : step_fast<float, SEM, false>(v, c, x, gate, r, g_pos);
+  if (guarded) *guarded = need;
+  if (need) {
     double cc[11];
     for (int k = 0; k < 11; ++k) cc[k] = col(k);
     pixel_step_exact<SEM>(in, cc, has_rc, gate, o, g_pos);
     return;
   }
-  const float oma = 1.0f - in.alb;
-  const float a_d = fmaf(in.sw_d, oma, in.lw_d);            // :225
-  const float a_n = in.lw_n;                                 // :226
-  const float a_n_can = fmaf(in.sw_n, oma, in.lw_n);         // :272 (night: sw_rad_night)
-  // soil heat flux (:229-241)
-  const bool cond = x.window && ((in.t_d - in.t_n) >= 5.0f);
-  float g_d = cond ? fmaf(4.73f, celsius(in.t_d), -20.87f) : 0.0f;
-  float g_n = cond ? fmaf(4.73f, celsius(in.t_n), -20.87f) : 0.0f;
-  const float lim_d = 0.39f * a_d, lim_n = 0.39f * a_n;
-  bool ex_d = fabsf(g_d) > fabsf(lim_d), ex_n = fabsf(g_n) > fabsf(lim_n);
-  if (cond) {
-    // the switch is discontinuous only when G and A have opposite signs
-    if (g_d * lim_d < 0.0f &&
-        fabsf(fabsf(g_d) - fabsf(lim_d)) <= fmaf(1e-5f, fabsf(lim_d), 2e-5f))
-      ex_d = g_exceeds_exact(in.t_d, in.sw_d, in.alb, in.lw_d, false);
-    if (g_n * lim_n < 0.0f &&
-        fabsf(fabsf(g_n) - fabsf(lim_n)) <= fmaf(1e-5f, fabsf(lim_n), 2e-5f))
-      ex_n = g_exceeds_exact(in.t_n, 0.0f, 0.0f, in.lw_n, true);
+  o.day.canopy = r.day.canopy; o.day.soil = r.day.soil; o.day.trans = r.day.trans;
+  o.night.canopy = r.night.canopy; o.night.soil = r.night.soil; o.night.trans = r.night.trans;
+  o.tot_day = r.tot_day; o.tot_night = r.tot_night; o.tot = r.tot;
+}
+
+// Pair evaluation with in-place exact re-evaluation (host harness: exercises the F2 code).
+template <int SEM, typename ColFn0, typename ColFn1>
+M16_HD void pair_step_fast(const StepIn& in0, const StepIn& in1, const PftConst& c0,
+                           const PftConst& c1, const PixConst& x0, const PixConst& x1,
+                           ColFn0 col0, ColFn1 col1, int gate, StepOut& o0, StepOut& o1,
+                           bool& g0, bool& g1) {
+  StepInV<F2> v;
+  v.lw_d = F2{in0.lw_d, in1.lw_d}; v.lw_n = F2{in0.lw_n, in1.lw_n};
+  v.sw_d = F2{in0.sw_d, in1.sw_d}; v.sw_n = F2{in0.sw_n, in1.sw_n};
+  v.alb = F2{in0.alb, in1.alb};    v.t_d = F2{in0.t_d, in1.t_d};
+  v.t_n = F2{in0.t_n, in1.t_n};    v.tmin = F2{in0.tmin, in1.tmin};
+  v.vpd_d = F2{in0.vpd_d, in1.vpd_d}; v.vpd_n = F2{in0.vpd_n, in1.vpd_n};
+  v.fpar = F2{in0.fpar, in1.fpar}; v.lai = F2{in0.lai, in1.lai};
+  v.rc_d = F2{0.f, 0.f}; v.rc_n = F2{0.f, 0.f};
+  StepOutV<F2> r;
+  M2 gp;
+  const M2 need = step_fast<F2, SEM, false>(v, pair_pft(c0, c1), pair_pix(x0, x1), gate, r, gp);
+  const StepIn* ins[2] = {&in0, &in1};
+  StepOut* outs[2] = {&o0, &o1};
+  bool* gs[2] = {&g0, &g1};
+  for (int l = 0; l < 2; ++l) {
+    if (l == 0 ? need.x : need.y) {
+      double cc[11];
+      for (int k = 0; k < 11; ++k) cc[k] = l == 0 ? col0(k) : col1(k);
+      pixel_step_exact<SEM>(*ins[l], cc, false, gate, *outs[l], *gs[l]);
+    } else {
+#define M16_L(v) (l == 0 ? (v).x : (v).y)
+      StepOut& o = *outs[l];
+      o.day.canopy = M16_L(r.day.canopy); o.day.soil = M16_L(r.day.soil);
+      o.day.trans = M16_L(r.day.trans);   o.night.canopy = M16_L(r.night.canopy);
+      o.night.soil = M16_L(r.night.soil); o.night.trans = M16_L(r.night.trans);
+      o.tot_day = M16_L(r.tot_day); o.tot_night = M16_L(r.tot_night); o.tot = M16_L(r.tot);
+      *gs[l] = M16_L(gp);
+#undef M16_L
+    }
   }
-  g_d = ex_d ? lim_d : g_d;                                                   // :239
-  g_n = ex_n ? lim_n : g_n;
-  g_d = ((a_d - g_d < 0.0f) && (a_d > 0.0f)) ? a_d : g_d;                     // :245-247
-  g_n = ((a_d > 0.0f) && ((a_n - g_n) < (-0.5f * a_d))) ? fmaf(0.5f, a_d, a_n) : g_n;
-  const float omf = 1.0f - in.fpar;
-  HalfIn hd, hn;
-  hd.t = in.t_d; hd.vpd = in.vpd_d; hd.a_can = in.fpar * a_d; hd.rc = in.rc_d;
-  hd.a_soil = omf * (a_d - g_d);                                              // :253
-  hn.t = in.t_n; hn.vpd = in.vpd_n; hn.a_can = in.fpar * a_n_can; hn.rc = in.rc_n;
-  hn.a_soil = omf * (a_n - g_n);                                              // :254
-  bool unused;
-  o.day = half_fast<SEM, true>(hd, in.tmin, in.fpar, in.lai, c, x, has_rc, gate, g_pos);
-  o.night = half_fast<SEM, false>(hn, in.tmin, in.fpar, in.lai, c, x, has_rc, gate, unused);
-  o.tot_day = half_total<float, SEM>(o.day);
-  o.tot_night = half_total<float, SEM>(o.night);
-  o.tot = o.tot_day + o.tot_night;
 }
 
 }  // namespace fast

@@ -64,7 +64,7 @@ def forward(params, drivers, semantics='static', gate='global', dtype=np.float64
     sem = {'static': 0, 'instance': 1}[semantics]
     g = {'open': 0, 'global': 0, 'element': 1, 'closed': 2}[gate]
     suffix = 'f64' if dtype == np.float64 else 'f32'
-    name = ('hm_fast_' if fast else 'hm_forward_') + suffix
+    name = (('hm_fastpair_' if fast == 'pair' else 'hm_fast_') if fast else 'hm_forward_') + suffix
     fn = getattr(lib(), name)
     fn.restype = None
     fn(ctypes.c_int(sem), ctypes.c_int(g), drv.ctypes.data_as(ctypes.c_void_p),
@@ -72,11 +72,13 @@ def forward(params, drivers, semantics='static', gate='global', dtype=np.float64
        ctypes.c_int(1 if r_corr_list is not None else 0), ctypes.c_int64(n),
        out.ctypes.data_as(ctypes.c_void_p), gpos.ctypes.data_as(ctypes.c_void_p))
     out = out.reshape((out.shape[0],) + shape)
-    gpos = gpos.reshape(shape).astype(bool)
+    guarded = (gpos.reshape(shape) & 2).astype(bool)
+    gpos = (gpos.reshape(shape) & 1).astype(bool)
     closed = semantics == 'static' and gate == 'global' and not gpos.any()
     if closed:
         out[2] = 0  # the batch-global gate is closed (:343-348)
-    res = dict(day=(out[0], out[1], out[2]), night=(out[3], out[4], out[5]), g_pos=gpos)
+    res = dict(day=(out[0], out[1], out[2]), night=(out[3], out[4], out[5]), g_pos=gpos,
+               guarded=guarded)
     if fast and not closed:
         res.update(tot_day=out[6], tot_night=out[7], tot=out[8])
     return res

@@ -41,35 +41,63 @@ static void run(int sem, int gate, const R* drv, const R* par, const R* rc, int 
 }
 
 #ifdef HM_WITH_FAST
+static fast::StepIn load_in(const float* c, const float* rc, int has_rc, int64_t n, int64_t i) {
+  fast::StepIn in;
+  in.lw_d = c[0 * n + i]; in.lw_n = c[1 * n + i]; in.sw_d = c[2 * n + i];
+  in.sw_n = c[3 * n + i]; in.alb = c[4 * n + i];  in.t_d = c[5 * n + i];
+  in.t_n = c[6 * n + i];  in.t_ann = c[7 * n + i]; in.tmin = c[8 * n + i];
+  in.vpd_d = c[9 * n + i]; in.vpd_n = c[10 * n + i]; in.p = c[11 * n + i];
+  in.fpar = c[12 * n + i]; in.lai = c[13 * n + i];
+  in.rc_d = has_rc ? rc[i] : 0.f;
+  in.rc_n = has_rc ? rc[n + i] : 0.f;
+  return in;
+}
+
+static void store_out(const fast::StepOut& r, bool g, bool guarded, int64_t n, int64_t i,
+                      float* out, uint8_t* gpos) {
+  out[0 * n + i] = r.day.canopy;   out[1 * n + i] = r.day.soil;
+  out[2 * n + i] = r.day.trans;    out[3 * n + i] = r.night.canopy;
+  out[4 * n + i] = r.night.soil;   out[5 * n + i] = r.night.trans;
+  out[6 * n + i] = r.tot_day;      out[7 * n + i] = r.tot_night;
+  out[8 * n + i] = r.tot;
+  gpos[i] = (g ? 1 : 0) | (guarded ? 2 : 0);
+}
+
+// pair != 0: elements are evaluated two at a time through the packed (F2) instantiation
 static void run_fast(int sem, int gate, const float* drv, const double* par, const float* rc,
-                     int has_rc, int64_t n, float* out, uint8_t* gpos) {
-  for (int64_t i = 0; i < n; ++i) {
-    fast::StepIn in;
-    const float* c = drv;
-    in.lw_d = c[0 * n + i]; in.lw_n = c[1 * n + i]; in.sw_d = c[2 * n + i];
-    in.sw_n = c[3 * n + i]; in.alb = c[4 * n + i];  in.t_d = c[5 * n + i];
-    in.t_n = c[6 * n + i];  in.t_ann = c[7 * n + i]; in.tmin = c[8 * n + i];
-    in.vpd_d = c[9 * n + i]; in.vpd_n = c[10 * n + i]; in.p = c[11 * n + i];
-    in.fpar = c[12 * n + i]; in.lai = c[13 * n + i];
-    in.rc_d = has_rc ? rc[i] : 0.f;
-    in.rc_n = has_rc ? rc[n + i] : 0.f;
-    double col[11];
-    for (int k = 0; k < 11; ++k) col[k] = par[k * n + i];
-    fast::PftConst pc = fast::make_pft_const(col, sem);
-    fast::PixConst px = fast::make_pix_const(in.p, in.t_ann, pc, sem);
-    fast::StepOut r;
-    bool g;
-    auto colfn = [&](int k) { return col[k]; };
-    if (sem == SEM_STATIC)
-      fast::pixel_step_fast<SEM_STATIC>(in, pc, px, colfn, has_rc != 0, gate, r, g);
-    else
-      fast::pixel_step_fast<SEM_INSTANCE>(in, pc, px, colfn, has_rc != 0, gate, r, g);
-    out[0 * n + i] = r.day.canopy;   out[1 * n + i] = r.day.soil;
-    out[2 * n + i] = r.day.trans;    out[3 * n + i] = r.night.canopy;
-    out[4 * n + i] = r.night.soil;   out[5 * n + i] = r.night.trans;
-    out[6 * n + i] = r.tot_day;      out[7 * n + i] = r.tot_night;
-    out[8 * n + i] = r.tot;
-    gpos[i] = g ? 1 : 0;
+                     int has_rc, int64_t n, float* out, uint8_t* gpos, int pair) {
+  for (int64_t i = 0; i < n; i += (pair && i + 1 < n && !has_rc) ? 2 : 1) {
+    const bool two = pair && i + 1 < n && !has_rc;
+    fast::StepIn in[2];
+    double col[2][11];
+    fast::PftConst pc[2];
+    fast::PixConst px[2];
+    for (int l = 0; l < (two ? 2 : 1); ++l) {
+      in[l] = load_in(drv, rc, has_rc, n, i + l);
+      for (int k = 0; k < 11; ++k) col[l][k] = par[k * n + i + l];
+      pc[l] = fast::make_pft_const(col[l], sem);
+      px[l] = fast::make_pix_const(in[l].p, in[l].t_ann, pc[l], sem);
+    }
+    fast::StepOut r[2];
+    bool g[2] = {false, false}, guarded[2] = {false, false};
+    auto c0 = [&](int k) { return col[0][k]; };
+    auto c1 = [&](int k) { return col[1][k]; };
+    if (two) {
+      if (sem == SEM_STATIC)
+        fast::pair_step_fast<SEM_STATIC>(in[0], in[1], pc[0], pc[1], px[0], px[1], c0, c1, gate,
+                                         r[0], r[1], g[0], g[1]);
+      else
+        fast::pair_step_fast<SEM_INSTANCE>(in[0], in[1], pc[0], pc[1], px[0], px[1], c0, c1,
+                                           gate, r[0], r[1], g[0], g[1]);
+    } else {
+      if (sem == SEM_STATIC)
+        fast::pixel_step_fast<SEM_STATIC>(in[0], pc[0], px[0], c0, has_rc != 0, gate, r[0], g[0],
+                                          &guarded[0]);
+      else
+        fast::pixel_step_fast<SEM_INSTANCE>(in[0], pc[0], px[0], c0, has_rc != 0, gate, r[0],
+                                            g[0], &guarded[0]);
+    }
+    for (int l = 0; l < (two ? 2 : 1); ++l) store_out(r[l], g[l], guarded[l], n, i + l, out, gpos);
   }
 }
 #endif
@@ -78,7 +106,11 @@ extern "C" {
 #ifdef HM_WITH_FAST
 void hm_fast_f32(int sem, int gate, const float* drv, const double* par, const float* rc,
                  int has_rc, int64_t n, float* out, uint8_t* gpos) {
-  run_fast(sem, gate, drv, par, rc, has_rc, n, out, gpos);
+  run_fast(sem, gate, drv, par, rc, has_rc, n, out, gpos, 0);
+}
+void hm_fastpair_f32(int sem, int gate, const float* drv, const double* par, const float* rc,
+                     int has_rc, int64_t n, float* out, uint8_t* gpos) {
+  run_fast(sem, gate, drv, par, rc, has_rc, n, out, gpos, 1);
 }
 #endif
 void hm_forward_f64(int sem, int gate, const double* drv, const double* par, const double* rc,

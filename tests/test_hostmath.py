@@ -105,9 +105,13 @@ def _table():
                              default_beta=250.0)
 
 
+FAST_MODES = [True, 'pair']   # scalar (float) and packed-pair (F2) instantiations
+
+
+@pytest.mark.parametrize('fast', FAST_MODES)
 @pytest.mark.parametrize('kind,nan', [('physical', 0.0), ('stress', 0.0),
                                       ('physical', 0.003), ('stress', 0.003)])
-def test_fast_f32_matches_f64_oracle(kind, nan):
+def test_fast_f32_matches_f64_oracle(kind, nan, fast):
     T, N = 40, 5000
     d = synthetic.host_drivers(T, N, 321, kind=kind, dtype=np.float32, nan_frac=nan,
                                fill_frac=nan)
@@ -118,7 +122,7 @@ def test_fast_f32_matches_f64_oracle(kind, nan):
     vec = [table[i][pft].reshape(1, N) for i in range(11)]
     with np.errstate(all='ignore'):
         od, on = orc.static_evapotranspiration(vec, *d64)
-    r = hostmath.forward(vec, drv, 'static', 'global', dtype=np.float32, fast=True)
+    r = hostmath.forward(vec, drv, 'static', 'global', dtype=np.float32, fast=fast)
     parity.assert_parity(r['tot_day'], od, np.float32, what='fast static day')
     parity.assert_parity(r['tot_night'], on, np.float32, what='fast static night')
     parity.assert_parity(r['tot'], od + on, np.float32, what='fast static sum')
@@ -126,14 +130,15 @@ def test_fast_f32_matches_f64_oracle(kind, nan):
     with np.errstate(all='ignore'):
         sep = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, col))).evapotranspiration(
             *d64, separate=True)
-    r = hostmath.forward(col, drv, 'instance', dtype=np.float32, fast=True)
+    r = hostmath.forward(col, drv, 'instance', dtype=np.float32, fast=fast)
     for h, hn_ in enumerate(('day', 'night')):
         for c in range(3):
             parity.assert_parity(r[hn_][c], sep[h][c], np.float32, parity.MASS_SCALE,
                                  what='fast instance %s %d' % (hn_, c))
 
 
-def test_fast_f32_tables(golden_dir):
+@pytest.mark.parametrize('fast', FAST_MODES)
+def test_fast_f32_tables(golden_dir, fast):
     z = np.load(os.path.join(golden_dir, 'tables.npz'))
     vec = list(z['params'])
     drv = [z['drivers'][:, i].astype(np.float32) for i in range(14)]
@@ -142,17 +147,18 @@ def test_fast_f32_tables(golden_dir):
         od, on = orc.static_evapotranspiration(vec, *d64, gate='element')
         sep = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, vec))).evapotranspiration(
             *d64, separate=True)
-    r = hostmath.forward(vec, drv, 'static', 'element', dtype=np.float32, fast=True)
+    r = hostmath.forward(vec, drv, 'static', 'element', dtype=np.float32, fast=fast)
     parity.assert_parity(r['tot_day'], od, np.float32, what='fast table day')
     parity.assert_parity(r['tot_night'], on, np.float32, what='fast table night')
-    r = hostmath.forward(vec, drv, 'instance', dtype=np.float32, fast=True)
+    r = hostmath.forward(vec, drv, 'instance', dtype=np.float32, fast=fast)
     for h, hn_ in enumerate(('day', 'night')):
         for c in range(3):
             parity.assert_parity(r[hn_][c], sep[h][c], np.float32, parity.MASS_SCALE,
                                  what='fast table inst %s %d' % (hn_, c))
 
 
-def test_fast_f32_guards_near_thresholds():
+@pytest.mark.parametrize('fast', FAST_MODES)
+def test_fast_f32_guards_near_thresholds(fast):
     'Elements placed within rounding of rh = 0.7, rh = 0+ and |G| = 0.39|A| (opposite sign).'
     rng = np.random.default_rng(8)
     n = 20000
@@ -177,6 +183,21 @@ def test_fast_f32_guards_near_thresholds():
     d64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
     with np.errstate(all='ignore'):
         od, on = orc.static_evapotranspiration(BPLUT7, *d64)
-    r = hostmath.forward(BPLUT7, drv, 'static', 'global', dtype=np.float32, fast=True)
+    r = hostmath.forward(BPLUT7, drv, 'static', 'global', dtype=np.float32, fast=fast)
     parity.assert_parity(r['tot_day'], od, np.float32, what='guards day')
     parity.assert_parity(r['tot_night'], on, np.float32, what='guards night')
+
+
+def test_fast_f32_guard_rate_is_small():
+    'The double-precision detour must stay rare on clean data (it costs ~20x a fast element).'
+    T, N = 50, 4000
+    table = _table()
+    pft = synthetic.host_pft_map(N, 5)
+    vec = [table[i][pft].reshape(1, N) for i in range(11)]
+    for kind, limit in (('physical', 2e-4), ('stress', 2e-3)):
+        d = synthetic.host_drivers(T, N, 99, kind=kind, dtype=np.float32)
+        r = hostmath.forward(vec, [d[k] for k in NAMES], 'static', 'global', dtype=np.float32,
+                             fast=True)
+        rate = r['guarded'].mean()
+        print('guard rate', kind, rate)
+        assert rate < limit, (kind, rate)
