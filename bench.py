@@ -51,9 +51,9 @@ def parse():
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--gate', default='global')
-    ap.add_argument('--kernel', default='pipe', choices=['pipe', 'direct', 'generic', 'mirror'],
-                    help='f32 kernel variant (profiling): bulk-copy pipeline (default), direct '
-                         '128-bit loads, strided fast math, op-for-op')
+    ap.add_argument('--kernel', default='pipe', choices=['pipe', 'generic', 'mirror'],
+                    help='f32 kernel variant (profiling): bulk-copy pipeline (default), strided '
+                         'fast math, op-for-op')
     return ap.parse_args()
 
 
@@ -258,7 +258,7 @@ def main():
     flag = torch.zeros(1, device=device, dtype=torch.int32)
     launches_per_step = 2 if args.gate == 'global' else 1   # forward kernel (+ gate fix-up)
 
-    force = {'pipe': 0, 'direct': _abi.FORCE_DIRECT, 'generic': _abi.FORCE_GENERIC,
+    force = {'pipe': 0, 'generic': _abi.FORCE_GENERIC,
              'mirror': _abi.FORCE_MIRROR}[args.kernel]
 
     def step():
@@ -364,7 +364,7 @@ def main():
                            bytes_per_unit * units_per_rank / 1e9)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                         'kernel': {'pipe': 'forward_pipe_kernel', 'direct': 'forward_vec4_kernel',
+                         'kernel': {'pipe': 'forward_pipe_kernel',
                                     'generic': 'forward_strided_fast_kernel',
                                     'mirror': 'forward_strided_kernel<float>'}[args.kernel]
                                    if np_dtype == np.float32 else 'forward_strided_kernel<double>',

@@ -90,8 +90,6 @@ enum {
    layout allows 128-bit loads, else the strided one */
 #define MOD16_FORCE_GENERIC 0x1000u
 #define MOD16_FORCE_MIRROR 0x2000u  /* f32: op-for-op transcription instead of fast math */
-#define MOD16_FORCE_DIRECT 0x4000u  /* f32: direct 128-bit global loads instead of the
-                                       bulk-copy pipeline */
 
 typedef struct mod16_driver {
   const void* ptr;   /* device array of float / double, or NULL: use `scalar` */

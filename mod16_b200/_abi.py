@@ -15,7 +15,7 @@ SEM_STATIC, SEM_INSTANCE = 0x0, 0x1
 OUT_SUM, OUT_DAY_NIGHT, OUT_COMPONENTS = 0x00, 0x10, 0x20
 GATE_GLOBAL, GATE_ELEMENT, GATE_OPEN, GATE_CLOSED = 0x000, 0x100, 0x200, 0x300
 GATE_OPEN_TRACK, GATE_FIXUP = 0x400, 0x500
-FORCE_GENERIC, FORCE_MIRROR, FORCE_DIRECT = 0x1000, 0x2000, 0x4000
+FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 

@@ -1,17 +1,18 @@
 // K1, float32 fast path.
 //
-// forward_vec4_kernel -- the headline kernel.  Layout: (T, N) row-major structure-of-arrays,
-//   one thread owns 4 consecutive pixels and walks a chunk of time steps.  Per step it
-//   issues eleven 128-bit streaming loads (one per per-step driver; a warp reads 512
-//   contiguous bytes of each array), evaluates the 4 pixel-timesteps with the rearranged
-//   math of mod16_fast.cuh and writes ET once with a 128-bit streaming store.  The BPLUT
-//   (13 land-cover columns x 16 derived constants) is staged in shared memory once per
-//   block and gathered by the pixel's land-cover code; pressure terms and the annual
-//   temperature window are hoisted out of the time loop.  Algorithmic traffic:
-//   11 x 4 B in + 4 B out = 48 B per pixel-timestep (OUT_SUM).
+// forward_pipe_kernel -- the headline kernel.  Layout: (T, N) row-major structure-of-arrays.
+//   One block per SM-resident tile of 480 pixels walks a chunk of time steps two at a time.
+//   A producer warp streams the eleven per-step driver rows of the next steps into a
+//   five-stage shared-memory ring with bulk asynchronous copies (cp.async.bulk, completion
+//   on an mbarrier); fifteen consumer warps evaluate the model with the packed-FP32
+//   (FFMA2) math of mod16_fast.cuh -- the two lanes of every packed instruction are the
+//   same pixel at two consecutive time steps, so all BPLUT-derived and per-pixel constants
+//   are scalar registers -- and write ET exactly once.  Algorithmic traffic: 11 x 4 B in +
+//   4 B out = 48 B per pixel-timestep (OUT_SUM).
 //
-// forward_strided_fast_kernel -- same math for layouts that do not allow 128-bit loads
-//   (broadcast strides, per-pixel parameter arrays, N % 4 != 0, r_corr_list).
+// forward_strided_fast_kernel -- same math, one pixel-timestep at a time, for layouts the
+//   bulk copies cannot express (broadcast strides, per-pixel parameter arrays, N % 4 != 0,
+//   unaligned bases, r_corr_list).
 #include "mod16_common.cuh"
 #include "mod16_fast.cuh"
 
@@ -21,41 +22,12 @@ using fast::PftConst;
 using fast::PixConst;
 using fast::StepIn;
 
-#ifndef VEC4_THREADS
-#define VEC4_THREADS 256
-#endif
-#ifndef VEC4_MIN_BLOCKS
-#define VEC4_MIN_BLOCKS 2
-#endif
-
-__device__ __forceinline__ float4 ld_stream(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_stream(float* p, float4 v) {
-  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"
-               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float comp(const float4& v, int j) {
-  return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
-}
-__device__ __forceinline__ void setc(float4& v, int j, float x) {
-  if (j == 0) v.x = x; else if (j == 1) v.y = x; else if (j == 2) v.z = x; else v.w = x;
-}
-
 // Shared-memory copy of the BPLUT: derived float constants for the fast math and the raw
 // double table for the op-for-op fallback.
 // Column MOD16_N_PFT is an all-NaN column for land-cover codes outside 0..12.
 struct SharedLut {
   PftConst pc[MOD16_N_PFT + 1];
   double tab[MOD16_N_PARAMS][MOD16_N_PFT + 1];
-};
-// The same constants for every PAIR of land-cover codes, interleaved so that one shared
-// load yields the packed (pixel 0, pixel 1) operand of an FFMA2 (14 x 14 x 96 B = 18.4 KB).
-struct PairLut {
-  fast::PftConstV<fast::F2> pp[MOD16_N_PFT + 1][MOD16_N_PFT + 1];
 };
 
 template <int SEM>
@@ -74,29 +46,24 @@ __device__ __forceinline__ void stage_lut(const ForwardArgs<float>& a, SharedLut
   __syncthreads();
 }
 
-__device__ __forceinline__ void stage_pair_lut(const SharedLut& s, PairLut& p) {
-  constexpr int NC = MOD16_N_PFT + 1, NF = sizeof(fast::PftConstV<float>) / sizeof(float);
-  static_assert(sizeof(fast::PftConstV<fast::F2>) == NF * sizeof(fast::F2), "layout");
-  for (int i = threadIdx.x; i < NC * NC * NF; i += blockDim.x) {
-    const int f = i % NF, b = (i / NF) % NC, a = i / (NF * NC);
-    const float* fa = reinterpret_cast<const float*>(static_cast<const fast::PftConstV<float>*>(&s.pc[a]));
-    const float* fb = reinterpret_cast<const float*>(static_cast<const fast::PftConstV<float>*>(&s.pc[b]));
-    reinterpret_cast<fast::F2*>(&p.pp[a][b])[f] = fast::F2{fa[f], fb[f]};
-  }
-  __syncthreads();
-}
-
-// Deferred exact re-evaluation of the elements of one float4 that step_fast() flagged.
-// Out of line and self-contained (re-reads its inputs from global memory, which the fast
-// pass has just pulled through L2), so that the double-precision code costs the hot loop
-// no registers.  Returns the gate predicate OR-ed over the re-evaluated elements.
+// Deferred exact re-evaluation of the elements that step_fast() flagged: element j of
+// `mask` is pixel n at time step t + j.  Out of line and self-contained (re-reads its
+// inputs from global memory, which the fast pass has just pulled through L2), so that the
+// double-precision code costs the hot loop no registers.  Returns the gate predicate OR-ed
+// over the re-evaluated elements.
 template <int SEM, int OUT>
-__device__ __noinline__ bool fix_exact_vec4(const ForwardArgs<float>& a, const SharedLut& lut,
-                                            int64_t t, int64_t n0, unsigned mask) {
+__device__ __noinline__ bool fix_exact_steps(const ForwardArgs<float>& a, const SharedLut& lut,
+                                             int64_t t, int64_t n, unsigned mask) {
   bool any_pos = false;
-  for (int j = 0; j < 4; ++j) {
-    if (!((mask >> j) & 1u)) continue;  // (the pipelined kernel passes pairs: j < 2)
-    const int64_t n = n0 + j;
+  int code = 0;
+  if (a.par_mode == 1) {
+    code = (int)__ldg(a.pft + n);
+    code = code < MOD16_N_PFT ? code : MOD16_N_PFT;
+  }
+  double col[MOD16_N_PARAMS];
+  for (int k = 0; k < MOD16_N_PARAMS; ++k) col[k] = lut.tab[k][code];
+  for (int j = 0; j < 2; ++j, ++t) {
+    if (!((mask >> j) & 1u)) continue;
     StepIn in;
     in.lw_d = a.drv[MOD16_D_LW_NET_DAY].at(t, n);
     in.lw_n = a.drv[MOD16_D_LW_NET_NIGHT].at(t, n);
@@ -113,13 +80,6 @@ __device__ __noinline__ bool fix_exact_vec4(const ForwardArgs<float>& a, const S
     in.fpar = a.drv[MOD16_D_FPAR].at(t, n);
     in.lai = a.drv[MOD16_D_LAI].at(t, n);
     in.rc_d = 0.0f; in.rc_n = 0.0f;
-    int code = 0;
-    if (a.par_mode == 1) {
-      code = (int)__ldg(a.pft + n);
-      code = code < MOD16_N_PFT ? code : MOD16_N_PFT;
-    }
-    double col[MOD16_N_PARAMS];
-    for (int k = 0; k < MOD16_N_PARAMS; ++k) col[k] = lut.tab[k][code];
     fast::StepOut r;
     bool g_pos;
     fast::pixel_step_exact<SEM>(in, col, false, a.gate, r, g_pos);
@@ -138,131 +98,30 @@ __device__ __noinline__ bool fix_exact_vec4(const ForwardArgs<float>& a, const S
   return any_pos;
 }
 
-__device__ __forceinline__ fast::F2 lo2(const float4& v) { return fast::F2{v.x, v.y}; }
-__device__ __forceinline__ fast::F2 hi2(const float4& v) { return fast::F2{v.z, v.w}; }
-
-template <int SEM, int OUT>
-__global__ void __launch_bounds__(VEC4_THREADS, VEC4_MIN_BLOCKS)
-forward_vec4_kernel(const __grid_constant__ ForwardArgs<float> a) {
-  using fast::F2;
-  using fast::M2;
-  __shared__ SharedLut lut;
-  __shared__ PairLut plut;
-  if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
-  stage_lut<SEM>(a, lut);
-  stage_pair_lut(lut, plut);
-  const int64_t n0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int64_t t0 = (int64_t)blockIdx.y * a.t_chunk;
-  int64_t t1 = t0 + a.t_chunk;
-  if (t1 > a.T) t1 = a.T;
-  bool any_pos = false;
-  if (n0 < a.N) {
-    // per-pixel state: land-cover codes, pressure terms, annual-temperature window
-    int code[4] = {0, 0, 0, 0};
-    if (a.par_mode == 1) {
-      const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(a.pft + n0));
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int c = (w >> (8 * j)) & 0xff;
-        code[j] = c < MOD16_N_PFT ? c : MOD16_N_PFT;  // out of range: the all-NaN column
-      }
-    }
-    const Arr<float>& ap = a.drv[MOD16_D_PRESSURE];
-    const Arr<float>& aa = a.drv[MOD16_D_TEMP_ANNUAL];
-    float4 p4, ta4;
-    if (ap.ptr) p4 = __ldg(reinterpret_cast<const float4*>(ap.ptr + n0));
-    else p4 = make_float4(ap.scalar, ap.scalar, ap.scalar, ap.scalar);
-    if (aa.ptr) ta4 = __ldg(reinterpret_cast<const float4*>(aa.ptr + n0));
-    else ta4 = make_float4(aa.scalar, aa.scalar, aa.scalar, aa.scalar);
-    fast::PixConstV<F2> px[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-      px[h] = fast::pair_pix(
-          fast::make_pix_const(comp(p4, 2 * h), comp(ta4, 2 * h), lut.pc[code[2 * h]], SEM),
-          fast::make_pix_const(comp(p4, 2 * h + 1), comp(ta4, 2 * h + 1),
-                               lut.pc[code[2 * h + 1]], SEM));
-    const fast::PftConstV<F2>* pc2[2] = {&plut.pp[code[0]][code[1]], &plut.pp[code[2]][code[3]]};
-
-    const Arr<float>& swn = a.drv[MOD16_D_SW_RAD_NIGHT];
-    const int gate = a.gate;
-    for (int64_t t = t0; t < t1; ++t) {
-      const int64_t off = t * a.N + n0;  // per-step arrays are dense (checked on the host)
-      const float4 lw_d = ld_stream(a.drv[MOD16_D_LW_NET_DAY].ptr + off);
-      const float4 lw_n = ld_stream(a.drv[MOD16_D_LW_NET_NIGHT].ptr + off);
-      const float4 sw_d = ld_stream(a.drv[MOD16_D_SW_RAD_DAY].ptr + off);
-      const float4 alb = ld_stream(a.drv[MOD16_D_SW_ALBEDO].ptr + off);
-      const float4 t_d = ld_stream(a.drv[MOD16_D_TEMP_DAY].ptr + off);
-      const float4 t_n = ld_stream(a.drv[MOD16_D_TEMP_NIGHT].ptr + off);
-      const float4 tmin = ld_stream(a.drv[MOD16_D_TMIN].ptr + off);
-      const float4 vpd_d = ld_stream(a.drv[MOD16_D_VPD_DAY].ptr + off);
-      const float4 vpd_n = ld_stream(a.drv[MOD16_D_VPD_NIGHT].ptr + off);
-      const float4 fpar = ld_stream(a.drv[MOD16_D_FPAR].ptr + off);
-      const float4 lai = ld_stream(a.drv[MOD16_D_LAI].ptr + off);
-      float4 sw_n;
-      if (swn.ptr) sw_n = ld_stream(swn.ptr + off);
-      else sw_n = make_float4(swn.scalar, swn.scalar, swn.scalar, swn.scalar);
-      F2 res[6][2];
-      unsigned redo = 0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        fast::StepInV<F2> in;
-        in.lw_d = h ? hi2(lw_d) : lo2(lw_d);   in.lw_n = h ? hi2(lw_n) : lo2(lw_n);
-        in.sw_d = h ? hi2(sw_d) : lo2(sw_d);   in.sw_n = h ? hi2(sw_n) : lo2(sw_n);
-        in.alb = h ? hi2(alb) : lo2(alb);      in.t_d = h ? hi2(t_d) : lo2(t_d);
-        in.t_n = h ? hi2(t_n) : lo2(t_n);      in.tmin = h ? hi2(tmin) : lo2(tmin);
-        in.vpd_d = h ? hi2(vpd_d) : lo2(vpd_d); in.vpd_n = h ? hi2(vpd_n) : lo2(vpd_n);
-        in.fpar = h ? hi2(fpar) : lo2(fpar);   in.lai = h ? hi2(lai) : lo2(lai);
-        in.rc_d = F2{0.f, 0.f}; in.rc_n = F2{0.f, 0.f};
-        fast::StepOutV<F2> r;
-        M2 g_pos;
-        const M2 need = fast::step_fast<F2, SEM, false>(in, *pc2[h], px[h], gate, r, g_pos);
-        redo |= (need.x ? 1u : 0u) << (2 * h) | (need.y ? 2u : 0u) << (2 * h);
-        any_pos |= (g_pos.x && !need.x) || (g_pos.y && !need.y);
-        if (OUT == 0) {
-          res[0][h] = r.tot;
-        } else if (OUT == 1) {
-          res[0][h] = r.tot_day; res[1][h] = r.tot_night;
-        } else {
-          res[0][h] = r.day.canopy;   res[1][h] = r.day.soil;   res[2][h] = r.day.trans;
-          res[3][h] = r.night.canopy; res[4][h] = r.night.soil; res[5][h] = r.night.trans;
-        }
-      }
-      constexpr int n_out = OUT == 0 ? 1 : (OUT == 1 ? 2 : 6);
-#pragma unroll
-      for (int k = 0; k < n_out; ++k)
-        st_stream(a.out[k] + off,
-                  make_float4(res[k][0].x, res[k][0].y, res[k][1].x, res[k][1].y));
-      if (redo) any_pos |= fix_exact_vec4<SEM, OUT>(a, lut, t, n0, redo);
-    }
-  }
-  if (a.track_gate) {
-    if (__any_sync(0xffffffffu, any_pos) && (threadIdx.x & 31) == 0) *a.gate_flag = 1;
-  }
-}
-
-// ---- forward_pipe_kernel: the headline kernel, fed by bulk asynchronous copies ----------
-// One block owns a tile of PIPE_TILE = 512 pixels (one packed pair per thread) and walks a
-// chunk of time steps.  For every step one elected thread issues eleven (twelve with a
-// sw_rad_night array) `cp.async.bulk` copies -- 2 KB of each driver row -- into one of
-// PIPE_STAGES shared-memory stages and arms the stage's `full` mbarrier with the byte
-// count.  Each warp waits on the barrier's phase, evaluates its 64 pixel-timesteps out of
-// shared memory (64-bit conflict-free LDS straight into FFMA2 operand pairs)
-// straight into registers and releases the stage at once (a shared counter); the last of
-// the eight warps to release a stage re-fills it, so nobody ever waits for a free stage.
-// Copies of the next PIPE_STAGES steps are in flight while a step is evaluated: HBM latency
-// is hidden by the copy engine instead of by registers (the direct-load kernel holds 44
-// registers of loads in flight and spills), there is no block-wide barrier and no address
-// arithmetic in the time loop.
-constexpr int PIPE_THREADS = 256;
-constexpr int PIPE_WARPS = PIPE_THREADS / 32;
-constexpr int PIPE_TILE = PIPE_THREADS * 2;
-constexpr int PIPE_STAGES = 4;
+// ---- forward_pipe_kernel ------------------------------------------------------------------
+// Warp specialisation: warp 15 is the PRODUCER; for every pair of time steps its elected
+// lane waits until a stage is free, arms the stage's `full` mbarrier with the byte count
+// and issues 22 (24 with a sw_rad_night array) `cp.async.bulk` copies of 1920 B, one per
+// driver row and step.  The fifteen CONSUMER warps wait on the barrier's phase, pull their
+// inputs out of shared memory (conflict-free 32-bit LDS, the rows of step t and t + 1
+// landing in the two halves of an FFMA2 operand pair), release the stage at once (`empty`
+// mbarrier) and then evaluate and store.  The copies of the next 2 x PIPE_STAGES steps are
+// in flight while a pair of steps is evaluated: HBM latency is hidden by the copy engine
+// instead of by registers, there is no block-wide barrier, no table gather and no address
+// arithmetic in the time loop, and issuing the copies costs the consumers nothing
+// (measured alternatives: profiles/r01_pipebench.txt and DESIGN.md).
+constexpr int PIPE_CONSUMER_WARPS = 15;
+constexpr int PIPE_CONSUMERS = PIPE_CONSUMER_WARPS * 32;
+constexpr int PIPE_THREADS = PIPE_CONSUMERS + 32;
+constexpr int PIPE_TILE = PIPE_CONSUMERS;  // pixels per block
+constexpr int PIPE_SUB = 2;                // time steps per stage (the two FFMA2 lanes)
+constexpr int PIPE_STAGES = 5;
 constexpr int PIPE_MAX_ARR = 12;
 
+// (all barrier / stage addresses are 32-bit shared-window addresses, computed once)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-// (all barrier / stage addresses are 32-bit shared-window addresses, computed once)
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -279,9 +138,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ fast::F2 lds2(uint32_t addr) {
-  fast::F2 v;
-  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+__device__ __forceinline__ float lds1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -295,39 +154,57 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "M16_DONE:\n"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void st_stream2(float* p, fast::F2 v) {
-  asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+__device__ __forceinline__ void st_stream1(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
 struct PipeSrc {  // per-step arrays in stage order
   const float* ptr[PIPE_MAX_ARR];
   int n_arr;
+  int n_stages;  // PIPE_STAGES, one fewer when a twelfth array must fit in shared memory
 };
 
-// Producer step (one thread): arm the barrier, start the row copies.  The array base
-// pointers are read from a shared-memory copy (a generic load from the kernel-parameter
-// space costs hundreds of cycles, and the eleven copies issue back to back).
-__device__ __forceinline__ void pipe_issue(const float* const* sptr, int n_arr, uint32_t dst,
-                                           uint32_t bar, int64_t off, uint32_t row_bytes) {
-  mbar_expect_tx(bar, row_bytes * (uint32_t)n_arr);
-#pragma unroll 4
-  for (int k = 0; k < n_arr; ++k)
-    bulk_g2s(dst + (uint32_t)k * PIPE_TILE * (uint32_t)sizeof(float), sptr[k] + off, row_bytes,
-             bar);
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(pred));
+  return pred != 0;
+}
+
+// Producer step, executed by the WHOLE producer warp so that addresses stay in uniform
+// registers and the base pointers come straight from the constant bank; one elected lane
+// arms the barrier and starts the row copies of `n_sub` time steps.  (Measured: this form
+// issues > 50 copies/us, an elected thread inside a divergent branch only 18 --
+// profiles/r01_issuebench.txt.)
+__device__ __forceinline__ void pipe_issue(const PipeSrc& src, int n_arr, int n_sub,
+                                           uint32_t dst, uint32_t bar, int64_t off,
+                                           int64_t t_stride, uint32_t row_bytes) {
+  if (elect_one()) {
+    mbar_expect_tx(bar, row_bytes * (uint32_t)(n_arr * n_sub));
+#pragma unroll
+    for (int u = 0; u < PIPE_SUB; ++u) {
+      if (u < n_sub) {
+#pragma unroll
+        for (int k = 0; k < PIPE_MAX_ARR; ++k)
+          if (k < n_arr)
+            bulk_g2s(dst + (uint32_t)(u * n_arr + k) * PIPE_TILE * (uint32_t)sizeof(float),
+                     src.ptr[k] + off + u * t_stride, row_bytes, bar);
+      }
+    }
+  }
+  __syncwarp();
 }
 
 template <int SEM, int OUT>
-__global__ void __launch_bounds__(PIPE_THREADS, 2)
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
 forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
                     const __grid_constant__ PipeSrc src) {
   using fast::F2;
   using fast::M2;
-  extern __shared__ __align__(128) unsigned char dyn_smem[];  // [stage][array][PIPE_TILE]
+  // [stage][sub-step][array][PIPE_TILE]
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ SharedLut lut;
-  __shared__ PairLut plut;
-  __shared__ __align__(8) uint64_t full[PIPE_STAGES];
-  __shared__ int released[PIPE_STAGES];  // warps that have read the stage's current contents
-  __shared__ const float* sptr[PIPE_MAX_ARR];
+  __shared__ __align__(8) uint64_t full[PIPE_STAGES], empty[PIPE_STAGES];
   if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
   const int tid = threadIdx.x;
   const int n_arr = src.n_arr;
@@ -336,98 +213,106 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   int64_t t1 = t0 + a.t_chunk;
   if (t1 > a.T) t1 = a.T;
   const int nsteps = (int)(t1 - t0);
+  const int niter = (nsteps + PIPE_SUB - 1) / PIPE_SUB;  // stage uses; the last may hold 1 step
   const int64_t left = a.N - tile0;
   const uint32_t row_bytes = (uint32_t)((left < PIPE_TILE ? left : PIPE_TILE) * sizeof(float));
-  const uint32_t stage_bytes = (uint32_t)n_arr * PIPE_TILE * sizeof(float);
-
-  const uint32_t full0 = smem_u32(&full[0]);
+  constexpr uint32_t ROWB = PIPE_TILE * sizeof(float);         // bytes per array row
+  const uint32_t SUBB = (uint32_t)n_arr * ROWB;                // bytes per sub-step
+  const uint32_t STAGEB = PIPE_SUB * SUBB;                     // bytes per stage
+  const int n_stages = src.n_stages;
+  const uint32_t full0 = smem_u32(&full[0]), empty0 = smem_u32(&empty[0]);
   const uint32_t data0 = smem_u32(dyn_smem);
-  if (tid == 0) {
-    for (int s = 0; s < PIPE_STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      released[s] = 0;
+  const bool producer = tid >= PIPE_CONSUMERS;
+
+  if (producer) {  // barriers, first fills (before the table staging: latency overlaps)
+    if (tid == PIPE_CONSUMERS) {
+      for (int s = 0; s < PIPE_STAGES; ++s) {
+        mbar_init(full0 + 8 * s, 1);
+        mbar_init(empty0 + 8 * s, PIPE_CONSUMER_WARPS);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < PIPE_MAX_ARR; ++k) sptr[k] = src.ptr[k];
-    for (int s = 0; s < PIPE_STAGES && s < nsteps; ++s)
-      pipe_issue(sptr, n_arr, data0 + s * stage_bytes, full0 + 8 * s, (t0 + s) * a.N + tile0,
+    __syncwarp();
+    for (int s = 0; s < n_stages && s < niter; ++s)
+      pipe_issue(src, n_arr, nsteps - s * PIPE_SUB >= PIPE_SUB ? PIPE_SUB : 1,
+                 data0 + s * STAGEB, full0 + 8 * s, (t0 + s * PIPE_SUB) * a.N + tile0, a.N,
                  row_bytes);
   }
-  stage_lut<SEM>(a, lut);       // (both contain __syncthreads: the barriers are visible)
-  stage_pair_lut(lut, plut);
+  stage_lut<SEM>(a, lut);  // (contains __syncthreads: the barriers are visible to everyone)
 
-  const int64_t n0 = tile0 + (int64_t)tid * 2;
-  const bool live = n0 < a.N;   // N is even: a pair is inside or outside as a whole
+  if (producer) {
+    int stage = 0;
+    uint32_t phase = 0;  // parity of the stage's previous use
+#pragma unroll 1
+    for (int i = n_stages; i < niter; ++i) {
+      mbar_wait(empty0 + 8 * stage, phase);  // all fifteen warps have read the stage
+      pipe_issue(src, n_arr, nsteps - i * PIPE_SUB >= PIPE_SUB ? PIPE_SUB : 1,
+                 data0 + (uint32_t)stage * STAGEB, full0 + 8 * stage,
+                 (t0 + (int64_t)i * PIPE_SUB) * a.N + tile0, a.N, row_bytes);
+      if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+    }
+    return;
+  }
+
+  const int64_t n = tile0 + tid;
+  const bool live = n < a.N;
   bool any_pos = false;
-  // per-pixel state: land-cover codes, pressure terms, annual-temperature window
-  int code0 = 0, code1 = 0;
+  // per-pixel state, all scalar: BPLUT column constants, pressure terms, annual window
+  fast::PftConstV<F2> pc;
   fast::PixConstV<F2> px;
   {
-    float2 p2 = make_float2(1e5f, 1e5f), ta2 = make_float2(0.f, 0.f);
+    int code = 0;
+    float p = 1e5f, ta = 0.f;
     if (live) {
       if (a.par_mode == 1) {
-        const uint32_t w = __ldg(reinterpret_cast<const uint16_t*>(a.pft + n0));
-        code0 = w & 0xff; code1 = (w >> 8) & 0xff;
-        code0 = code0 < MOD16_N_PFT ? code0 : MOD16_N_PFT;  // out of range: all-NaN column
-        code1 = code1 < MOD16_N_PFT ? code1 : MOD16_N_PFT;
+        code = (int)__ldg(a.pft + n);
+        code = code < MOD16_N_PFT ? code : MOD16_N_PFT;  // out of range: the all-NaN column
       }
-      const Arr<float>& ap = a.drv[MOD16_D_PRESSURE];
-      const Arr<float>& aa = a.drv[MOD16_D_TEMP_ANNUAL];
-      if (ap.ptr) p2 = __ldg(reinterpret_cast<const float2*>(ap.ptr + n0));
-      else p2 = make_float2(ap.scalar, ap.scalar);
-      if (aa.ptr) ta2 = __ldg(reinterpret_cast<const float2*>(aa.ptr + n0));
-      else ta2 = make_float2(aa.scalar, aa.scalar);
+      p = a.drv[MOD16_D_PRESSURE].at(0, n);   // per pixel or scalar (checked on the host)
+      ta = a.drv[MOD16_D_TEMP_ANNUAL].at(0, n);
     }
-    px = fast::pair_pix(fast::make_pix_const(p2.x, ta2.x, lut.pc[code0], SEM),
-                        fast::make_pix_const(p2.y, ta2.y, lut.pc[code1], SEM));
+    const PftConst c1 = lut.pc[code];
+    const PixConst x1 = fast::make_pix_const(p, ta, c1, SEM);
+    pc = fast::pair_pft(c1, c1);
+    px = fast::pair_pix(x1, x1);
   }
-  const fast::PftConstV<F2>& pc2 = plut.pp[code0][code1];
   const float swn_scalar = a.drv[MOD16_D_SW_RAD_NIGHT].scalar;
   const bool swn_array = n_arr == PIPE_MAX_ARR;
   const int gate = a.gate;
-  constexpr uint32_t ROWB = PIPE_TILE * sizeof(float);  // bytes per array row of a stage
   constexpr int n_out = OUT == 0 ? 1 : (OUT == 1 ? 2 : 6);
-  const uint32_t my0 = data0 + (uint32_t)tid * 8u;  // this thread's pair within a row
-  int64_t off = t0 * a.N + n0;                      // running output offset
+  const uint32_t my0 = data0 + (uint32_t)tid * 4u;  // this thread's pixel within a row
   const int64_t t_stride = a.N;
+  int64_t off = t0 * t_stride + n;                  // running output offset
   const bool warp_lead = (tid & 31) == 0;
   int stage = 0;
   uint32_t phase = 0;
 
 #pragma unroll 1
-  for (int i = 0; i < nsteps; ++i) {
+  for (int i = 0; i < niter; ++i) {
+    const bool two = nsteps - i * PIPE_SUB >= PIPE_SUB;  // (block-uniform) both steps exist
     mbar_wait(full0 + 8 * stage, phase);
-    // stage order == PipeSrc order (see launch_pipe).  The step's inputs are pulled into
-    // registers at once so that the stage can be re-filled while the step is evaluated.
+    // stage order == PipeSrc order (see launch_pipe).  The inputs are pulled into registers
+    // at once so that the stage can be re-filled while the steps are evaluated.  Lane x of
+    // every pair is step t, lane y is step t + 1 (step t again when the chunk is odd).
     fast::StepInV<F2> in;
     {
-      const uint32_t sp = my0 + (uint32_t)stage * stage_bytes;
-      in.lw_d = lds2(sp + 0 * ROWB);  in.lw_n = lds2(sp + 1 * ROWB);  in.sw_d = lds2(sp + 2 * ROWB);
-      in.alb = lds2(sp + 3 * ROWB);   in.t_d = lds2(sp + 4 * ROWB);   in.t_n = lds2(sp + 5 * ROWB);
-      in.tmin = lds2(sp + 6 * ROWB);  in.vpd_d = lds2(sp + 7 * ROWB); in.vpd_n = lds2(sp + 8 * ROWB);
-      in.fpar = lds2(sp + 9 * ROWB);  in.lai = lds2(sp + 10 * ROWB);
-      in.sw_n = swn_array ? lds2(sp + 11 * ROWB) : F2{swn_scalar, swn_scalar};
+      const uint32_t s0 = my0 + (uint32_t)stage * STAGEB;
+      const uint32_t s1 = two ? s0 + SUBB : s0;
+#define M16_IN(k) F2{lds1(s0 + (k) * ROWB), lds1(s1 + (k) * ROWB)}
+      in.lw_d = M16_IN(0);  in.lw_n = M16_IN(1);  in.sw_d = M16_IN(2);  in.alb = M16_IN(3);
+      in.t_d = M16_IN(4);   in.t_n = M16_IN(5);   in.tmin = M16_IN(6);  in.vpd_d = M16_IN(7);
+      in.vpd_n = M16_IN(8); in.fpar = M16_IN(9);  in.lai = M16_IN(10);
+      in.sw_n = swn_array ? M16_IN(11) : F2{swn_scalar, swn_scalar};
+#undef M16_IN
       in.rc_d = F2{0.f, 0.f}; in.rc_n = F2{0.f, 0.f};
     }
     __syncwarp();
-    if (warp_lead) {
-      // release the stage; the last of the eight warps to do so re-fills it (nobody waits)
-      __threadfence_block();
-      const int prior = atomicAdd(&released[stage], 1);
-      if (prior == PIPE_WARPS - 1) {
-        released[stage] = 0;
-        __threadfence_block();
-        if (i + PIPE_STAGES < nsteps)
-          pipe_issue(sptr, n_arr, data0 + (uint32_t)stage * stage_bytes, full0 + 8 * stage,
-                     (t0 + i + PIPE_STAGES) * a.N + tile0, row_bytes);
-      }
-    }
-    __syncwarp();
+    if (warp_lead) mbar_arrive(empty0 + 8 * stage);  // this warp has read the stage
     if (live) {
       fast::StepOutV<F2> r;
       M2 g_pos;
-      const M2 need = fast::step_fast<F2, SEM, false>(in, pc2, px, gate, r, g_pos);
+      M2 need = fast::step_fast<F2, SEM, false>(in, pc, px, gate, r, g_pos);
+      need.y = need.y && two;
       any_pos |= (g_pos.x && !need.x) || (g_pos.y && !need.y);
       F2 res[6];
       if (OUT == 0) {
@@ -439,12 +324,16 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
         res[3] = r.night.canopy; res[4] = r.night.soil; res[5] = r.night.trans;
       }
 #pragma unroll
-      for (int k = 0; k < n_out; ++k) st_stream2(a.out[k] + off, res[k]);
+      for (int k = 0; k < n_out; ++k) {
+        st_stream1(a.out[k] + off, res[k].x);
+        if (two) st_stream1(a.out[k] + off + t_stride, res[k].y);
+      }
       if (need.x || need.y)
-        any_pos |= fix_exact_vec4<SEM, OUT>(a, lut, t0 + i, n0, (need.x ? 1u : 0u) | (need.y ? 2u : 0u));
+        any_pos |= fix_exact_steps<SEM, OUT>(a, lut, t0 + (int64_t)i * PIPE_SUB, n,
+                                             (need.x ? 1u : 0u) | (need.y ? 2u : 0u));
     }
-    off += t_stride;
-    if (++stage == PIPE_STAGES) { stage = 0; phase ^= 1u; }
+    off += PIPE_SUB * t_stride;
+    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
   }
   if (a.track_gate) {
     if (__any_sync(0xffffffffu, any_pos) && (threadIdx.x & 31) == 0) *a.gate_flag = 1;
@@ -524,10 +413,11 @@ forward_strided_fast_kernel(const __grid_constant__ ForwardArgs<float> a) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// The vectorised kernel needs: N % 4 == 0; the eleven per-step drivers dense (T, N) and
-// 16-byte aligned; sw_rad_night a scalar or dense; pressure / temp_annual per pixel (or
-// scalar); parameters from the table (uniform or gathered by land cover); no r_corr_list.
-static bool vec4_ok(const ForwardArgs<float>& a) {
+// The pipelined kernel needs: N % 4 == 0 and 16-byte aligned bases (every bulk copy is a
+// multiple of 16 bytes at a 16-byte aligned address); the eleven per-step drivers dense
+// (T, N); sw_rad_night a scalar or dense; pressure / temp_annual per pixel (or scalar);
+// parameters from the table (uniform or gathered by land cover); no r_corr_list.
+static bool pipe_ok(const ForwardArgs<float>& a) {
   if (a.N % 4 != 0 || a.has_rc || a.par_mode == 2) return false;
   static const int per_step[] = {
       MOD16_D_LW_NET_DAY, MOD16_D_LW_NET_NIGHT, MOD16_D_SW_RAD_DAY, MOD16_D_SW_ALBEDO,
@@ -542,35 +432,14 @@ static bool vec4_ok(const ForwardArgs<float>& a) {
   if (sn.ptr && (sn.ns != 1 || !aligned16(sn.ptr) || (a.T > 1 && sn.ts != a.N))) return false;
   for (int k : {MOD16_D_PRESSURE, MOD16_D_TEMP_ANNUAL}) {
     const Arr<float>& d = a.drv[k];
-    if (d.ptr && (d.ts != 0 || d.ns != 1 || !aligned16(d.ptr))) return false;
+    if (d.ptr && (d.ts != 0 || d.ns != 1)) return false;
   }
-  if (a.par_mode == 1 && (reinterpret_cast<uintptr_t>(a.pft) & 3) != 0) return false;
-  for (int k = 0; k < 6; ++k)
-    if (a.out[k] && !aligned16(a.out[k])) return false;
   return true;
 }
 
 bool fast_f32_applicable(const ForwardArgs<float>& a, uint32_t flags) {
   (void)a; (void)flags;
-  return true;  // every layout has a fast-math kernel; vec4_ok() picks which
-}
-
-template <int SEM>
-static int launch_sem(const ForwardArgs<float>& a, uint32_t om, bool vec, dim3 grid,
-                      dim3 block, cudaStream_t st) {
-#define M16_LAUNCH(K, O) K<SEM, O><<<grid, block, 0, st>>>(a)
-  if (vec) {
-    if (om == MOD16_OUT_SUM) M16_LAUNCH(forward_vec4_kernel, 0);
-    else if (om == MOD16_OUT_DAY_NIGHT) M16_LAUNCH(forward_vec4_kernel, 1);
-    else M16_LAUNCH(forward_vec4_kernel, 2);
-  } else {
-    if (om == MOD16_OUT_SUM) M16_LAUNCH(forward_strided_fast_kernel, 0);
-    else if (om == MOD16_OUT_DAY_NIGHT) M16_LAUNCH(forward_strided_fast_kernel, 1);
-    else M16_LAUNCH(forward_strided_fast_kernel, 2);
-  }
-#undef M16_LAUNCH
-  M16_CUDA_CHECK(cudaGetLastError());
-  return MOD16_OK;
+  return true;  // every layout has a fast-math kernel; pipe_ok() picks which
 }
 
 template <int SEM, int OUT>
@@ -578,9 +447,9 @@ static int launch_pipe_one(const ForwardArgs<float>& a, const PipeSrc& src, dim3
                            size_t smem, cudaStream_t st) {
   static bool configured = false;  // per instantiation; the attribute is per function
   if (!configured) {
-    M16_CUDA_CHECK(cudaFuncSetAttribute(forward_pipe_kernel<SEM, OUT>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        PIPE_STAGES * PIPE_MAX_ARR * PIPE_TILE * (int)sizeof(float)));
+    M16_CUDA_CHECK(cudaFuncSetAttribute(
+        forward_pipe_kernel<SEM, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PIPE_STAGES * PIPE_SUB * (PIPE_MAX_ARR - 1) * PIPE_TILE * (int)sizeof(float)));
     configured = true;
   }
   forward_pipe_kernel<SEM, OUT><<<grid, PIPE_THREADS, smem, st>>>(a, src);
@@ -588,9 +457,9 @@ static int launch_pipe_one(const ForwardArgs<float>& a, const PipeSrc& src, dim3
   return MOD16_OK;
 }
 
-// Grid of the pipelined kernel: one block per 1024-pixel tile and time chunk; the chunk is
-// as long as possible (the per-block LUT staging is amortised over it) while the grid
-// still holds several waves of 148 SMs x 2 resident blocks.
+// Grid of the pipelined kernel: one block per 480-pixel tile and time chunk; the chunk is
+// as long as possible (the per-block set-up is amortised over it) while the grid still
+// holds several waves of 148 SMs x 1 resident block.
 static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
   static const int order[] = {
       MOD16_D_LW_NET_DAY, MOD16_D_LW_NET_NIGHT, MOD16_D_SW_RAD_DAY, MOD16_D_SW_ALBEDO,
@@ -601,15 +470,17 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
   for (int k = 0; k < PIPE_MAX_ARR; ++k) src.ptr[k] = k < src.n_arr ? a.drv[order[k]].ptr : nullptr;
   const int64_t bx = (a.N + PIPE_TILE - 1) / PIPE_TILE;
   if (bx > 2147483647LL) return MOD16_ERR_SHAPE;
-  int64_t want_rows = (148 * 2 * 6 + bx - 1) / bx;
+  int64_t want_rows = (148 * 6 + bx - 1) / bx;
   if (want_rows < 1) want_rows = 1;
   int64_t chunk = (a.T + want_rows - 1) / want_rows;
   if (chunk < 8) chunk = a.T < 8 ? a.T : 8;
+  chunk += chunk & 1;  // even chunks: only the last one may end on a single step
   int64_t by = (a.T + chunk - 1) / chunk;
   while (by > 65535) { chunk *= 2; by = (a.T + chunk - 1) / chunk; }
   a.t_chunk = (int)chunk;
   dim3 grid((unsigned)bx, (unsigned)by);
-  const size_t smem = (size_t)PIPE_STAGES * src.n_arr * PIPE_TILE * sizeof(float);
+  src.n_stages = src.n_arr == PIPE_MAX_ARR ? PIPE_STAGES - 1 : PIPE_STAGES;
+  const size_t smem = (size_t)src.n_stages * PIPE_SUB * src.n_arr * PIPE_TILE * sizeof(float);
   const uint32_t om = flags & MOD16_OUT_MASK;
   const bool is_static = (flags & MOD16_SEM_MASK) == MOD16_SEM_STATIC;
 #define M16_PIPE(S, O) return launch_pipe_one<S, O>(a, src, grid, smem, st)
@@ -624,13 +495,21 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
 #undef M16_PIPE
 }
 
+template <int SEM>
+static int launch_strided_sem(const ForwardArgs<float>& a, uint32_t om, dim3 grid, dim3 block,
+                              cudaStream_t st) {
+  if (om == MOD16_OUT_SUM) forward_strided_fast_kernel<SEM, 0><<<grid, block, 0, st>>>(a);
+  else if (om == MOD16_OUT_DAY_NIGHT) forward_strided_fast_kernel<SEM, 1><<<grid, block, 0, st>>>(a);
+  else forward_strided_fast_kernel<SEM, 2><<<grid, block, 0, st>>>(a);
+  M16_CUDA_CHECK(cudaGetLastError());
+  return MOD16_OK;
+}
+
 int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
   if (a.T == 0 || a.N == 0) return MOD16_OK;
-  const bool vec = !(flags & MOD16_FORCE_GENERIC) && vec4_ok(a);
-  if (vec && !(flags & MOD16_FORCE_DIRECT)) return launch_pipe(a, flags, st);
-  const int threads = vec ? VEC4_THREADS : 256;
-  const int64_t cols = vec ? a.N / 4 : a.N;
-  const int64_t bx = (cols + threads - 1) / threads;
+  if (!(flags & MOD16_FORCE_GENERIC) && pipe_ok(a)) return launch_pipe(a, flags, st);
+  const int threads = 256;
+  const int64_t bx = (a.N + threads - 1) / threads;
   if (bx > 2147483647LL) return MOD16_ERR_SHAPE;
   // Block rows: split time so that the grid is several waves of 148 SMs x resident blocks
   // while each thread amortises its per-pixel setup over a run of time steps.
@@ -645,8 +524,8 @@ int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
   dim3 grid((unsigned)bx, (unsigned)by), block(threads);
   const uint32_t om = flags & MOD16_OUT_MASK;
   if ((flags & MOD16_SEM_MASK) == MOD16_SEM_STATIC)
-    return launch_sem<SEM_STATIC>(a, om, vec, grid, block, st);
-  return launch_sem<SEM_INSTANCE>(a, om, vec, grid, block, st);
+    return launch_strided_sem<SEM_STATIC>(a, om, grid, block, st);
+  return launch_strided_sem<SEM_INSTANCE>(a, om, grid, block, st);
 }
 
 }  // namespace mod16

@@ -16,8 +16,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarri
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+#ifndef WAITMODE
+#define WAITMODE 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if WAITMODE == 0
   asm volatile("{\n.reg .pred p;\nW:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D;\nbra W;\nD:\n}" ::"r"(bar), "r"(parity) : "memory");
+#elif WAITMODE == 1   // suspend-time hint (ns)
+  asm volatile("{\n.reg .pred p;\nW:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n@p bra D;\nbra W;\nD:\n}" ::"r"(bar), "r"(parity), "r"(20000u) : "memory");
+#else                 // test_wait + nanosleep back-off
+  asm volatile("{\n.reg .pred p;\nW:\nmbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D;\nnanosleep.u32 200;\nbra W;\nD:\n}" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 
 // MODE 0: thread 0 of warp 0 is consumer + producer (as forward_pipe_kernel r01)
@@ -27,13 +36,14 @@ __global__ void __launch_bounds__(THREADS + (MODE == 1 ? 32 : 0))
 pipe(Src src, float* out, int64_t N, int T) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+  __shared__ int released[STAGES];
   const int tid = threadIdx.x;
   const int64_t tile0 = (int64_t)blockIdx.x * TILE;
   constexpr uint32_t ROWB = TILE * 4, STAGEB = ROWB * NARR;
   const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), data0 = smem_u32(smem);
   constexpr int CW = THREADS / 32;
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CW); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CW); released[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -53,27 +63,51 @@ pipe(Src src, float* out, int64_t N, int T) {
     }
     return;
   }
-  if (MODE == 0 && tid == 0) for (int s = 0; s < STAGES && s < T; ++s) issue(s, s);
+  if (MODE != 1 && MODE != 3 && tid == 0) for (int s = 0; s < STAGES && s < T; ++s) issue(s, s);
   float acc = 0.f;
   constexpr int PER = TILE / THREADS;  // floats per thread per row
   for (int i = 0; i < T; ++i) {
     const int s = i % STAGES;
     const uint32_t ph = (i / STAGES) & 1;
-    mbar_wait(full0 + 8 * s, ph);
+    if (MODE != 3) mbar_wait(full0 + 8 * s, ph);
     const float* sp = reinterpret_cast<const float*>(smem + s * STAGEB) + tid * PER;
 #pragma unroll
     for (int k = 0; k < NARR; ++k)
 #pragma unroll
       for (int j = 0; j < PER; ++j) acc += sp[k * TILE + j];
-    // synthetic compute: WORK dependent FMAs per element pair
-#pragma unroll 1
-    for (int w = 0; w < WORK; ++w) acc = fmaf(acc, 1.0000001f, 1e-9f);
-    __syncwarp();
-    if ((tid & 31) == 0) {
-      mbar_arrive(empty0 + 8 * s);
-      if (MODE == 0 && tid == 0 && i + STAGES < T) { mbar_wait(empty0 + 8 * s, ph); issue(s, i + STAGES); }
+    if (MODE == 2) {  // release at once; the last warp to release re-fills
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        __threadfence_block();
+        if (atomicAdd(&released[s], 1) == CW - 1) {
+          released[s] = 0;
+          __threadfence_block();
+          if (i + STAGES < T) issue(s, i + STAGES);
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
+    // synthetic compute: WORK issue-bound FMAs (8 independent chains) per thread and step
+    {
+      float c[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c[j] = acc + j;
+#pragma unroll 1
+      for (int w = 0; w < WORK / 8; ++w) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = fmaf(c[j], 1.0000001f, 1e-9f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += c[j];
+    }
+    if (MODE != 2 && MODE != 3) {
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        mbar_arrive(empty0 + 8 * s);
+        if (MODE == 0 && tid == 0 && i + STAGES < T) { mbar_wait(empty0 + 8 * s, ph); issue(s, i + STAGES); }
+      }
+      __syncwarp();
+    }
   }
   out[(int64_t)blockIdx.x * THREADS + tid] = acc;
 }
@@ -102,18 +136,13 @@ int main() {
   Src src; float* out;
   for (int k = 0; k < NARR; ++k) { float* p; cudaMalloc(&p, N * T * 4); cudaMemset(p, 0, N * T * 4); src.p[k] = p; }
   cudaMalloc(&out, 64 << 20);
-  run<512, 4, 256, 0, 0>("tile512 st4 mode0 work0", src, out, N, T);
-  run<512, 4, 256, 0, 400>("tile512 st4 mode0 work400", src, out, N, T);
-  run<512, 4, 256, 1, 0>("tile512 st4 mode1 work0", src, out, N, T);
+  run<512, 4, 256, 3, 400>("tile512 st4 COMPUTE ONLY work400", src, out, N, T);
+  run<512, 4, 256, 3, 600>("tile512 st4 COMPUTE ONLY work600", src, out, N, T);
   run<512, 4, 256, 1, 400>("tile512 st4 mode1 work400", src, out, N, T);
-  run<512, 3, 256, 0, 0>("tile512 st3 mode0 work0", src, out, N, T);
-  run<512, 2, 256, 0, 0>("tile512 st2 mode0 work0", src, out, N, T);
-  run<1024, 2, 256, 0, 0>("tile1024 st2 mode0 work0", src, out, N, T);
-  run<1024, 2, 256, 0, 400>("tile1024 st2 mode0 work400", src, out, N, T);
-  run<1024, 2, 256, 1, 400>("tile1024 st2 mode1 work400", src, out, N, T);
-  run<256, 8, 128, 0, 0>("tile256 st8 t128 mode0 work0", src, out, N, T);
-  run<256, 4, 128, 0, 400>("tile256 st4 t128 mode0 work400", src, out, N, T);
-  run<256, 4, 128, 1, 400>("tile256 st4 t128 mode1 work400", src, out, N, T);
-  run<2048, 2, 512, 0, 0>("tile2048 st2 t512 mode0 work0", src, out, N, T);
+  run<512, 4, 256, 1, 600>("tile512 st4 mode1 work600", src, out, N, T);
+  run<512, 4, 256, 2, 400>("tile512 st4 mode2 work400", src, out, N, T);
+  run<512, 3, 256, 1, 400>("tile512 st3 mode1 work400 occ3", src, out, N, T);
+  run<1024, 4, 512, 1, 400>("tile1024 st4 t512 mode1 work400", src, out, N, T);
+  run<256, 4, 128, 1, 400>("tile256 st4 t128 mode1 work400 occ5", src, out, N, T);
   return 0;
 }
