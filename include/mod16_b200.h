@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 1
+#define MOD16_ABI_VERSION 2
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -124,9 +124,16 @@ typedef struct mod16_params {
 typedef struct mod16_out {
   void* out[6];       /* device (T, N) row-major, dense; see MOD16_OUT_* */
   int32_t* gate_flag; /* device int; required by GATE_GLOBAL / OPEN_TRACK / FIXUP */
+  /* Optional device scratch of the float32 path (8-byte aligned, mod16_workspace_bytes()
+     recommended): the rare elements that must be re-evaluated in double precision are
+     queued here and evaluated by a second, tiny launch.  NULL / too small: they are
+     evaluated inside the main kernel (same results, slower).  Contents are scratch. */
+  void* workspace;
+  int64_t workspace_bytes;
 } mod16_out_t;
 
 int mod16_abi_version(void);
+int64_t mod16_workspace_bytes(void); /* recommended size of mod16_out_t.workspace */
 int mod16_last_cuda_error(void);
 const char* mod16_error_string(int code);
 

@@ -19,7 +19,7 @@ FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                         'libmod16_b200.so')
 
@@ -42,7 +42,8 @@ class Params(ctypes.Structure):
 
 
 class Out(ctypes.Structure):
-    _fields_ = [('out', ctypes.c_void_p * 6), ('gate_flag', ctypes.c_void_p)]
+    _fields_ = [('out', ctypes.c_void_p * 6), ('gate_flag', ctypes.c_void_p),
+                ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_int64)]
 
 
 class Mod16Error(RuntimeError):
@@ -55,6 +56,7 @@ _lib = None
 # against the header and the built library
 EXPORTS = {
     'mod16_abi_version': (ctypes.c_int, []),
+    'mod16_workspace_bytes': (ctypes.c_int64, []),
     'mod16_last_cuda_error': (ctypes.c_int, []),
     'mod16_error_string': (ctypes.c_char_p, [ctypes.c_int]),
     'mod16_forward_f32': (ctypes.c_int, [

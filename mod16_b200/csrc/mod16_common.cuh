@@ -46,6 +46,8 @@ struct ForwardArgs {
   // outputs
   R* out[6];
   int* gate_flag;
+  unsigned long long* redo_ws;  // [0] = count, [1 ..] = queued linear indices t * N + n
+  long long redo_cap;           // entries the queue can hold (0: no queue)
   int skip_if_flag;  // fix-up launch: return at once when *gate_flag != 0
   int track_gate;    // OR (g_surf > 0) into *gate_flag
   int gate;          // mod16::Gate

@@ -111,6 +111,13 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
     if (k < n_out && !a.out[k] && T * N > 0) return MOD16_ERR_NULL;
   }
   a.gate_flag = out->gate_flag;
+  a.redo_ws = nullptr;
+  a.redo_cap = 0;
+  if (out->workspace && out->workspace_bytes >= 16 &&
+      (reinterpret_cast<uintptr_t>(out->workspace) & 7) == 0) {
+    a.redo_ws = (unsigned long long*)out->workspace;
+    a.redo_cap = out->workspace_bytes / 8 - 1;
+  }
   const bool needs_flag = sem == MOD16_SEM_STATIC &&
                           (gm == MOD16_GATE_GLOBAL || gm == MOD16_GATE_OPEN_TRACK ||
                            gm == MOD16_GATE_FIXUP);
@@ -208,6 +215,7 @@ template int build_forward_args<double>(const mod16_drivers_t*, const mod16_para
 extern "C" {
 
 int mod16_abi_version(void) { return MOD16_ABI_VERSION; }
+int64_t mod16_workspace_bytes(void) { return (int64_t)8 << 20; }
 int mod16_last_cuda_error(void) { return mod16::g_last_cuda_error; }
 
 const char* mod16_error_string(int code) {

@@ -46,15 +46,13 @@ __device__ __forceinline__ void stage_lut(const ForwardArgs<float>& a, SharedLut
   __syncthreads();
 }
 
-// Deferred exact re-evaluation of the elements that step_fast() flagged: element j of
-// `mask` is pixel n at time step t + j.  Out of line and self-contained (re-reads its
-// inputs from global memory, which the fast pass has just pulled through L2), so that the
-// double-precision code costs the hot loop no registers.  Returns the gate predicate OR-ed
-// over the re-evaluated elements.
+// Exact re-evaluation of ONE element that step_fast() flagged (pixel n, time step t).  Out
+// of line and self-contained (re-reads its inputs from global memory, which the fast pass
+// has just pulled through L2), so that the double-precision code costs the hot loop no
+// registers.  Returns the gate predicate of the element.
 template <int SEM, int OUT>
-__device__ __noinline__ bool fix_exact_steps(const ForwardArgs<float>& a, const SharedLut& lut,
-                                             int64_t t, int64_t n, unsigned mask) {
-  bool any_pos = false;
+__device__ __noinline__ bool fix_exact_one(const ForwardArgs<float>& a, const SharedLut& lut,
+                                           int64_t t, int64_t n) {
   int code = 0;
   if (a.par_mode == 1) {
     code = (int)__ldg(a.pft + n);
@@ -62,40 +60,36 @@ __device__ __noinline__ bool fix_exact_steps(const ForwardArgs<float>& a, const 
   }
   double col[MOD16_N_PARAMS];
   for (int k = 0; k < MOD16_N_PARAMS; ++k) col[k] = lut.tab[k][code];
-  for (int j = 0; j < 2; ++j, ++t) {
-    if (!((mask >> j) & 1u)) continue;
-    StepIn in;
-    in.lw_d = a.drv[MOD16_D_LW_NET_DAY].at(t, n);
-    in.lw_n = a.drv[MOD16_D_LW_NET_NIGHT].at(t, n);
-    in.sw_d = a.drv[MOD16_D_SW_RAD_DAY].at(t, n);
-    in.sw_n = a.drv[MOD16_D_SW_RAD_NIGHT].at(t, n);
-    in.alb = a.drv[MOD16_D_SW_ALBEDO].at(t, n);
-    in.t_d = a.drv[MOD16_D_TEMP_DAY].at(t, n);
-    in.t_n = a.drv[MOD16_D_TEMP_NIGHT].at(t, n);
-    in.t_ann = a.drv[MOD16_D_TEMP_ANNUAL].at(t, n);
-    in.tmin = a.drv[MOD16_D_TMIN].at(t, n);
-    in.vpd_d = a.drv[MOD16_D_VPD_DAY].at(t, n);
-    in.vpd_n = a.drv[MOD16_D_VPD_NIGHT].at(t, n);
-    in.p = a.drv[MOD16_D_PRESSURE].at(t, n);
-    in.fpar = a.drv[MOD16_D_FPAR].at(t, n);
-    in.lai = a.drv[MOD16_D_LAI].at(t, n);
-    in.rc_d = 0.0f; in.rc_n = 0.0f;
-    fast::StepOut r;
-    bool g_pos;
-    fast::pixel_step_exact<SEM>(in, col, false, a.gate, r, g_pos);
-    any_pos |= g_pos;
-    const int64_t o = t * a.N + n;
-    if (OUT == 0) {
-      a.out[0][o] = r.tot;
-    } else if (OUT == 1) {
-      a.out[0][o] = r.tot_day;
-      a.out[1][o] = r.tot_night;
-    } else {
-      a.out[0][o] = r.day.canopy;   a.out[1][o] = r.day.soil;   a.out[2][o] = r.day.trans;
-      a.out[3][o] = r.night.canopy; a.out[4][o] = r.night.soil; a.out[5][o] = r.night.trans;
-    }
+  StepIn in;
+  in.lw_d = a.drv[MOD16_D_LW_NET_DAY].at(t, n);
+  in.lw_n = a.drv[MOD16_D_LW_NET_NIGHT].at(t, n);
+  in.sw_d = a.drv[MOD16_D_SW_RAD_DAY].at(t, n);
+  in.sw_n = a.drv[MOD16_D_SW_RAD_NIGHT].at(t, n);
+  in.alb = a.drv[MOD16_D_SW_ALBEDO].at(t, n);
+  in.t_d = a.drv[MOD16_D_TEMP_DAY].at(t, n);
+  in.t_n = a.drv[MOD16_D_TEMP_NIGHT].at(t, n);
+  in.t_ann = a.drv[MOD16_D_TEMP_ANNUAL].at(t, n);
+  in.tmin = a.drv[MOD16_D_TMIN].at(t, n);
+  in.vpd_d = a.drv[MOD16_D_VPD_DAY].at(t, n);
+  in.vpd_n = a.drv[MOD16_D_VPD_NIGHT].at(t, n);
+  in.p = a.drv[MOD16_D_PRESSURE].at(t, n);
+  in.fpar = a.drv[MOD16_D_FPAR].at(t, n);
+  in.lai = a.drv[MOD16_D_LAI].at(t, n);
+  in.rc_d = 0.0f; in.rc_n = 0.0f;
+  fast::StepOut r;
+  bool g_pos;
+  fast::pixel_step_exact<SEM>(in, col, false, a.gate, r, g_pos);
+  const int64_t o = t * a.N + n;
+  if (OUT == 0) {
+    a.out[0][o] = r.tot;
+  } else if (OUT == 1) {
+    a.out[0][o] = r.tot_day;
+    a.out[1][o] = r.tot_night;
+  } else {
+    a.out[0][o] = r.day.canopy;   a.out[1][o] = r.day.soil;   a.out[2][o] = r.day.trans;
+    a.out[3][o] = r.night.canopy; a.out[4][o] = r.night.soil; a.out[5][o] = r.night.trans;
   }
-  return any_pos;
+  return g_pos;
 }
 
 // ---- forward_pipe_kernel ------------------------------------------------------------------
@@ -110,6 +104,10 @@ __device__ __noinline__ bool fix_exact_steps(const ForwardArgs<float>& a, const 
 // instead of by registers, there is no block-wide barrier, no table gather and no address
 // arithmetic in the time loop, and issuing the copies costs the consumers nothing
 // (measured alternatives: profiles/r01_pipebench.txt and DESIGN.md).
+// Elements that need the double-precision code are not evaluated in the loop -- one such
+// element would hold its warp for ~20 us and, through the ring, the whole block -- but
+// queued and evaluated afterwards, one element per thread: by redo_queue_kernel when the
+// caller supplied a workspace, else by this block after its loop.
 constexpr int PIPE_CONSUMER_WARPS = 15;
 constexpr int PIPE_CONSUMERS = PIPE_CONSUMER_WARPS * 32;
 constexpr int PIPE_THREADS = PIPE_CONSUMERS + 32;
@@ -117,6 +115,7 @@ constexpr int PIPE_TILE = PIPE_CONSUMERS;  // pixels per block
 constexpr int PIPE_SUB = 2;                // time steps per stage (the two FFMA2 lanes)
 constexpr int PIPE_STAGES = 5;
 constexpr int PIPE_MAX_ARR = 12;
+constexpr int PIPE_QCAP = 2048;            // deferred exact re-evaluations per block
 
 // (all barrier / stage addresses are 32-bit shared-window addresses, computed once)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -205,6 +204,8 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ SharedLut lut;
   __shared__ __align__(8) uint64_t full[PIPE_STAGES], empty[PIPE_STAGES];
+  __shared__ uint32_t redo_q[PIPE_QCAP];  // (step within the chunk) << 9 | consumer thread
+  __shared__ int redo_n;
   if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
   const int tid = threadIdx.x;
   const int n_arr = src.n_arr;
@@ -231,6 +232,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
         mbar_init(empty0 + 8 * s, PIPE_CONSUMER_WARPS);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      redo_n = 0;
     }
     __syncwarp();
     for (int s = 0; s < n_stages && s < niter; ++s)
@@ -325,15 +327,41 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       }
 #pragma unroll
       for (int k = 0; k < n_out; ++k) {
-        st_stream1(a.out[k] + off, res[k].x);
-        if (two) st_stream1(a.out[k] + off + t_stride, res[k].y);
+        if (!need.x) st_stream1(a.out[k] + off, res[k].x);
+        if (two && !need.y) st_stream1(a.out[k] + off + t_stride, res[k].y);
       }
-      if (need.x || need.y)
-        any_pos |= fix_exact_steps<SEM, OUT>(a, lut, t0 + (int64_t)i * PIPE_SUB, n,
-                                             (need.x ? 1u : 0u) | (need.y ? 2u : 0u));
+      if (need.x || need.y) {  // rare: queue for the double-precision pass after the loop
+#pragma unroll
+        for (int j = 0; j < PIPE_SUB; ++j) {
+          if (j == 0 ? need.x : need.y) {
+            const int64_t t = t0 + i * PIPE_SUB + j;
+            bool queued = false;
+            if (a.redo_cap > 0) {  // global queue, evaluated by redo_queue_kernel
+              const unsigned long long slot = atomicAdd(a.redo_ws, 1ULL);
+              queued = slot < (unsigned long long)a.redo_cap;
+              if (queued) a.redo_ws[1 + slot] = (unsigned long long)(t * a.N + n);
+            } else {               // no workspace: block-local queue, evaluated after the loop
+              const int slot = atomicAdd(&redo_n, 1);
+              queued = slot < PIPE_QCAP;
+              if (queued) redo_q[slot] = (uint32_t)(i * PIPE_SUB + j) << 9 | (uint32_t)tid;
+            }
+            // queue full (fill-heavy data): evaluate in place
+            if (!queued) any_pos |= fix_exact_one<SEM, OUT>(a, lut, t, n);
+          }
+        }
+      }
     }
     off += PIPE_SUB * t_stride;
     if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+  }
+  // the block-local deferred pass: consumers only (named barrier 1), one element each
+  if (a.redo_cap == 0) {
+    asm volatile("bar.sync 1, %0;" ::"n"(PIPE_CONSUMERS) : "memory");
+    const int total = redo_n < PIPE_QCAP ? redo_n : PIPE_QCAP;
+    for (int e = tid; e < total; e += PIPE_CONSUMERS) {
+      const uint32_t q = redo_q[e];
+      any_pos |= fix_exact_one<SEM, OUT>(a, lut, t0 + (int64_t)(q >> 9), tile0 + (q & 511u));
+    }
   }
   if (a.track_gate) {
     if (__any_sync(0xffffffffu, any_pos) && (threadIdx.x & 31) == 0) *a.gate_flag = 1;
@@ -411,6 +439,27 @@ forward_strided_fast_kernel(const __grid_constant__ ForwardArgs<float> a) {
   }
 }
 
+// Second, tiny launch of the float32 path: evaluates the queued elements in double.
+template <int SEM, int OUT>
+__global__ void __launch_bounds__(128)
+redo_queue_kernel(const __grid_constant__ ForwardArgs<float> a) {
+  __shared__ SharedLut lut;
+  if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
+  unsigned long long cnt = a.redo_ws[0];
+  if (cnt == 0) return;
+  if (cnt > (unsigned long long)a.redo_cap) cnt = (unsigned long long)a.redo_cap;
+  stage_lut<SEM>(a, lut);
+  bool any_pos = false;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    const long long idx = (long long)a.redo_ws[1 + e];
+    any_pos |= fix_exact_one<SEM, OUT>(a, lut, idx / a.N, idx % a.N);
+  }
+  if (a.track_gate) {
+    if (__any_sync(0xffffffffu, any_pos) && (threadIdx.x & 31) == 0) *a.gate_flag = 1;
+  }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // The pipelined kernel needs: N % 4 == 0 and 16-byte aligned bases (every bulk copy is a
@@ -452,8 +501,13 @@ static int launch_pipe_one(const ForwardArgs<float>& a, const PipeSrc& src, dim3
         PIPE_STAGES * PIPE_SUB * (PIPE_MAX_ARR - 1) * PIPE_TILE * (int)sizeof(float)));
     configured = true;
   }
+  if (a.redo_cap > 0) M16_CUDA_CHECK(cudaMemsetAsync(a.redo_ws, 0, 8, st));
   forward_pipe_kernel<SEM, OUT><<<grid, PIPE_THREADS, smem, st>>>(a, src);
   M16_CUDA_CHECK(cudaGetLastError());
+  if (a.redo_cap > 0) {
+    redo_queue_kernel<SEM, OUT><<<148 * 2, 128, 0, st>>>(a);
+    M16_CUDA_CHECK(cudaGetLastError());
+  }
   return MOD16_OK;
 }
 

@@ -131,6 +131,22 @@ class _Staged(object):
         slot.scalar = 0.0
 
 
+_WORKSPACES = {}
+
+
+def _workspace(dev, stream_handle, lib):
+    '''
+    Per-device, per-stream scratch of the float32 path (the queue of elements re-evaluated in
+    double precision).  Cached: calls on one stream are ordered, so they can share it.
+    '''
+    key = (dev.index, stream_handle)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        ws = torch.empty(lib.mod16_workspace_bytes() // 8, device=dev, dtype=torch.int64)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def _view_2d(shape):
     'Maps a broadcast result shape onto the kernels\' (T, N) view.'
     if len(shape) == 0:
@@ -145,7 +161,8 @@ def _view_2d(shape):
 
 def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static',
                 out_mode='sum', gate='global', dtype=None, r_corr_list=None, device=None,
-                stream=None, force=0, as_torch=None, gate_flag=None, out=None):
+                stream=None, force=0, as_torch=None, gate_flag=None, out=None,
+                workspace=None):
     '''
     Launches K1 once.
 
@@ -157,6 +174,8 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     gate     : 'global' (reference) | 'element' | 'open' | 'closed' | 'open_track' | 'fixup'
 
     out      : optional list of preallocated CUDA tensors ((T, N), contiguous) to write into
+    workspace : optional int64 CUDA tensor, scratch of the float32 path (default: a cached
+               per-device, per-stream buffer of ``mod16_workspace_bytes()``)
 
     Returns a list of 1, 2 or 6 arrays of the broadcast shape (numpy, unless an input was
     a CUDA tensor or ``as_torch`` is set).
@@ -250,6 +269,11 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
         co.gate_flag = gate_flag.data_ptr()
         s = stream if stream is not None else torch.cuda.current_stream(dev)
         handle = s.cuda_stream if hasattr(s, 'cuda_stream') else int(s)
+        if np_dtype == np.dtype('float32'):
+            ws = workspace if workspace is not None else _workspace(dev, handle, lib)
+            co.workspace = ws.data_ptr()
+            co.workspace_bytes = ws.numel() * ws.element_size()
+            st.keep.append(ws)
         fn = lib.mod16_forward_f32 if np_dtype == np.dtype('float32') else lib.mod16_forward_f64
         _abi.check(fn(ctypes.byref(cd), ctypes.byref(cp), ctypes.byref(co), T, N, flags,
                       ctypes.c_void_p(handle)))
