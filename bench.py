@@ -256,7 +256,10 @@ def main():
     drv_list = [drv[k] for k in synthetic.DRIVER_NAMES]
     out = torch.empty((T, N), device=device, dtype=t_dtype)
     flag = torch.zeros(1, device=device, dtype=torch.int32)
-    launches_per_step = 2 if args.gate == 'global' else 1   # forward kernel (+ gate fix-up)
+    # per `_et` call: forward kernel + redo-queue kernel (f32 pipeline), twice when the call-exact
+    # global gate adds its fix-up pass
+    launches_per_step = ((2 if (np_dtype == np.float32 and args.kernel == 'pipe') else 1) *
+                         (2 if args.gate == 'global' else 1))
 
     force = {'pipe': 0, 'generic': _abi.FORCE_GENERIC,
              'mirror': _abi.FORCE_MIRROR}[args.kernel]
@@ -300,6 +303,16 @@ def main():
     kernel_ms = float(np.mean(step_ms))
     achieved = bytes_per_unit * units_per_rank / (kernel_ms * 1e-3) / 1e9
 
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
+    # (bytes per pixel-timestep x the units of one launch), see profiles/traffic.json
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    kname = ('forward_pipe_kernel' if args.kernel == 'pipe' else args.kernel) \
+        if np_dtype == np.float32 else 'forward_strided_kernel<double>'
+    if os.path.exists(tpath):
+        rec = json.load(open(tpath)).get(kname)
+        if rec:
+            traffic = rec['dram_bytes_per_unit'] * units_per_rank
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json)'
@@ -363,7 +376,7 @@ def main():
                        'l2': 'inputs (%.1f GB per GPU) exceed L2 (126 MB); no flush needed' % (
                            bytes_per_unit * units_per_rank / 1e9)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                         'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'kernel': {'pipe': 'forward_pipe_kernel',
                                     'generic': 'forward_strided_fast_kernel',
                                     'mirror': 'forward_strided_kernel<float>'}[args.kernel]
