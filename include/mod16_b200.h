@@ -145,6 +145,31 @@ int mod16_forward_f64(const mod16_drivers_t* drivers, const mod16_params_t* para
                       const mod16_out_t* out, int64_t T, int64_t N, uint32_t flags,
                       void* stream);
 
+/* K3 -- per-pixel time aggregates (annual sums of the calibration's precipitation
+ * constraint, mod16/calibration.py:783-790: mass = x * 86400 / lhv, negatives dropped,
+ * summed per year).  term(t, n) = x * scale / divisor (divisor NULL: x * scale);
+ * out[g][n] = sum of the terms of the steps whose group index is g; total[g] = sum over n.
+ * Accumulation is in double; NaN terms propagate like numpy's sum unless SKIP_NAN. */
+#define MOD16_AGG_CLAMP_NEG 0x1u /* negative terms count as 0 (calibration.py:784) */
+#define MOD16_AGG_SKIP_NAN 0x2u  /* NaN terms count as 0 (nansum) */
+
+typedef struct mod16_aggregate {
+  const void* x;        /* device (T, N) dense, float / double as the entry */
+  const void* divisor;  /* device (T, N) dense, or NULL */
+  double scale;
+  const int32_t* group; /* device (T,): group of each step, outside [0, n_groups) = skipped;
+                           NULL: one group */
+  int32_t n_groups;
+  int32_t reserved;
+  double* out;          /* device (n_groups, N), overwritten */
+  double* total;        /* device (n_groups,), overwritten; or NULL */
+} mod16_aggregate_t;
+
+int mod16_time_aggregate_f32(const mod16_aggregate_t* agg, int64_t T, int64_t N, uint32_t flags,
+                             void* stream);
+int mod16_time_aggregate_f64(const mod16_aggregate_t* agg, int64_t T, int64_t N, uint32_t flags,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

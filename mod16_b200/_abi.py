@@ -46,6 +46,16 @@ class Out(ctypes.Structure):
                 ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_int64)]
 
 
+class Aggregate(ctypes.Structure):
+    _fields_ = [('x', ctypes.c_void_p), ('divisor', ctypes.c_void_p), ('scale', ctypes.c_double),
+                ('group', ctypes.c_void_p), ('n_groups', ctypes.c_int32),
+                ('reserved', ctypes.c_int32), ('out', ctypes.c_void_p),
+                ('total', ctypes.c_void_p)]
+
+
+AGG_CLAMP_NEG, AGG_SKIP_NAN = 0x1, 0x2
+
+
 class Mod16Error(RuntimeError):
     pass
 
@@ -65,6 +75,12 @@ EXPORTS = {
     'mod16_forward_f64': (ctypes.c_int, [
         ctypes.POINTER(Drivers), ctypes.POINTER(Params), ctypes.POINTER(Out),
         ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p]),
+    'mod16_time_aggregate_f32': (ctypes.c_int, [
+        ctypes.POINTER(Aggregate), ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32,
+        ctypes.c_void_p]),
+    'mod16_time_aggregate_f64': (ctypes.c_int, [
+        ctypes.POINTER(Aggregate), ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32,
+        ctypes.c_void_p]),
 }
 
 

@@ -256,6 +256,8 @@ def static_evapotranspiration(
             t = np.where(g_surf > 0, t_open, 0)
         elif gate == 'open':
             t = t_open
+        elif gate == 'closed':
+            t = 0
         else:
             raise ValueError(gate)
 
@@ -486,3 +488,20 @@ def nse_from_stats(sse, obs, norm=True):
     o = obs[~np.isnan(obs)]
     nse = 1 - sse / np.sum((o - o.mean())**2)
     return 1 / (2 - nse) if norm else nse
+
+
+# --------------------------------------------------------------------------
+# Annual sums of the calibration's precipitation constraint
+# --------------------------------------------------------------------------
+
+def annual_mass_sums(pred_le, years, lhv_arr):
+    '''
+    (Y, N) annual evapotranspiration [mm] from (T, N) latent heat flux [W m-2]:
+    the first half of `constrain_by_map` (mod16/calibration.py:783-790).
+    '''
+    mass_rate = (pred_le * 60 * 60 * 24) / lhv_arr
+    mass_rate[mass_rate < 0] = 0
+    annual = []
+    for y in np.unique(years):
+        annual.append(np.apply_along_axis(lambda x: x.sum(), 0, mass_rate[years == y]))
+    return np.stack(annual, axis=0)

@@ -1,0 +1,71 @@
+'''
+GPU parity tests of K3 (per-pixel time aggregates) against the oracle's restatement of the
+calibration's annual sums (reference mod16/calibration.py:783-790).
+'''
+import numpy as np
+import pytest
+import torch
+
+from mod16_b200 import aggregate, synthetic
+from oracle import mod16_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('T,N', [(730, 317), (366, 4096 + 3), (5, 1)])
+def test_annual_mass_sums_like_constrain_by_map(cuda_lib, dtype, T, N):
+    rng = np.random.default_rng(T + N)
+    le = rng.normal(60, 50, (T, N)).astype(dtype)          # negative rates occur
+    temp = rng.uniform(255, 305, (T, N)).astype(dtype)
+    lhv = orc.lhv(temp).astype(dtype)
+    years = 2000 + (np.arange(T) // 365)
+    ref = orc.annual_mass_sums(le.astype(np.float64), years, lhv.astype(np.float64))
+    got = aggregate.annual_mass_sums(le, years, lhv)
+    assert got.shape == ref.shape and got.dtype == np.float64
+    tol = 1e-10 if dtype == np.float64 else 2e-6   # f32: the division is done in double
+    np.testing.assert_allclose(got, ref, rtol=tol, atol=tol)
+
+
+def test_groups_nan_and_total(cuda_lib):
+    rng = np.random.default_rng(3)
+    T, N = 50, 777
+    x = rng.normal(0, 1, (T, N))
+    x[rng.random((T, N)) < 0.01] = np.nan
+    group = rng.integers(-1, 4, T)                 # -1: skipped steps; unsorted labels
+    out, tot = aggregate.time_aggregate(x, group=group, n_groups=4, total=True)
+    for g in range(4):
+        ref = x[group == g].sum(axis=0)
+        assert np.array_equal(np.isnan(out[g]), np.isnan(ref))
+        np.testing.assert_allclose(out[g], ref, rtol=1e-12, atol=1e-12)
+        assert np.isnan(tot[g]) == np.isnan(ref.sum())
+    out2, tot2 = aggregate.time_aggregate(x, group=group, n_groups=4, skip_nan=True, total=True)
+    for g in range(4):
+        np.testing.assert_allclose(out2[g], np.nansum(x[group == g], axis=0), rtol=1e-12,
+                                   atol=1e-12)
+        np.testing.assert_allclose(tot2[g], np.nansum(x[group == g]), rtol=1e-10)
+    # one group, CUDA tensors in and out
+    xt = torch.from_numpy(np.nan_to_num(x)).cuda()
+    o = aggregate.time_aggregate(xt)
+    assert isinstance(o, torch.Tensor) and o.shape == (1, N)
+    np.testing.assert_allclose(o.cpu().numpy()[0], np.nan_to_num(x).sum(axis=0), rtol=1e-12,
+                               atol=1e-12)
+
+
+def test_aggregate_of_forward_output_is_the_annual_et(cuda_lib):
+    'K1 -> K3 on the device: a year of `_et` summed per pixel without leaving the GPU.'
+    from mod16_b200 import MOD16
+    T, N = 365, 512
+    d = synthetic.host_drivers(T, N, 5, dtype=np.float32)
+    names = list(synthetic.DRIVER_NAMES)
+    p7 = [-8., 8.8, 650., 4400., .02, .02, 1e-5, .0055, 60., 95., 250.]
+    drv = [torch.from_numpy(d[k]).cuda() if isinstance(d[k], np.ndarray) else d[k] for k in names]
+    et = MOD16._et(p7, *drv, dtype=np.float32)
+    lhv = torch.from_numpy(orc.lhv(d['temp_day'].astype(np.float64)).astype(np.float32)).cuda()
+    got = aggregate.annual_mass_sums(et, np.zeros(T, np.int32), lhv).cpu().numpy()
+    with np.errstate(all='ignore'):
+        ref_et = orc.static_et(p7, *[d[k].astype(np.float64) if isinstance(d[k], np.ndarray)
+                                     else d[k] for k in names])
+    ref = orc.annual_mass_sums(ref_et, np.zeros(T, np.int32),
+                               orc.lhv(d['temp_day'].astype(np.float64)))
+    np.testing.assert_allclose(got, ref, rtol=2e-5)

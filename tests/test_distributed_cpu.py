@@ -1,0 +1,104 @@
+'''
+CPU tests (gloo, world_size 2) of the multi-GPU host logic in mod16_b200/distributed.py.
+The oracle stands in for the CUDA kernel (`forward=` hook), so what is exercised is the
+partitioning, the two-pass gate protocol with its one-int all-reduce and the objective
+reductions -- the parts that do not need a GPU.
+'''
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mod16_b200 import distributed as D
+from mod16_b200 import synthetic
+from oracle import mod16_oracle as orc
+
+NAMES = list(synthetic.DRIVER_NAMES)
+BPLUT7 = [-8., 8.8, 650., 4400., .02, .02, 1e-5, .0055, 60., 95., 250.]
+
+
+def test_ranges_cover_and_align():
+    for n, w in ((5760000, 8), (25920000, 8), (1001, 3), (7, 4), (0, 2), (300, 7)):
+        edges = [D.pixel_range(n, r, w) for r in range(w)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        for (a, b), (c, d) in zip(edges[:-1], edges[1:]):
+            assert b == c and a <= b and a % 4 == 0
+        assert max(b - a for a, b in edges) - min(b - a for a, b in edges) <= 4 + n % 4
+        de = [D.draw_range(n, r, w) for r in range(w)]
+        assert de[0][0] == 0 and de[-1][1] == n and all(b == c for (_, b), (c, _) in zip(de, de[1:]))
+
+
+def _oracle_forward(drivers, *, params, gate, gate_flag, as_torch=True, out=None, **kw):
+    'Stands in for run_forward: implements the open_track / fixup halves of the gate protocol.'
+    drv = [d.numpy() if isinstance(d, torch.Tensor) else d for d in drivers]
+    with np.errstate(all='ignore'):
+        if gate == 'open_track':
+            day, night = orc.static_evapotranspiration(params, *drv, gate='open')
+            # the gate predicate on this shard, as the kernel evaluates it: g_surf > 0 (:343)
+            g_surf = (params[7] * orc.ramp_up(drv[8] - 273.15, params[0], params[1]) *
+                      orc.ramp_down(drv[9], params[2], params[3]))
+            if np.any(g_surf / orc.r_correction(drv[11], drv[5]) > 0):
+                gate_flag.fill_(1)
+            return [torch.from_numpy(np.asarray(day + night))]
+        assert gate == 'fixup'
+        if int(gate_flag.item()) == 0:
+            day, night = orc.static_evapotranspiration(params, *drv, gate='closed')
+            out[0].copy_(torch.from_numpy(np.asarray(day + night)))
+        return out
+
+
+def _worker(rank, size, port, case, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    try:
+        T, N = 6, 64
+        d = synthetic.host_drivers(T, N, 77)
+        if case == 'closed':
+            d['tmin'] = np.full((T, N), 240.0)          # nobody transpires: gate closed
+        elif case == 'one_shard_open':
+            d['tmin'] = np.full((T, N), 240.0)
+            d['tmin'][:, N - 3:] = 290.0                # only the last rank sees g_surf > 0
+        drv = [d[k] for k in NAMES]
+        with np.errstate(all='ignore'):
+            ref = orc.static_et(BPLUT7, *drv)           # one reference call on the whole domain
+        lo, hi = D.pixel_range(N, rank, size)
+        local = D.shard_pixels(drv, lo, hi)
+        out = D.forward_global_gate(local, forward=_oracle_forward, params=BPLUT7,
+                                    device=torch.device('cpu'))[0].numpy()
+        ok = np.allclose(out, ref[:, lo:hi], rtol=1e-12, atol=1e-12, equal_nan=True)
+        # objective partials sharded by site: all-reduce(sum) of 2 x D values
+        obs = ref + 1.0
+        sse = torch.tensor([float(np.nansum((out - obs[:, lo:hi])**2)), 2.0 * rank],
+                           dtype=torch.float64)
+        cnt = torch.tensor([float(out.size), 1.0], dtype=torch.float64)
+        D.reduce_objective(sse, cnt)
+        ok = ok and abs(sse[0].item() - T * N) < 1e-6 and cnt[0].item() == T * N \
+            and sse[1].item() == 2.0 * sum(range(size))
+        # draw-sharded results: all-gather back to the full vector
+        dl, dh = D.draw_range(11, rank, size)
+        full = D.gather_draws(torch.arange(dl, dh, dtype=torch.float64).reshape(-1, 1), 11)
+        ok = ok and torch.equal(full.ravel(), torch.arange(11, dtype=torch.float64))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('case', ['open', 'closed', 'one_shard_open'])
+def test_gate_protocol_and_reductions_world2(case):
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)], res
