@@ -33,6 +33,14 @@ struct Arr {
 };
 
 template <typename R>
+inline void fill_arr(Arr<R>& dst, const mod16_driver_t& src) {
+  dst.ptr = (const R*)src.ptr;
+  dst.ts = src.ptr ? src.t_stride : 0;
+  dst.ns = src.ptr ? src.n_stride : 0;
+  dst.scalar = (R)src.scalar;
+}
+
+template <typename R>
 struct ForwardArgs {
   Arr<R> drv[MOD16_N_DRIVERS];
   Arr<R> rc[2];

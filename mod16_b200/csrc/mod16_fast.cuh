@@ -400,6 +400,31 @@ M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in) {
               mand(vlt(th, splat<V>(340.0f)), mand(veq(s1, s1), veq(s2, s2))));
 }
 
+// Draw-independent part of step_fast()'s guards, for batches that evaluate MANY parameter
+// sets on the same element (K2): true when the element is outside the fast domain or within
+// rounding of a discontinuity for ANY parameter set -- the soil-heat-flux guard is taken for
+// both states of the (parameter-dependent) annual-temperature window.
+M16_HD bool element_needs_exact(const StepInV<float>& in, float p) {
+  bool need = !((p >= 3.0e4f) && (p <= 1.2e5f) && in_domain<float>(in));
+  const float a_d = fmaf(in.sw_d, 1.0f - in.alb, in.lw_d);
+  const float a_n = in.lw_n;
+  const float g_d = fmaf(celsius<float>(in.t_d), 4.73f, -20.87f);
+  const float g_n = fmaf(celsius<float>(in.t_n), 4.73f, -20.87f);
+  const float lim_d = fabsf(0.39f * a_d), lim_n = fabsf(0.39f * a_n);
+  need = need || (fabsf(fabsf(g_d) - lim_d) <= 1.0e-4f) || (fabsf(fabsf(g_n) - lim_n) <= 1.0e-4f) ||
+         (lim_d <= 1.0e-4f) || (lim_n <= 1.0e-4f) || (fabsf(a_d) < 1.0e-4f);
+  // (t_d - t_n) >= 5 is exact in float for inputs within a factor of two (Sterbenz)
+  const float ts[2] = {in.t_d, in.t_n}, vs[2] = {in.vpd_d, in.vpd_n};
+  for (int h = 0; h < 2; ++h) {
+    const float tc = celsius<float>(ts[h]);
+    const float xe = ((float)(17.27 * 1.4426950408889634) * tc) * s_rcp(tc + 237.3f);
+    const float ies = (float)(1.0 / 610.8) * s_ex2(-xe);
+    const float rh = fmaxf(fmaf(-vs[h], ies, 1.0f), 0.0f);
+    need = need || (fabsf(rh - 0.7f) < 4.0e-6f) || (fabsf(rh - 1.0e-3f) < 1.0e-3f);
+  }
+  return need;
+}
+
 // One pixel-timestep (or pair), both halves.  Returns the mask of elements that must be
 // re-evaluated by pixel_step_exact (outside the domain, or within rounding of a
 // discontinuity); their entries of `o` are unspecified.

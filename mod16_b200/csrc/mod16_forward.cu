@@ -59,14 +59,6 @@ forward_strided_kernel(const __grid_constant__ ForwardArgs<R> a) {
   }
 }
 
-template <typename R>
-static void fill_arr(Arr<R>& dst, const mod16_driver_t& src) {
-  dst.ptr = (const R*)src.ptr;
-  dst.ts = src.ptr ? src.t_stride : 0;
-  dst.ns = src.ptr ? src.n_stride : 0;
-  dst.scalar = (R)src.scalar;
-}
-
 // Validates the ABI structs and fills the kernel argument block (shared with the fast path).
 template <typename R>
 int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
