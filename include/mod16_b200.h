@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 2
+#define MOD16_ABI_VERSION 3
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -144,6 +144,41 @@ int mod16_forward_f32(const mod16_drivers_t* drivers, const mod16_params_t* para
 int mod16_forward_f64(const mod16_drivers_t* drivers, const mod16_params_t* params,
                       const mod16_out_t* out, int64_t T, int64_t N, uint32_t flags,
                       void* stream);
+
+/* K2 -- objective batch: D parameter draws evaluated on the SAME (T, N) block of drivers,
+ * reduced on the device to the sufficient statistics of the callers' objectives.
+ * Replaces the loops `for X in param_sweep: yhat = MOD16._et(X, *drivers); nash_sutcliffe(
+ * yhat, obs)` (mod16/sensitivity.py:94-96) and mod17's BlackBoxLikelihood calling
+ * `model(params, *drivers)` once per MCMC proposal (mod16/calibration.py:224-227, 907-909).
+ *
+ *   pred(d; t, n) = `_et(draws[d], *drivers)` (MOD16_SEM_STATIC; SEM_INSTANCE: day + night
+ *                   of evapotranspiration())
+ *   sse[d]   = sum over valid (t, n) of ((pred - observed) * weights)^2
+ *   count[d] = number of valid (t, n): observed, weights and pred all non-NaN
+ * so that RMSD = sqrt(sse / count) (= sqrt(nanmean(((pred - obs) w)^2))) and
+ * NSE = 1 - sse / sum((obs - mean(obs))^2) with unit weights.
+ *
+ * The static path's batch-global transpiration gate `if np.any(g_surf > 0)` (:343) is
+ * evaluated PER DRAW over all its elements, as one reference call per draw would
+ * (MOD16_GATE_GLOBAL); MOD16_GATE_OPEN / MOD16_GATE_CLOSED fix it.  r_corr_list is not
+ * supported.  All reductions are deterministic (no floating-point atomics).
+ */
+typedef struct mod16_objective {
+  const double* draws;     /* device (D, 11) row-major, order of required_parameters */
+  mod16_driver_t observed; /* (T, N) broadcastable like a driver; NaN = no observation */
+  mod16_driver_t weights;  /* residual weights; ptr NULL: the scalar (1.0 = unweighted) */
+  double* sse;             /* device (D,), overwritten */
+  double* count;           /* device (D,), overwritten */
+  int32_t* gate;           /* device (D,) or NULL: 1 where any g_surf > 0 for the draw */
+  void* workspace;         /* device scratch, 256-byte aligned */
+  int64_t workspace_bytes; /* >= mod16_objective_workspace_bytes(T, N, D, f32) */
+} mod16_objective_t;
+
+int64_t mod16_objective_workspace_bytes(int64_t T, int64_t N, int64_t D, int is_f32);
+int mod16_objective_batch_f32(const mod16_drivers_t* drivers, const mod16_objective_t* obj,
+                              int64_t T, int64_t N, int64_t D, uint32_t flags, void* stream);
+int mod16_objective_batch_f64(const mod16_drivers_t* drivers, const mod16_objective_t* obj,
+                              int64_t T, int64_t N, int64_t D, uint32_t flags, void* stream);
 
 /* K3 -- per-pixel time aggregates (annual sums of the calibration's precipitation
  * constraint, mod16/calibration.py:783-790: mass = x * 86400 / lhv, negatives dropped,

@@ -19,7 +19,7 @@ FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                         'libmod16_b200.so')
 
@@ -56,6 +56,13 @@ class Aggregate(ctypes.Structure):
 AGG_CLAMP_NEG, AGG_SKIP_NAN = 0x1, 0x2
 
 
+class Objective(ctypes.Structure):
+    _fields_ = [('draws', ctypes.c_void_p), ('observed', Driver), ('weights', Driver),
+                ('sse', ctypes.c_void_p), ('count', ctypes.c_void_p),
+                ('gate', ctypes.c_void_p), ('workspace', ctypes.c_void_p),
+                ('workspace_bytes', ctypes.c_int64)]
+
+
 class Mod16Error(RuntimeError):
     pass
 
@@ -75,6 +82,14 @@ EXPORTS = {
     'mod16_forward_f64': (ctypes.c_int, [
         ctypes.POINTER(Drivers), ctypes.POINTER(Params), ctypes.POINTER(Out),
         ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p]),
+    'mod16_objective_workspace_bytes': (ctypes.c_int64, [
+        ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    'mod16_objective_batch_f32': (ctypes.c_int, [
+        ctypes.POINTER(Drivers), ctypes.POINTER(Objective), ctypes.c_int64, ctypes.c_int64,
+        ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p]),
+    'mod16_objective_batch_f64': (ctypes.c_int, [
+        ctypes.POINTER(Drivers), ctypes.POINTER(Objective), ctypes.c_int64, ctypes.c_int64,
+        ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p]),
     'mod16_time_aggregate_f32': (ctypes.c_int, [
         ctypes.POINTER(Aggregate), ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32,
         ctypes.c_void_p]),

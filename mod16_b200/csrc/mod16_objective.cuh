@@ -1,0 +1,255 @@
+// K2 math: many parameter draws evaluated on the same elements (pixel-timesteps).
+//
+// The objective loops of the reference call `MOD16._et(params_vector, *drivers)` once per
+// parameter draw on the SAME drivers (mod16/sensitivity.py:94-96, mod16/calibration.py:
+// 224-227 through mod17's BlackBoxLikelihood), so nearly all of the model is
+// draw-independent: saturation vapour pressure, slope, psychrometric constant, air density,
+// r_corr, net radiation, soil heat flux, f_wet and every product of them.  make_elem_rec()
+// evaluates that part ONCE per element with the formulas of mod16_fast.cuh (half_fast) and
+// stores the coefficients; objective_step() is what remains per (draw, element): the two
+// ramps, the conductance algebra, three to five reciprocals and two exponentials.
+//
+// objective_step() is written over a value type V: `float`, or `F2` = two DRAWS in one
+// packed-FP32 register pair.  The element coefficients are then scalars shared by both
+// lanes (SASS: FFMA2 with an .F32 broadcast operand), and every property of the element
+// (f_wet == 0: no wet canopy) is a warp-uniform branch.
+//
+// Static semantics only (`_et`): that is what both callers pass.  Elements for which the
+// rearranged float algebra is not trusted for EVERY draw (fast::element_needs_exact, plus
+// lai == 0 and rh == 1) are not given a record; the kernels evaluate them with the
+// op-for-op double code for every draw.
+// Citations are file:line under /root/reference/mod16/__init__.py.
+#pragma once
+#include "mod16_fast.cuh"
+
+namespace mod16 {
+namespace obj {
+
+using fast::F2;
+using fast::M2;
+
+// ---- per-element record (48 floats = 12 quads, read with uniform 128-bit loads) ---------
+// SAs0 / SAs1: S x radiation reaching the soil with the soil heat flux G = 0 / G computed;
+// which one applies depends on the draw (annual-temperature window, :230-233).
+struct alignas(16) ElemRec {
+  // quad 0
+  float obs, w, tann_eff, tminc;
+  // quads 1-4: day, always needed
+  float d_vpd, d_inv_rc, d_lo, d_X;
+  float d_B, d_Kf, d_SA, d_SGX;
+  float d_G, d_oX, d_SAs0, d_SAs1;
+  float d_Ko, d_SX, d_vl, d_omfw;
+  // quad 5: day wet canopy (f_wet > 0 only); d_fw doubles as the branch condition
+  float d_fw, d_u, d_Su, d_fwu;
+  // quads 6-8: night, always needed
+  float n_vpd, n_inv_rc, n_X, n_B;
+  float n_G, n_SAs0, n_SAs1, n_Ko;
+  float n_SX, n_vl, n_omfw, n_fw;
+  // quads 9-10: night wet canopy
+  float n_Kf, n_SA, n_u, n_Su;
+  float n_fwu, pad0, pad1, pad2;
+  // quad 11: spare (keeps the record at 192 bytes, a multiple of 64)
+  float pad3, pad4, pad5, pad6;
+};
+static_assert(sizeof(ElemRec) == 192, "ElemRec layout");
+
+// Element coefficients of one half-day; same expressions as fast::half_fast.
+struct HalfCoef {
+  float S, G, Kv, X, B, inv_rc, fw, omfw, vl, rh;
+};
+
+M16_HD HalfCoef half_coef(float t, float vpd, float p) {
+  using namespace fast;
+  HalfCoef h;
+  const float tc = celsius<float>(t);
+  const float xe = ((float)(17.27 * 1.4426950408889634) * tc) * s_rcp(tc + 237.3f);
+  const float e = s_ex2(xe);
+  const float ies = (float)(1.0 / 610.8) * s_ex2(-xe);
+  const float rh = fmaxf(fmaf(-vpd, ies, 1.0f), 0.0f);            // :280-281
+  const float rh2 = rh * rh;
+  h.rh = rh;
+  h.fw = rh >= 0.7f ? rh2 * rh2 : 0.0f;                            // :282
+  h.omfw = 1.0f - h.fw;
+  const float q = t * (float)(1.0 / kT0);
+  const float d2 = tc + 239.0f;
+  const float dd = d2 * d2;
+  const float lam_n = fmaf(tc, (float)(-2361.0 / kLam0), (float)(2.501e6 / kLam0));
+  h.S = (((float)(17.38 * 239.0 * 610.8 / kDD0) * e) * lam_n) * q;
+  const float cpp_n = p * (float)(kCp / kEps / (kLam0 * kDD0));
+  h.G = (cpp_n * q) * dd;
+  h.Kv = (((float)(kCp / (kT0 * kDD0)) * lam_n) * dd) * vpd;
+  const float pa = 0.348444f * (p * 0.01f);
+  h.X = fmaf(rh, fmaf(tc, -0.252f, 2.0582f), pa);
+  const float q2 = q * q;
+  h.B = (float)(4.0 * kSigma * kT0 * kT0 * kT0 * kT0 / kCp) * (q2 * q2);
+  h.inv_rc = (p * (float)(1.0 / 101300.0)) * s_ex2(-1.75f * s_lg2(q));
+  h.vl = vpd * s_lg2(rh);  // rh^(vpd / beta) = 2^(vl / beta)
+  return h;
+}
+
+// Builds the record of one element.  Returns false when the element must take the exact
+// path for every draw (the record is then not used).
+M16_HD bool make_elem_rec(const fast::StepIn& in, float obs, float w, ElemRec& r) {
+  using namespace fast;
+  const StepInV<float> v = to_v(in);
+  if (element_needs_exact(v, in.p)) return false;
+  if (!(in.lai > 0.0f)) return false;  // g_canopy switches to 1e-7 (:336-337)
+  const HalfCoef d = half_coef(in.t_d, in.vpd_d, in.p);
+  const HalfCoef n = half_coef(in.t_n, in.vpd_n, in.p);
+  if (!(d.omfw > 0.0f) || !(n.omfw > 0.0f)) return false;  // rh == 1: same switch
+  const float oma = 1.0f - in.alb;
+  const float a_d = fmaf(in.sw_d, oma, in.lw_d);   // :225
+  const float a_n = in.lw_n;                        // :226
+  const float a_nc = fmaf(in.sw_n, oma, in.lw_n);   // :272 (night)
+  const float omf = 1.0f - in.fpar;
+  // radiation reaching the soil for both states of the annual-temperature window
+  float as_d[2], as_n[2];
+  const bool dt_ok = (in.t_d - in.t_n) >= 5.0f;     // :234
+  const bool below = (double)in.t_ann < 273.15 + 25;  // :231
+  for (int k = 0; k < 2; ++k) {
+    const bool cond = k == 1 && dt_ok && below;
+    float g_d = cond ? fmaf(celsius<float>(in.t_d), 4.73f, -20.87f) : 0.0f;   // :237
+    float g_n = cond ? fmaf(celsius<float>(in.t_n), 4.73f, -20.87f) : 0.0f;
+    const float lim_d = 0.39f * a_d, lim_n = 0.39f * a_n;
+    g_d = fabsf(g_d) > fabsf(lim_d) ? lim_d : g_d;                             // :239
+    g_n = fabsf(g_n) > fabsf(lim_n) ? lim_n : g_n;
+    float r_d = a_d - g_d, r_n = a_n - g_n;
+    const bool a_pos = a_d > 0.0f;
+    r_d = (a_pos && r_d < 0.0f) ? 0.0f : r_d;                                  // :245-247
+    const float floor_n = -0.5f * a_d;
+    r_n = (a_pos && r_n < floor_n) ? floor_n : r_n;                            // :248-252
+    as_d[k] = omf * r_d;
+    as_n[k] = omf * r_n;
+  }
+  r.obs = obs; r.w = w;
+  // the window's draw-dependent side is t_ann > 273.15 + tmin_open (:233): elements whose
+  // other two conditions fail can never satisfy it
+  r.tann_eff = (dt_ok && below) ? in.t_ann : -1.0e30f;
+  r.tminc = celsius<float>(in.tmin);
+  const float fpar = in.fpar;
+  // day
+  r.d_vpd = in.vpd_d; r.d_inv_rc = d.inv_rc; r.d_lo = in.lai * d.omfw; r.d_X = d.X;
+  r.d_B = d.B; r.d_Kf = d.Kv * fpar; r.d_SA = d.S * (fpar * a_d); r.d_SGX = (d.S + d.G) * d.X;
+  r.d_G = d.G; r.d_oX = d.omfw * d.X; r.d_SAs0 = d.S * as_d[0]; r.d_SAs1 = d.S * as_d[1];
+  r.d_Ko = d.Kv * omf; r.d_SX = d.S * d.X; r.d_vl = d.vl; r.d_omfw = d.omfw;
+  r.d_fw = d.fw; r.d_u = (in.lai * d.fw) * d.X; r.d_Su = d.S * r.d_u; r.d_fwu = d.fw * r.d_u;
+  // night
+  r.n_vpd = in.vpd_n; r.n_inv_rc = n.inv_rc; r.n_X = n.X; r.n_B = n.B;
+  r.n_G = n.G; r.n_SAs0 = n.S * as_n[0]; r.n_SAs1 = n.S * as_n[1]; r.n_Ko = n.Kv * omf;
+  r.n_SX = n.S * n.X; r.n_vl = n.vl; r.n_omfw = n.omfw; r.n_fw = n.fw;
+  r.n_Kf = n.Kv * fpar; r.n_SA = n.S * (fpar * a_nc); r.n_u = (in.lai * n.fw) * n.X;
+  r.n_Su = n.S * r.n_u;
+  r.n_fwu = n.fw * r.n_u;
+  r.pad0 = r.pad1 = r.pad2 = r.pad3 = r.pad4 = r.pad5 = r.pad6 = 0.0f;
+  return true;
+}
+
+// ---- per-draw constants -------------------------------------------------------------------
+template <class V>
+struct DrawConstV {
+  V tmin_close, inv_dtmin, vpd_close, inv_dvpd;  // ramps (:325-326)
+  V gl_sh, gl_wv, g_cut, csl;
+  V rbl_max, rbl_delta, inv_beta;
+  V tann_lo;  // largest float <= 273.15 + tmin_open: x > lo in double <=> x > tann_lo in float
+};
+
+// Largest float that is <= x.
+M16_HD float float_round_down(double x) {
+  float f = (float)x;
+  if ((double)f > x) f = nextafterf(f, -3.0e38f);
+  return f;
+}
+
+// Returns false when the draw is outside the domain of the rearranged algebra (the kernels
+// then evaluate the whole draw with the op-for-op double code): same test as make_pft_const.
+M16_HD bool make_draw_const(const double v[11], DrawConstV<float>& c) {
+  const fast::PftConst p = fast::make_pft_const(v, SEM_STATIC);
+  c.tmin_close = p.tmin_close; c.inv_dtmin = p.inv_dtmin;
+  c.vpd_close = p.vpd_close;   c.inv_dvpd = p.inv_dvpd;
+  c.gl_sh = p.gl_sh; c.gl_wv = p.gl_wv; c.g_cut = p.g_cut; c.csl = p.csl;
+  c.rbl_max = p.rbl_max; c.rbl_delta = p.rbl_delta; c.inv_beta = p.inv_beta;
+  c.tann_lo = float_round_down(273.15 + v[1]);
+  return p.ok != 0.0f;
+}
+
+M16_HD DrawConstV<F2> pair_draws(const DrawConstV<float>& a, const DrawConstV<float>& b) {
+  DrawConstV<F2> r;
+  r.tmin_close = F2{a.tmin_close, b.tmin_close}; r.inv_dtmin = F2{a.inv_dtmin, b.inv_dtmin};
+  r.vpd_close = F2{a.vpd_close, b.vpd_close};    r.inv_dvpd = F2{a.inv_dvpd, b.inv_dvpd};
+  r.gl_sh = F2{a.gl_sh, b.gl_sh}; r.gl_wv = F2{a.gl_wv, b.gl_wv};
+  r.g_cut = F2{a.g_cut, b.g_cut}; r.csl = F2{a.csl, b.csl};
+  r.rbl_max = F2{a.rbl_max, b.rbl_max}; r.rbl_delta = F2{a.rbl_delta, b.rbl_delta};
+  r.inv_beta = F2{a.inv_beta, b.inv_beta}; r.tann_lo = F2{a.tann_lo, b.tann_lo};
+  return r;
+}
+
+// scalar-on-the-left forms used below (the element coefficient is the scalar)
+M16_HD float bsub(float a, float b) { return a - b; }
+M16_HD F2 bsub(float a, F2 b) { return a - b; }
+M16_HD float bsel(bool m, float a, float b) { return m ? a : b; }
+M16_HD F2 bsel(M2 m, float a, float b) { return F2{m.x ? a : b, m.y ? a : b}; }
+M16_HD bool bgt(float a, float b) { return a > b; }
+M16_HD M2 bgt(float a, F2 b) { return M2{a > b.x, a > b.y}; }
+
+// One element for one draw (or draw pair).  Returns day + night with the transpiration
+// gate OPEN; `tr` is the day transpiration (so the caller can form the gate-closed total
+// as well) and `gs` the gate quantity csl m_tmin m_vpd (> 0 <=> g_surf > 0, :343).
+template <class V>
+M16_HD V objective_step(const ElemRec& e, const DrawConstV<V>& c, V& tr, V& gs) {
+  using namespace fast;
+  typedef typename MaskOf<V>::type M;
+  const M win = bgt(e.tann_eff, c.tann_lo);                                  // :233
+  // ---- day
+  const V m_t = vsat(bsub(e.tminc, c.tmin_close) * c.inv_dtmin);             // :325
+  const V m_vd = vsat((c.vpd_close - e.d_vpd) * c.inv_dvpd);                 // :326
+  gs = (c.csl * m_t) * m_vd;                                                 // :327
+  V tot;
+  {
+    const V sc = (c.g_cut + gs) * e.d_inv_rc;                                // :328-329
+    const V gbl = c.gl_sh * e.d_lo;                                          // :333
+    const V prod = gbl * sc, sum = gbl + sc;                                 // :334-335
+    const V Yd = vfma(c.gl_sh, e.d_X, e.d_B);                                // :340
+    const V num = vfma(e.d_Kf, Yd, e.d_SA);
+    const V den = vfma(e.d_SGX * prod, splat<V>(1.0f), (e.d_G * Yd) * sum);
+    tr = (num * (e.d_oX * prod)) * vrcp(den);                                // :344-346
+    // bare soil (:357-376)
+    const V r_t = vfma(-c.rbl_delta, m_vd, c.rbl_max) * e.d_inv_rc;
+    const V W = vfma(r_t, e.d_B, e.d_X);
+    const V sas = bsel(win, e.d_SAs1, e.d_SAs0);
+    const V nums = vfma(sas, r_t, e.d_Ko * W);
+    const V dens = r_t * vfma(e.d_G, W, e.d_SX);
+    const V qn = (nums * e.d_X) * vrcp(dens);
+    const V pw = vex2(c.inv_beta * e.d_vl);
+    const V mix = vfma(e.d_omfw, pw, e.d_fw);
+    tot = vfma(qn, mix, tr);
+  }
+  if (e.d_fw > 0.0f) {  // wet canopy (:305-320); uniform branch
+    const V Y = vfma(c.gl_sh, e.d_u, e.d_B);
+    const V num = vfma(e.d_Kf, Y, e.d_SA);
+    const V den = vfma(c.gl_wv, e.d_Su, e.d_G * Y);
+    tot = vfma(num * (c.gl_wv * e.d_fwu), vrcp(den), tot);
+  }
+  // ---- night (static: no transpiration, :323-348)
+  {
+    const V m_vn = vsat((c.vpd_close - e.n_vpd) * c.inv_dvpd);
+    const V r_t = vfma(-c.rbl_delta, m_vn, c.rbl_max) * e.n_inv_rc;
+    const V W = vfma(r_t, e.n_B, e.n_X);
+    const V sas = bsel(win, e.n_SAs1, e.n_SAs0);
+    const V nums = vfma(sas, r_t, e.n_Ko * W);
+    const V dens = r_t * vfma(e.n_G, W, e.n_SX);
+    const V qn = (nums * e.n_X) * vrcp(dens);
+    const V pw = vex2(c.inv_beta * e.n_vl);
+    const V mix = vfma(e.n_omfw, pw, e.n_fw);
+    tot = vfma(qn, mix, tot);
+  }
+  if (e.n_fw > 0.0f) {
+    const V Y = vfma(c.gl_sh, e.n_u, e.n_B);
+    const V num = vfma(e.n_Kf, Y, e.n_SA);
+    const V den = vfma(c.gl_wv, e.n_Su, e.n_G * Y);
+    tot = vfma(num * (c.gl_wv * e.n_fwu), vrcp(den), tot);
+  }
+  return tot;
+}
+
+}  // namespace obj
+}  // namespace mod16

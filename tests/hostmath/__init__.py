@@ -82,3 +82,29 @@ def forward(params, drivers, semantics='static', gate='global', dtype=np.float64
     if fast and not closed:
         res.update(tot_day=out[6], tot_night=out[7], tot=out[8])
     return res
+
+
+def objective(draws, drivers, pair=False):
+    '''
+    K2 math on the host: for every (draw, element) the gate-open prediction, the day
+    transpiration and the gate quantity.  Returns dict(tot, tr, gs: (D, n) float32 arrays
+    (NaN where the element has no fast record), fast: bool (n,), draw_ok: bool (D,)).
+    '''
+    allv, shape = _flat(list(drivers), np.float32)
+    n = allv.shape[1]
+    drv = np.ascontiguousarray(allv[:14])
+    dr = np.ascontiguousarray(np.asarray(draws, np.float64).reshape(-1, 11))
+    D = dr.shape[0]
+    tot = np.full((D, n), np.nan, np.float32)
+    tr = np.full((D, n), np.nan, np.float32)
+    gs = np.full((D, n), np.nan, np.float32)
+    cls = np.zeros(n, np.uint8)
+    ok = np.zeros(D, np.uint8)
+    fn = lib().hm_objective_f32
+    fn.restype = None
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    fn(p(drv), p(dr), ctypes.c_int64(D), ctypes.c_int64(n), ctypes.c_int(1 if pair else 0),
+       p(tot), p(tr), p(gs), p(cls), p(ok))
+    rs = lambda a: a.reshape((D,) + shape)
+    return dict(tot=rs(tot), tr=rs(tr), gs=rs(gs), fast=(cls == 1).reshape(shape),
+                draw_ok=ok.astype(bool))

@@ -2,9 +2,11 @@
 // the host with g++, so that the math can be checked against the oracle in a container
 // that has no GPU.  Nothing in the product loads this library.
 #include <stdint.h>
+#include <vector>
 #include "../../mod16_b200/csrc/mod16_math.cuh"
 #ifdef HM_WITH_FAST
 #include "../../mod16_b200/csrc/mod16_fast.cuh"
+#include "../../mod16_b200/csrc/mod16_objective.cuh"
 #endif
 
 using namespace mod16;
@@ -102,8 +104,44 @@ static void run_fast(int sem, int gate, const float* drv, const double* par, con
 }
 #endif
 
+#ifdef HM_WITH_FAST
+// K2 math: per (draw, element) prediction with the gate open, the day transpiration and the
+// gate quantity; cls[i] = 1 when the element has a fast record, 2 when it needs the exact path
+static void run_objective(const float* drv, const double* draws, int64_t D, int64_t n, int pair,
+                          float* tot, float* tr, float* gs, uint8_t* cls, uint8_t* draw_ok) {
+  std::vector<obj::ElemRec> recs(n);
+  for (int64_t i = 0; i < n; ++i) {
+    fast::StepIn in = load_in(drv, nullptr, 0, n, i);
+    cls[i] = obj::make_elem_rec(in, 0.0f, 1.0f, recs[i]) ? 1 : 2;
+  }
+  std::vector<obj::DrawConstV<float>> dc(D);
+  for (int64_t d = 0; d < D; ++d) draw_ok[d] = obj::make_draw_const(draws + 11 * d, dc[d]) ? 1 : 0;
+  for (int64_t d = 0; d < D; d += pair ? 2 : 1) {
+    const int64_t d1 = (pair && d + 1 < D) ? d + 1 : d;
+    const obj::DrawConstV<fast::F2> pc = obj::pair_draws(dc[d], dc[d1]);
+    for (int64_t i = 0; i < n; ++i) {
+      if (cls[i] != 1) continue;
+      if (pair) {
+        fast::F2 t2, g2;
+        const fast::F2 r = obj::objective_step<fast::F2>(recs[i], pc, t2, g2);
+        tot[d * n + i] = r.x; tr[d * n + i] = t2.x; gs[d * n + i] = g2.x;
+        tot[d1 * n + i] = r.y; tr[d1 * n + i] = t2.y; gs[d1 * n + i] = g2.y;
+      } else {
+        float t1, g1;
+        tot[d * n + i] = obj::objective_step<float>(recs[i], dc[d], t1, g1);
+        tr[d * n + i] = t1; gs[d * n + i] = g1;
+      }
+    }
+  }
+}
+#endif
+
 extern "C" {
 #ifdef HM_WITH_FAST
+void hm_objective_f32(const float* drv, const double* draws, int64_t D, int64_t n, int pair,
+                      float* tot, float* tr, float* gs, uint8_t* cls, uint8_t* draw_ok) {
+  run_objective(drv, draws, D, n, pair, tot, tr, gs, cls, draw_ok);
+}
 void hm_fast_f32(int sem, int gate, const float* drv, const double* par, const float* rc,
                  int has_rc, int64_t n, float* out, uint8_t* gpos) {
   run_fast(sem, gate, drv, par, rc, has_rc, n, out, gpos, 0);

@@ -1,0 +1,257 @@
+'''
+K2 -- objective batch (many parameter draws on the same drivers).
+
+CPU part (`-m "not gpu"`): the draw/element factorisation of the kernel math
+(mod16_b200/csrc/mod16_objective.cuh, compiled for the host by tests/hostmath) against the
+numpy oracle's `_et`, one oracle call per draw -- exactly the loop the reference runs
+(mod16/sensitivity.py:94-96).
+GPU part: `mod16_objective_batch_{f32,f64}` through the C ABI against
+`oracle.objective_stats(oracle.static_et(draw, *drivers), obs, w)` per draw.
+
+Criteria.  float64: sse within 1e-10 relative, count exact.  float32: RMSD is the L2 norm of
+the weighted residual / sqrt(n), so a per-element prediction error of at most
+delta = max(1e-5 |pred|, 1e-3 W m-2) (the north-star tolerance) moves it by at most
+max(w delta): |rmsd - rmsd_ref| <= max over elements of w * delta.  Counts are exact.
+'''
+import numpy as np
+import pytest
+
+import hostmath
+import parity
+from mod16_b200 import synthetic, utils
+from oracle import mod16_oracle as orc
+
+NAMES = list(synthetic.DRIVER_NAMES)
+
+
+def _column(pft=7):
+    table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51), orc.PARAM_ORDER,
+                              default_beta=250.0)
+    return np.array(table[:, pft], np.float64)
+
+
+def _problem(T, N, D, seed, kind='physical', nan_frac=0.0, fixed=True, obs_nan=0.3,
+             dtype=np.float32):
+    d = synthetic.host_drivers(T, N, seed, kind=kind, dtype=dtype, nan_frac=nan_frac,
+                               fill_frac=nan_frac)
+    drv = [d[k] for k in NAMES]
+    d64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
+    col = _column()
+    draws = synthetic.host_param_draws(
+        D, seed + 1, bplut_column=col,
+        fixed=('tmin_close', 'tmin_open', 'vpd_open') if fixed else ())
+    rng = np.random.default_rng(seed + 2)
+    with np.errstate(all='ignore'):
+        truth = orc.static_et(list(col), *d64)
+    obs = truth + rng.normal(0, 15, truth.shape)
+    obs[obs < 0] = np.nan                       # calibration.py:631
+    obs[rng.random(obs.shape) < obs_nan] = np.nan
+    w = rng.uniform(0.2, 1.0, obs.shape)
+    return drv, d64, draws, obs.astype(dtype), w.astype(dtype)
+
+
+def _reference_stats(d64, draws, obs, w, gate='global', semantics='static'):
+    'One oracle call per draw, as the reference loops do.'
+    sse = np.zeros(len(draws))
+    cnt = np.zeros(len(draws))
+    tol = np.zeros(len(draws))
+    o64, w64 = np.asarray(obs, np.float64), np.asarray(w, np.float64)
+    for i, x in enumerate(draws):
+        with np.errstate(all='ignore'):
+            if semantics == 'static':
+                pred = orc.static_et(list(x), *d64, gate=gate)
+            else:
+                day, night = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, x))).evapotranspiration(
+                    *d64)
+                pred = day + night
+        sse[i], cnt[i] = orc.objective_stats(pred, o64, w64)
+        ok = ~np.isnan((pred - o64) * w64)
+        if ok.any():
+            tol[i] = np.max((w64 * np.maximum(1e-5 * np.abs(pred), 1e-3))[ok])
+    return sse, cnt, tol
+
+
+# ---- CPU: the factorised math -------------------------------------------------------------
+@pytest.mark.parametrize('pair', [False, True])
+@pytest.mark.parametrize('kind,fixed', [('physical', True), ('physical', False),
+                                        ('stress', False)])
+def test_factorised_math_matches_oracle_per_draw(kind, fixed, pair):
+    T, N, D = 12, 700, 9
+    drv, d64, draws, _, _ = _problem(T, N, D, 77, kind=kind, fixed=fixed)
+    r = hostmath.objective(draws, drv, pair=pair)
+    assert r['draw_ok'].all()
+    assert r['fast'].mean() > 0.95
+    for i, x in enumerate(draws):
+        with np.errstate(all='ignore'):
+            day, night = orc.static_evapotranspiration(list(x), *d64, gate='open')
+            closed = orc.static_et(list(x), *d64, gate='closed')
+        ref = day + night
+        m = r['fast']
+        parity.assert_parity(r['tot'][i][m], ref[m], np.float32, what='K2 pred draw %d' % i)
+        parity.assert_parity((r['tot'][i] - r['tr'][i])[m], closed[m], np.float32,
+                             what='K2 gate-closed pred draw %d' % i)
+
+
+def test_elements_outside_the_fast_domain_get_no_record():
+    T, N = 6, 400
+    d = synthetic.host_drivers(T, N, 5, dtype=np.float32, nan_frac=0.01, fill_frac=0.01)
+    d['lai'][0, :7] = 0.0       # g_canopy switches to 1e-7 (:336-337)
+    d['vpd_day'][1, :5] = 0.0   # rh == 1
+    drv = [d[k] for k in NAMES]
+    r = hostmath.objective(_column()[None], drv)
+    bad = np.zeros((T, N), bool)
+    for k in NAMES:
+        # (a NaN / fill annual temperature only fails the window test, :230-233: finite result)
+        if isinstance(d[k], np.ndarray) and k != 'temp_annual':
+            bad |= np.broadcast_to(np.isnan(d[k]) | (d[k] == -9999), (T, N))
+    assert not r['fast'][bad].any()
+    assert not r['fast'][0, :7].any() and not r['fast'][1, :5].any()
+    assert r['fast'].mean() > 0.7
+
+
+def test_degenerate_draws_are_flagged():
+    col = _column()
+    draws = np.stack([col, col, col, col])
+    draws[1, 10] = np.nan          # beta
+    draws[2, 1] = draws[2, 0]      # zero-width tmin ramp
+    draws[3, 4] = 0.0              # gl_sh
+    drv = [synthetic.host_drivers(2, 8, 1, dtype=np.float32)[k] for k in NAMES]
+    r = hostmath.objective(draws, drv)
+    assert list(r['draw_ok']) == [True, False, False, False]
+
+
+# ---- GPU: through the C ABI ---------------------------------------------------------------
+def _check(sse, cnt, ref_sse, ref_cnt, tol, dtype):
+    assert np.array_equal(cnt, ref_cnt), 'valid-pair counts differ'
+    if np.dtype(dtype) == np.float64:
+        assert np.all(np.abs(sse - ref_sse) <= 1e-10 * np.maximum(ref_sse, 1.0))
+    else:
+        with np.errstate(invalid='ignore', divide='ignore'):
+            r0, r1 = np.sqrt(sse / cnt), np.sqrt(ref_sse / ref_cnt)
+        ok = ref_cnt > 0
+        assert np.all(np.abs(r0 - r1)[ok] <= tol[ok]), (np.abs(r0 - r1)[ok] / tol[ok]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('kind,nan,fixed', [('physical', 0.0, True), ('physical', 0.002, False),
+                                            ('stress', 0.002, False)])
+def test_objective_batch_matches_oracle_loop(cuda_lib, dtype, kind, nan, fixed):
+    from mod16_b200.objective import objective_batch
+    T, N, D = 37, 301, 70
+    drv, d64, draws, obs, w = _problem(T, N, D, 404, kind=kind, nan_frac=nan, fixed=fixed,
+                                       dtype=dtype)
+    ref_sse, ref_cnt, tol = _reference_stats(d64, draws, obs, w)
+    sse, cnt = objective_batch(draws, drv, obs, w, dtype=dtype)
+    _check(sse, cnt, ref_sse, ref_cnt, tol, dtype)
+    # unweighted, observations complete
+    obs2 = np.where(np.isnan(obs), 50.0, obs).astype(dtype)
+    ref_sse, ref_cnt, tol = _reference_stats(d64, draws, obs2, 1.0)
+    sse, cnt = objective_batch(draws, drv, obs2, None, dtype=dtype)
+    _check(sse, cnt, ref_sse, ref_cnt, tol, dtype)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_objective_batch_flat_calibration_layout(cuda_lib, dtype):
+    'The calibration passes 1-D drivers with the NaN observations already removed.'
+    from mod16_b200.objective import ObjectiveBackend
+    T, N, D = 50, 120, 200
+    drv, d64, draws, obs, w = _problem(T, N, D, 11, dtype=dtype)
+    keep = ~np.isnan(obs)
+    flat = [v[keep] if isinstance(v, np.ndarray) and v.shape == obs.shape else
+            (np.broadcast_to(v, obs.shape)[keep] if isinstance(v, np.ndarray) else v)
+            for v in drv]
+    f64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in flat]
+    ref_sse, ref_cnt, tol = _reference_stats(f64, draws[:40], obs[keep], w[keep])
+    backend = ObjectiveBackend(flat, obs[keep], w[keep], dtype=dtype)
+    sse, cnt = backend(draws)
+    _check(sse[:40], cnt[:40], ref_sse, ref_cnt, tol, dtype)
+    # repeatable bit for bit (deterministic reductions), and independent of the batch split
+    sse2, cnt2 = backend(draws)
+    assert np.array_equal(sse, sse2) and np.array_equal(cnt, cnt2)
+    a, _ = backend(draws[:64])
+    b, _ = backend(draws[64:])
+    if np.dtype(dtype) == np.float64:
+        assert np.array_equal(np.concatenate([a, b]), sse)
+    else:
+        assert np.allclose(np.concatenate([a, b]), sse, rtol=1e-6)
+    nr = backend.neg_rmsd(draws[:3])
+    assert np.allclose(nr, -np.sqrt(sse[:3] / cnt[:3]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_objective_batch_per_draw_gate(cuda_lib, dtype):
+    '''
+    `if np.any(g_surf > 0)` is evaluated per reference call, i.e. per draw: a draw with
+    csl == 0 (or a Tmin ramp that never opens) loses its cuticular transpiration too.
+    '''
+    from mod16_b200.objective import objective_batch
+    T, N, D = 9, 257, 40
+    drv, d64, draws, obs, w = _problem(T, N, D, 31, dtype=dtype, fixed=False)
+    draws[3, 7] = 0.0                         # csl = 0: g_surf == 0 everywhere
+    draws[5, 0], draws[5, 1] = 60.0, 80.0     # Tmin ramp above every Tmin
+    for gate in ('global', 'open', 'closed'):
+        ref_sse, ref_cnt, tol = _reference_stats(d64, draws, obs, w, gate=gate)
+        sse, cnt, g = objective_batch(draws, drv, obs, w, dtype=dtype, gate=gate,
+                                      return_gate=True)
+        _check(sse, cnt, ref_sse, ref_cnt, tol, dtype)
+        assert not g[3] and not g[5] and g[[0, 1, 2, 4]].all()
+
+
+@pytest.mark.gpu
+def test_objective_batch_degenerate_draws_and_small_batches(cuda_lib):
+    from mod16_b200.objective import objective_batch
+    T, N, D = 11, 200, 48
+    drv, d64, draws, obs, w = _problem(T, N, D, 8, fixed=False)
+    draws[1, 10] = np.nan          # beta NaN: every prediction NaN, nothing is valid
+    draws[2, 1] = draws[2, 0]      # zero-width Tmin ramp: double code decides
+    draws[7, 3] = draws[7, 2]      # zero-width VPD ramp
+    ref_sse, ref_cnt, tol = _reference_stats(d64, draws, obs, w)
+    sse, cnt = objective_batch(draws, drv, obs, w, dtype=np.float32)
+    assert cnt[1] == 0 and ref_cnt[1] == 0
+    _check(sse, cnt, ref_sse, ref_cnt, tol, np.float32)
+    # D below the fast-path threshold, D == 1 (a sequential MCMC proposal), D == 0
+    for k in (1, 5):
+        s, c = objective_batch(draws[3:3 + k], drv, obs, w, dtype=np.float32)
+        _check(s, c, ref_sse[3:3 + k], ref_cnt[3:3 + k], tol[3:3 + k], np.float32)
+    s, c = objective_batch(np.zeros((0, 11)), drv, obs, w, dtype=np.float32)
+    assert s.shape == (0,) and c.shape == (0,)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_objective_batch_instance_semantics(cuda_lib, dtype):
+    from mod16_b200.objective import objective_batch
+    T, N, D = 7, 150, 6
+    drv, d64, draws, obs, w = _problem(T, N, D, 3, dtype=dtype)
+    obs = (obs / 2.45e6).astype(dtype)
+    ref_sse, ref_cnt, _ = _reference_stats(d64, draws, obs, w, semantics='instance')
+    sse, cnt = objective_batch(draws, drv, obs, w, dtype=dtype, semantics='instance')
+    assert np.array_equal(cnt, ref_cnt)
+    assert np.all(np.abs(sse - ref_sse) <= 1e-10 * ref_sse)
+
+
+@pytest.mark.gpu
+def test_objective_batch_sobol_sized_slice(cuda_lib):
+    '''
+    A slice of BASELINE config 5 (parameter rows x 1000 pixels x 365 days): size-independent
+    properties at a size the oracle cannot loop over -- the fast and the double path agree
+    within the RMSD bound, the statistics of a draw do not depend on its batch.
+    '''
+    from mod16_b200.objective import ObjectiveBackend
+    T, N, D = 365, 1000, 2048
+    drv, d64, draws, obs, w = _problem(T, N, D, 16005, fixed=False)
+    fast = ObjectiveBackend(drv, obs, w, dtype=np.float32)
+    s32, c32 = fast(draws)
+    exact = ObjectiveBackend([v.astype(np.float64) if isinstance(v, np.ndarray) else v
+                              for v in drv], obs.astype(np.float64), w.astype(np.float64),
+                             dtype=np.float64)
+    pick = np.arange(0, D, 97)
+    s64, c64 = exact(draws[pick])
+    assert np.array_equal(c32[pick], c64)
+    r32, r64 = np.sqrt(s32[pick] / c32[pick]), np.sqrt(s64 / c64)
+    assert np.all(np.abs(r32 - r64) <= np.maximum(1e-5 * r64, 1e-3)), np.abs(r32 - r64).max()
+    ref_sse, ref_cnt, tol = _reference_stats(d64, draws[:2], obs, w)
+    _check(s32[:2], c32[:2], ref_sse, ref_cnt, tol, np.float32)
