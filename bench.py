@@ -67,7 +67,7 @@ def bplut_table():
 class ClockSampler(threading.Thread):
     'Samples SM clock and throttle reasons of one GPU through NVML while the bench runs.'
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()

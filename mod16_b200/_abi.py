@@ -104,7 +104,8 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    # MOD16_B200_LIB: an alternative build of the same ABI (kernel A/B experiments)
+    path = path or os.environ.get('MOD16_B200_LIB') or LIB_PATH
     if not os.path.exists(path):
         raise Mod16Error(
             'CUDA library %s is not built; run `python -m mod16_b200.build` '

@@ -109,14 +109,20 @@ __device__ __noinline__ bool fix_exact_one(const ForwardArgs<float>& a, const Sh
 // element would hold its warp for ~20 us and, through the ring, the whole block -- but
 // queued and evaluated afterwards, one element per thread: by redo_queue_kernel when the
 // caller supplied a workspace, else by this block after its loop.
-constexpr int PIPE_CONSUMER_WARPS = 15;
+#ifndef M16_PIPE_WARPS
+#define M16_PIPE_WARPS 15
+#endif
+#ifndef M16_PIPE_STAGES
+#define M16_PIPE_STAGES 5
+#endif
+constexpr int PIPE_CONSUMER_WARPS = M16_PIPE_WARPS;
 constexpr int PIPE_CONSUMERS = PIPE_CONSUMER_WARPS * 32;
 constexpr int PIPE_THREADS = PIPE_CONSUMERS + 32;
 constexpr int PIPE_TILE = PIPE_CONSUMERS;  // pixels per block
 constexpr int PIPE_SUB = 2;                // time steps per stage (the two FFMA2 lanes)
-constexpr int PIPE_STAGES = 5;
+constexpr int PIPE_STAGES = M16_PIPE_STAGES;
 constexpr int PIPE_MAX_ARR = 12;
-constexpr int PIPE_QCAP = 2048;            // deferred exact re-evaluations per block
+constexpr int PIPE_QCAP = 512;             // deferred exact re-evaluations per block
 
 struct PipeSrc {  // per-step arrays in stage order
   const float* ptr[PIPE_MAX_ARR];
@@ -158,7 +164,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ SharedLut lut;
   __shared__ __align__(8) uint64_t full[PIPE_STAGES], empty[PIPE_STAGES];
-  __shared__ uint32_t redo_q[PIPE_QCAP];  // (step within the chunk) << 9 | consumer thread
+  __shared__ uint32_t redo_q[PIPE_QCAP];  // (step within the chunk) << 10 | consumer thread
   __shared__ int redo_n;
   if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
   const int tid = threadIdx.x;
@@ -297,7 +303,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
             } else {               // no workspace: block-local queue, evaluated after the loop
               const int slot = atomicAdd(&redo_n, 1);
               queued = slot < PIPE_QCAP;
-              if (queued) redo_q[slot] = (uint32_t)(i * PIPE_SUB + j) << 9 | (uint32_t)tid;
+              if (queued) redo_q[slot] = (uint32_t)(i * PIPE_SUB + j) << 10 | (uint32_t)tid;
             }
             // queue full (fill-heavy data): evaluate in place
             if (!queued) any_pos |= fix_exact_one<SEM, OUT>(a, lut, t, n);
@@ -314,7 +320,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     const int total = redo_n < PIPE_QCAP ? redo_n : PIPE_QCAP;
     for (int e = tid; e < total; e += PIPE_CONSUMERS) {
       const uint32_t q = redo_q[e];
-      any_pos |= fix_exact_one<SEM, OUT>(a, lut, t0 + (int64_t)(q >> 9), tile0 + (q & 511u));
+      any_pos |= fix_exact_one<SEM, OUT>(a, lut, t0 + (int64_t)(q >> 10), tile0 + (q & 1023u));
     }
   }
   if (a.track_gate) {

@@ -213,7 +213,14 @@ obj_pack_kernel(const __grid_constant__ ObjArgs<float> a) {
 }
 
 // ---- 4: the hot loop ----------------------------------------------------------------------
-__global__ void __launch_bounds__(OBJ_THREADS, 2)
+#ifndef M16_OBJ_BLOCKS
+#define M16_OBJ_BLOCKS 3
+#endif
+#ifndef M16_OBJ_UNROLL
+#define M16_OBJ_UNROLL 1
+#endif
+constexpr int OBJ_UNROLL = M16_OBJ_UNROLL;
+__global__ void __launch_bounds__(OBJ_THREADS, M16_OBJ_BLOCKS)
 objective_fast_kernel(const __grid_constant__ ObjArgs<float> a) {
   __shared__ __align__(128) ElemRec ring[OBJ_STAGES][OBJ_TILE];
   __shared__ __align__(8) uint64_t full[OBJ_STAGES], empty[OBJ_STAGES];
@@ -284,7 +291,7 @@ objective_fast_kernel(const __grid_constant__ ObjArgs<float> a) {
     const int cnt = left < OBJ_TILE ? (int)left : OBJ_TILE;
     mbar_wait(full0 + 8 * stage, phase);
     F2 acc_o = F2{0.0f, 0.0f}, acc_c = F2{0.0f, 0.0f};
-#pragma unroll 1
+#pragma unroll OBJ_UNROLL
     for (int j = 0; j < cnt; ++j) {
       const ElemRec& e = ring[stage][j];
       F2 tr, gs;
@@ -470,7 +477,7 @@ static ObjPlan make_plan(int64_t T, int64_t N, int64_t D, bool want_fast) {
   p.nblk = (p.E + OBJ_CLS_THREADS - 1) / OBJ_CLS_THREADS;
   const int64_t draw_blocks = (D + OBJ_DRAWS_PER_BLOCK - 1) / OBJ_DRAWS_PER_BLOCK;
   const int64_t tiles = (p.E + OBJ_TILE - 1) / OBJ_TILE;
-  int64_t nf = (148 * 2 * 2 + draw_blocks - 1) / (draw_blocks > 0 ? draw_blocks : 1);
+  int64_t nf = (148 * M16_OBJ_BLOCKS * 2 + draw_blocks - 1) / (draw_blocks > 0 ? draw_blocks : 1);
   if (nf > tiles) nf = tiles;
   if (nf > 65535) nf = 65535;
   if (nf < 1) nf = 1;

@@ -35,7 +35,7 @@ keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
         'sm__cycles_elapsed.avg', 'smsp__thread_inst_executed_per_inst_executed.ratio', 'lts__t_sector_hit_rate.pct']
 kname = r[hdr.index('Kernel Name')]
-short = kname.split('<')[0].split('::')[-1].replace('void ', '')
+short = kname.split('<')[0].split('(')[0].split('::')[-1].replace('void ', '')
 with open('profiles/%s_%s_full.txt' % (tag, short), 'w') as f:
     f.write('ncu --set full --clock-control none --import-source on: %s\n' % cmd)
     f.write('kernel: %s\n%.4g pixel-timesteps per launch (algorithmic bytes %.4g GB at 48 B each)\n\n' % (kname, units, units * 48 / 1e9))
@@ -47,7 +47,7 @@ with open('profiles/%s_%s_full.txt' % (tag, short), 'w') as f:
     try:
         ms = float(vals['gpu__time_duration.sum']); 
         if un[hdr.index('gpu__time_duration.sum')] == 'us': ms /= 1e3
-        f.write('\n=> %.1f G pixel-timesteps/s under the profiler; %.1f warp-instructions per 32 pixel-timesteps\n' % (
+        f.write('\n=> %.1f G units/s under the profiler; %.1f warp-instructions per 32 units\n' % (
             units / ms / 1e6, float(vals['smsp__inst_executed.sum']) / (units / 32)))
     except Exception as e:
         f.write('(derived figures unavailable: %s)\n' % e)

@@ -5,7 +5,8 @@ import csv, subprocess, sys, collections, io
 rep = sys.argv[1]
 txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 blocks = txt.split('"Kernel Name"')
-which = int(sys.argv[2]) if len(sys.argv) > 2 else len(blocks) - 1
+args = [x for x in sys.argv[2:] if not x.startswith('--')]
+which = int(args[0]) if args else len(blocks) - 1
 blk = '"Kernel Name"' + blocks[which]
 rows = list(csv.reader(io.StringIO(blk)))
 print(rows[0][1])
