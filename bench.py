@@ -43,6 +43,11 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--pixels', type=int, default=TILE_N, help='pixels per GPU')
+    ap.add_argument('--workload', default='tile', choices=['tile', 'global'],
+                    help="tile: one MODIS tile-year per GPU (BASELINE configs[1], weak scaling; "
+                         "the default and the headline); global: the 0.05 deg CMG year "
+                         "(7200 x 3600, configs[2]) pixel-tiled across the ranks (strong "
+                         "scaling; needs >= 4 GPUs to be resident)")
     ap.add_argument('--T', type=int, default=YEAR_T, help='time steps resident per GPU')
     ap.add_argument('--dtype', default='float32', choices=['float32', 'float64'])
     ap.add_argument('--kind', default='physical', choices=['physical', 'stress'])
@@ -192,6 +197,9 @@ def run_reference(args):
 
 
 def workload_name(args):
+    if args.workload == 'global':
+        return ('global 0.05 deg CMG grid 7200x3600 x %d daily steps pixel-tiled across the '
+                'ranks, synthetic %s drivers' % (args.T, args.kind))
     if args.pixels == TILE_N and args.T == YEAR_T:
         return 'MODIS 500 m tile 2400x2400 x 365 daily steps, synthetic %s drivers' % args.kind
     return '%d pixels x %d steps per GPU, synthetic %s drivers' % (args.pixels, args.T, args.kind)
@@ -250,6 +258,14 @@ def main():
     np_dtype = np.dtype(args.dtype)
     t_dtype = torch.float32 if np_dtype == np.float32 else torch.float64
     T, N = args.T, args.pixels
+    if args.workload == 'global':
+        from mod16_b200.distributed import pixel_range
+        lo, hi = pixel_range(7200 * 3600, rank, world)
+        N = hi - lo
+        need = 48.0 * T * N / 1e9
+        if need > 170.0:
+            raise SystemExit('global workload: %.0f GB per GPU do not fit; use more GPUs or '
+                             'a smaller --T' % need)
     table = bplut_table()
     pft = torch.from_numpy(synthetic.host_pft_map(N, 16002 + rank)).to(device)
     drv = resident_drivers(T, N, 16002 + 1000 * rank, device, t_dtype, args.kind)
@@ -265,6 +281,18 @@ def main():
              'mirror': _abi.FORCE_MIRROR}[args.kernel]
 
     def step():
+        if args.workload == 'global' and args.gate == 'global' and world > 1:
+            # one reference call over the WHOLE grid: the transpiration gate is evaluated
+            # across the ranks (open pass, all-reduce(max) of one int, fix-up pass)
+            run_forward(drv_list, pft=pft, table=table, semantics='static', out_mode='sum',
+                        gate='open_track', dtype=np_dtype, device=device, gate_flag=flag,
+                        out=[out], force=force)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            run_forward(drv_list, pft=pft, table=table, semantics='static', out_mode='sum',
+                        gate='fixup', dtype=np_dtype, device=device, gate_flag=flag,
+                        out=[out], force=force)
+            flag.zero_()
+            return
         run_forward(drv_list, pft=pft, table=table, semantics='static', out_mode='sum',
                     gate=args.gate, dtype=np_dtype, device=device, gate_flag=flag, out=[out],
                     force=force)
@@ -298,7 +326,11 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     total_ms = float(tm.item())
     units_per_rank = T * N
-    value = world * units_per_rank * args.steps / (total_ms * 1e-3)
+    tu = torch.tensor([units_per_rank], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tu, op=dist.ReduceOp.SUM)
+    units_total = float(tu.item())
+    value = units_total * args.steps / (total_ms * 1e-3)
     bytes_per_unit = BYTES_PER_UNIT_F32 * (2 if np_dtype == np.float64 else 1)
     kernel_ms = float(np.mean(step_ms))
     achieved = bytes_per_unit * units_per_rank / (kernel_ms * 1e-3) / 1e9
@@ -369,10 +401,10 @@ def main():
             'metric': METRIC, 'value': value, 'unit': 'pixel-timesteps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None,
+            'scaling': 'strong' if args.workload == 'global' else 'weak', 'vs_baseline': None,
             'dtype': 'f32' if np_dtype == np.float32 else 'f64', 'data': 'synthetic',
             'config': {'workload': workload_name(args), 'pixels_per_gpu': N, 'steps_per_gpu': T,
-                       'units_per_step': world * units_per_rank, 'gate': args.gate,
+                       'units_per_step': units_total, 'gate': args.gate,
                        'l2': 'inputs (%.1f GB per GPU) exceed L2 (126 MB); no flush needed' % (
                            bytes_per_unit * units_per_rank / 1e9)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
