@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 3
+#define MOD16_ABI_VERSION 4
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -179,6 +179,62 @@ int mod16_objective_batch_f32(const mod16_drivers_t* drivers, const mod16_object
                               int64_t T, int64_t N, int64_t D, uint32_t flags, void* stream);
 int mod16_objective_batch_f64(const mod16_drivers_t* drivers, const mod16_objective_t* obj,
                               int64_t T, int64_t N, int64_t D, uint32_t flags, void* stream);
+
+/* K4 -- component methods and physics helpers of the reference's public API, elementwise.
+ * `in[k]` are the positional arguments of the reference signature (file:line under
+ * mod16/__init__.py), each broadcastable to (T, N); bit k of `present` says that argument k
+ * was supplied -- required arguments must be present, optional ones (marked [..]) fall back
+ * to the reference's defaults.  `params` are the instance parameters of MOD16(params), in
+ * required_parameters order (unused by the free functions).  Outputs are dense (T, N).
+ *
+ *   op                              arguments                                       out
+ *   SVP                    :1340    temp_k                                          Pa
+ *   SVP_SLOPE              :1370    temp_k, [s]                                     Pa K-1
+ *   LHV                    :121     temp_k                                          J kg-1
+ *   PSYCHROMETRIC          :1261    pressure, temp_k                                Pa K-1
+ *   AIR_DENSITY            :385     temp_k, pressure, rhumidity                     kg m-3
+ *   RHUMIDITY              :647     temp_k, vpd                                     [0, 1]
+ *   VPD                    :605     qv10m, pressure, tmean                          Pa
+ *   AIR_PRESSURE           :415     elevation_m                                     Pa
+ *   RADIATION_NET          :1293    sw_rad, sw_albedo, temp_k                       W m-2
+ *   SOIL_HEAT_FLUX         :1055    rad_net_day, rad_net_night, temp_day,
+ *                                   temp_night, temp_annual                         2 x W m-2
+ *   RADIATION_SOIL         :963     lw_net_day, lw_net_night, sw_rad_day,
+ *                                   sw_rad_night, sw_albedo, temp_day, temp_night,
+ *                                   temp_annual, fpar                               2 x W m-2
+ *   POTENTIAL_SOIL_EVAPORATION :450 pressure, temp_k, vpd, fpar, rad_soil, [r_corr],
+ *                                   [lhv], [rhumidity], [f_wet]                     2 x W m-2
+ *   EVAPORATION_SOIL       :795     (same)                                          kg m-2 s-1
+ *   EVAPORATION_WET_CANOPY :866     pressure, temp_k, vpd, lai, fpar, rad_canopy,
+ *                                   [lhv], [rhumidity], [f_wet]; opt[1] = tiny      kg m-2 s-1
+ *   SURFACE_CONDUCTANCE    :1121    tmin, vpd_day                                   m s-1
+ *   TRANSPIRATION          :1152    pressure, temp_k, vpd, lai, fpar, rad_canopy, tmin,
+ *                                   [r_corr], [lhv], [rhumidity], [f_wet];
+ *                                   opt[0] = daytime (0 / 1), opt[1] = tiny         kg m-2 s-1
+ *   POTENTIAL_TRANSPIRATION :547    lw_net, sw_rad, sw_albedo, pressure, temp_k, vpd,
+ *                                   fpar, [rhumidity], [f_wet]; opt[0] = alpha      W m-2
+ */
+enum {
+  MOD16_OP_SVP = 0, MOD16_OP_SVP_SLOPE, MOD16_OP_LHV, MOD16_OP_PSYCHROMETRIC,
+  MOD16_OP_AIR_DENSITY, MOD16_OP_RHUMIDITY, MOD16_OP_VPD, MOD16_OP_AIR_PRESSURE,
+  MOD16_OP_RADIATION_NET, MOD16_OP_SOIL_HEAT_FLUX, MOD16_OP_RADIATION_SOIL,
+  MOD16_OP_POTENTIAL_SOIL_EVAPORATION, MOD16_OP_EVAPORATION_SOIL,
+  MOD16_OP_EVAPORATION_WET_CANOPY, MOD16_OP_SURFACE_CONDUCTANCE, MOD16_OP_TRANSPIRATION,
+  MOD16_OP_POTENTIAL_TRANSPIRATION, MOD16_OP_COUNT
+};
+#define MOD16_MAX_OP_INPUTS 12
+
+typedef struct mod16_elementwise {
+  int32_t op;        /* MOD16_OP_* */
+  uint32_t present;  /* bit k: in[k] was supplied */
+  mod16_driver_t in[MOD16_MAX_OP_INPUTS];
+  double params[MOD16_N_PARAMS];
+  double opt[2];
+  void* out[2];      /* device, dense (T, N), float / double as the entry; out[1] may be NULL */
+} mod16_elementwise_t;
+
+int mod16_elementwise_f32(const mod16_elementwise_t* ew, int64_t T, int64_t N, void* stream);
+int mod16_elementwise_f64(const mod16_elementwise_t* ew, int64_t T, int64_t N, void* stream);
 
 /* K3 -- per-pixel time aggregates (annual sums of the calibration's precipitation
  * constraint, mod16/calibration.py:783-790: mass = x * 86400 / lhv, negatives dropped,

@@ -7,6 +7,8 @@ signatures and run as one fused CUDA kernel (sm_100a) behind the C ABI declared 
 ``include/mod16_b200.h``.  There is no CPU implementation in this package.
 '''
 from .model import MOD16, PFT_VALID  # noqa: F401
+from .components import (  # noqa: F401
+    latent_heat_vaporization, psychrometric_constant, radiation_net, svp, svp_slope)
 
 STEFAN_BOLTZMANN = 5.67e-8
 SPECIFIC_HEAT_CAPACITY_AIR = 1013

@@ -19,7 +19,7 @@ FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                         'libmod16_b200.so')
 
@@ -63,6 +63,19 @@ class Objective(ctypes.Structure):
                 ('workspace_bytes', ctypes.c_int64)]
 
 
+MAX_OP_INPUTS = 12
+OPS = ('svp', 'svp_slope', 'lhv', 'psychrometric', 'air_density', 'rhumidity', 'vpd',
+       'air_pressure', 'radiation_net', 'soil_heat_flux', 'radiation_soil',
+       'potential_soil_evaporation', 'evaporation_soil', 'evaporation_wet_canopy',
+       'surface_conductance', 'transpiration', 'potential_transpiration')
+
+
+class Elementwise(ctypes.Structure):
+    _fields_ = [('op', ctypes.c_int32), ('present', ctypes.c_uint32),
+                ('inp', Driver * MAX_OP_INPUTS), ('params', ctypes.c_double * N_PARAMS),
+                ('opt', ctypes.c_double * 2), ('out', ctypes.c_void_p * 2)]
+
+
 class Mod16Error(RuntimeError):
     pass
 
@@ -90,6 +103,10 @@ EXPORTS = {
     'mod16_objective_batch_f64': (ctypes.c_int, [
         ctypes.POINTER(Drivers), ctypes.POINTER(Objective), ctypes.c_int64, ctypes.c_int64,
         ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p]),
+    'mod16_elementwise_f32': (ctypes.c_int, [
+        ctypes.POINTER(Elementwise), ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    'mod16_elementwise_f64': (ctypes.c_int, [
+        ctypes.POINTER(Elementwise), ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     'mod16_time_aggregate_f32': (ctypes.c_int, [
         ctypes.POINTER(Aggregate), ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32,
         ctypes.c_void_p]),

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libmod16_b200.so')
 SOURCES = ['mod16_forward.cu', 'mod16_forward_fast.cu', 'mod16_aggregate.cu',
-           'mod16_objective.cu']
+           'mod16_objective.cu', 'mod16_elementwise.cu']
 HEADERS = ['mod16_math.cuh', 'mod16_fast.cuh', 'mod16_common.cuh', 'mod16_pipe.cuh',
            'mod16_objective.cuh', os.path.join('..', '..', 'include', 'mod16_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')

@@ -273,7 +273,8 @@ struct StepOutV {  // components and totals of one pixel-timestep (or pair)
 template <class V, int SEM, bool DAY, bool HAS_RC>
 M16_HD HalfV<V> half_fast(V t, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V omf, V lai,
                           const PftConstV<V>& c, const PixConstV<V>& x, int gate,
-                          typename MaskOf<V>::type& g_pos, typename MaskOf<V>::type& need) {
+                          typename MaskOf<V>::type& g_pos, typename MaskOf<V>::type& need,
+                          V& gs_out) {
   typedef typename MaskOf<V>::type M;
   const V tc = celsius<V>(t);
   // saturation vapour pressure 610.8 exp(17.27 Tc / (Tc + 237.3)) and its reciprocal (:1365)
@@ -334,6 +335,7 @@ M16_HD HalfV<V> half_fast(V t, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V
   }
   // -- transpiration (:323-349, :1233-1258)
   g_pos = mask_splat<V>(false);
+  gs_out = splat<V>(0.0f);
   if (DAY || SEM == SEM_INSTANCE) {
     V gs = splat<V>(0.0f);
     if (DAY) {
@@ -341,6 +343,7 @@ M16_HD HalfV<V> half_fast(V t, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V
       gs = ((c.csl * m_t) * m_v) * inv_rc;                                      // :327-328
     }
     g_pos = vgt(gs, splat<V>(0.0f));
+    gs_out = gs;
     const V sc = vfma(c.g_cut, inv_rc, gs);                                     // :329
     const V gbl = (c.gl_sh * lai) * omfw;                                       // :333
     const M ok = mand(vgt(lai, splat<V>(0.0f)), vgt(omfw, splat<V>(0.0f)));     // :336
@@ -428,10 +431,12 @@ M16_HD bool element_needs_exact(const StepInV<float>& in, float p) {
 // One pixel-timestep (or pair), both halves.  Returns the mask of elements that must be
 // re-evaluated by pixel_step_exact (outside the domain, or within rounding of a
 // discontinuity); their entries of `o` are unspecified.
+// `gs_day` receives the day's gate quantity g_surf (> 0 <=> g_pos), so that a caller can
+// track `any(g_surf > 0)` with one max instead of predicate logic.
 template <class V, int SEM, bool HAS_RC>
 M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,
                                           const PixConstV<V>& x, int gate, StepOutV<V>& o,
-                                          typename MaskOf<V>::type& g_pos) {
+                                          typename MaskOf<V>::type& g_pos, V& gs_day) {
   typedef typename MaskOf<V>::type M;
   M need = mnot(mand(x.ok, in_domain<V>(in)));
   const V oma = 1.0f - in.alb;
@@ -458,12 +463,13 @@ M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<
   r_n = vsel(mand(a_pos, vlt(r_n, floor_n)), floor_n, r_n);  // :248-252 (G := A_n + A_d / 2)
   const V omf = 1.0f - in.fpar;
   M unused = mask_splat<V>(false);
+  V gs_unused;
   o.day = half_fast<V, SEM, true, HAS_RC>(in.t_d, in.vpd_d, in.fpar * a_d, omf * r_d, in.rc_d,
                                           in.tmin, in.fpar, omf, in.lai, c, x, gate, g_pos,
-                                          need);
+                                          need, gs_day);
   o.night = half_fast<V, SEM, false, HAS_RC>(in.t_n, in.vpd_n, in.fpar * a_nc, omf * r_n,
                                              in.rc_n, in.tmin, in.fpar, omf, in.lai, c, x, gate,
-                                             unused, need);
+                                             unused, need, gs_unused);
   if (SEM == SEM_STATIC) {  // :380
     o.tot_day = (o.day.trans + o.day.canopy) + o.day.soil;
     o.tot_night = (o.night.trans + o.night.canopy) + o.night.soil;
@@ -473,6 +479,13 @@ M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<
   }
   o.tot = o.tot_day + o.tot_night;
   return need;
+}
+template <class V, int SEM, bool HAS_RC>
+M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,
+                                          const PixConstV<V>& x, int gate, StepOutV<V>& o,
+                                          typename MaskOf<V>::type& g_pos) {
+  V gs_day;
+  return step_fast<V, SEM, HAS_RC>(in, c, x, gate, o, g_pos, gs_day);
 }
 
 // ---- scalar interface used by the strided kernel, the fix-up and the host harness -------

@@ -13,6 +13,8 @@
 // forward_strided_fast_kernel -- same math, one pixel-timestep at a time, for layouts the
 //   bulk copies cannot express (broadcast strides, per-pixel parameter arrays, N % 4 != 0,
 //   unaligned bases, r_corr_list).
+#include <type_traits>
+
 #include "mod16_common.cuh"
 #include "mod16_fast.cuh"
 #include "mod16_pipe.cuh"
@@ -154,7 +156,7 @@ __device__ __forceinline__ void pipe_issue(const PipeSrc& src, int n_arr, int n_
   __syncwarp();
 }
 
-template <int SEM, int OUT>
+template <int SEM, int OUT, bool SWN>
 __global__ void __launch_bounds__(PIPE_THREADS, 1)
 forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
                     const __grid_constant__ PipeSrc src) {
@@ -219,6 +221,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   const int64_t n = tile0 + tid;
   const bool live = n < a.N;
   bool any_pos = false;
+  float gs_max = 0.0f;  // max of the gate quantity g_surf over this thread's elements (:343)
   // per-pixel state, all scalar: BPLUT column constants, pressure terms, annual window
   fast::PftConstV<F2> pc;
   fast::PixConstV<F2> px;
@@ -233,13 +236,15 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       p = a.drv[MOD16_D_PRESSURE].at(0, n);   // per pixel or scalar (checked on the host)
       ta = a.drv[MOD16_D_TEMP_ANNUAL].at(0, n);
     }
-    const PftConst c1 = lut.pc[code];
+    PftConst c1 = lut.pc[code];
+    // threads past the last pixel run the loop on whatever the stage holds (they take part
+    // in the barriers); csl = 0 keeps them out of the gate, `live` out of stores and queue
+    if (!live) c1.csl = 0.0f;
     const PixConst x1 = fast::make_pix_const(p, ta, c1, SEM);
     pc = fast::pair_pft(c1, c1);
     px = fast::pair_pix(x1, x1);
   }
   const float swn_scalar = a.drv[MOD16_D_SW_RAD_NIGHT].scalar;
-  const bool swn_array = n_arr == PIPE_MAX_ARR;
   const int gate = a.gate;
   constexpr int n_out = OUT == 0 ? 1 : (OUT == 1 ? 2 : 6);
   const uint32_t my0 = data0 + (uint32_t)tid * 4u;  // this thread's pixel within a row
@@ -249,71 +254,89 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   int stage = 0;
   uint32_t phase = 0;
 
-#pragma unroll 1
-  for (int i = 0; i < niter; ++i) {
-    const bool two = nsteps - i * PIPE_SUB >= PIPE_SUB;  // (block-uniform) both steps exist
+  // One use of a stage.  TWO: both time steps of the pair exist (always, except for the last
+  // use of an odd chunk, which is peeled off the loop below so that the loop carries no
+  // tail handling).  Stage order == PipeSrc order (see launch_pipe).  The inputs are pulled
+  // into registers at once so that the stage can be re-filled while the steps are
+  // evaluated.  Lane x of every pair is step t, lane y is step t + 1 (step t again when the
+  // chunk is odd).
+  auto consume = [&](auto two_tag, const int i) {
+    constexpr bool TWO = decltype(two_tag)::value;
     mbar_wait(full0 + 8 * stage, phase);
-    // stage order == PipeSrc order (see launch_pipe).  The inputs are pulled into registers
-    // at once so that the stage can be re-filled while the steps are evaluated.  Lane x of
-    // every pair is step t, lane y is step t + 1 (step t again when the chunk is odd).
     fast::StepInV<F2> in;
     {
       const uint32_t s0 = my0 + (uint32_t)stage * STAGEB;
-      const uint32_t s1 = two ? s0 + SUBB : s0;
+      const uint32_t s1 = TWO ? s0 + SUBB : s0;
 #define M16_IN(k) F2{lds1(s0 + (k) * ROWB), lds1(s1 + (k) * ROWB)}
       in.lw_d = M16_IN(0);  in.lw_n = M16_IN(1);  in.sw_d = M16_IN(2);  in.alb = M16_IN(3);
       in.t_d = M16_IN(4);   in.t_n = M16_IN(5);   in.tmin = M16_IN(6);  in.vpd_d = M16_IN(7);
       in.vpd_n = M16_IN(8); in.fpar = M16_IN(9);  in.lai = M16_IN(10);
-      in.sw_n = swn_array ? M16_IN(11) : F2{swn_scalar, swn_scalar};
+      if (SWN) in.sw_n = M16_IN(11);
+      else in.sw_n = F2{swn_scalar, swn_scalar};
 #undef M16_IN
       in.rc_d = F2{0.f, 0.f}; in.rc_n = F2{0.f, 0.f};
     }
     __syncwarp();
     if (warp_lead) mbar_arrive(empty0 + 8 * stage);  // this warp has read the stage
-    if (live) {
-      fast::StepOutV<F2> r;
-      M2 g_pos;
-      M2 need = fast::step_fast<F2, SEM, false>(in, pc, px, gate, r, g_pos);
-      need.y = need.y && two;
-      any_pos |= (g_pos.x && !need.x) || (g_pos.y && !need.y);
-      F2 res[6];
-      if (OUT == 0) {
-        res[0] = r.tot;
-      } else if (OUT == 1) {
-        res[0] = r.tot_day; res[1] = r.tot_night;
-      } else {
-        res[0] = r.day.canopy;   res[1] = r.day.soil;   res[2] = r.day.trans;
-        res[3] = r.night.canopy; res[4] = r.night.soil; res[5] = r.night.trans;
+    fast::StepOutV<F2> r;
+    M2 g_pos;
+    F2 gs;
+    M2 need = fast::step_fast<F2, SEM, false>(in, pc, px, gate, r, g_pos, gs);
+    need.x = need.x && live;
+    need.y = need.y && live && TWO;
+    F2 res[6];
+    if (OUT == 0) {
+      res[0] = r.tot;
+    } else if (OUT == 1) {
+      res[0] = r.tot_day; res[1] = r.tot_night;
+    } else {
+      res[0] = r.day.canopy;   res[1] = r.day.soil;   res[2] = r.day.trans;
+      res[3] = r.night.canopy; res[4] = r.night.soil; res[5] = r.night.trans;
+    }
+    if (!(need.x || need.y)) {
+      // (a NaN gate quantity -- garbage read by a thread past the last pixel -- is dropped)
+      gs_max = fmaxf(gs_max, fmaxf(gs.x, gs.y));
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < n_out; ++k) {
+          st_stream1(a.out[k] + off, res[k].x);
+          if (TWO) st_stream1(a.out[k] + off + t_stride, res[k].y);
+        }
       }
+    } else {  // rare: queue for the double-precision pass after the loop
+      any_pos |= (g_pos.x && !need.x) || (g_pos.y && !need.y);
 #pragma unroll
       for (int k = 0; k < n_out; ++k) {
         if (!need.x) st_stream1(a.out[k] + off, res[k].x);
-        if (two && !need.y) st_stream1(a.out[k] + off + t_stride, res[k].y);
+        if (TWO && !need.y) st_stream1(a.out[k] + off + t_stride, res[k].y);
       }
-      if (need.x || need.y) {  // rare: queue for the double-precision pass after the loop
 #pragma unroll
-        for (int j = 0; j < PIPE_SUB; ++j) {
-          if (j == 0 ? need.x : need.y) {
-            const int64_t t = t0 + i * PIPE_SUB + j;
-            bool queued = false;
-            if (a.redo_cap > 0) {  // global queue, evaluated by redo_queue_kernel
-              const unsigned long long slot = atomicAdd(a.redo_ws, 1ULL);
-              queued = slot < (unsigned long long)a.redo_cap;
-              if (queued) a.redo_ws[1 + slot] = (unsigned long long)(t * a.N + n);
-            } else {               // no workspace: block-local queue, evaluated after the loop
-              const int slot = atomicAdd(&redo_n, 1);
-              queued = slot < PIPE_QCAP;
-              if (queued) redo_q[slot] = (uint32_t)(i * PIPE_SUB + j) << 10 | (uint32_t)tid;
-            }
-            // queue full (fill-heavy data): evaluate in place
-            if (!queued) any_pos |= fix_exact_one<SEM, OUT>(a, lut, t, n);
+      for (int j = 0; j < PIPE_SUB; ++j) {
+        if (j == 0 ? need.x : need.y) {
+          const int64_t t = t0 + i * PIPE_SUB + j;
+          bool queued = false;
+          if (a.redo_cap > 0) {  // global queue, evaluated by redo_queue_kernel
+            const unsigned long long slot = atomicAdd(a.redo_ws, 1ULL);
+            queued = slot < (unsigned long long)a.redo_cap;
+            if (queued) a.redo_ws[1 + slot] = (unsigned long long)(t * a.N + n);
+          } else {               // no workspace: block-local queue, evaluated after the loop
+            const int slot = atomicAdd(&redo_n, 1);
+            queued = slot < PIPE_QCAP;
+            if (queued) redo_q[slot] = (uint32_t)(i * PIPE_SUB + j) << 10 | (uint32_t)tid;
           }
+          // queue full (fill-heavy data): evaluate in place
+          if (!queued) any_pos |= fix_exact_one<SEM, OUT>(a, lut, t, n);
         }
       }
     }
     off += PIPE_SUB * t_stride;
     if (++stage == n_stages) { stage = 0; phase ^= 1u; }
-  }
+  };
+  const int nfull = nsteps / PIPE_SUB;
+#pragma unroll 1
+  for (int i = 0; i < nfull; ++i) consume(std::true_type(), i);
+  if (nsteps & 1) consume(std::false_type(), nfull);
+  any_pos |= gs_max > 0.0f;
   // the block-local deferred pass: consumers only (named barrier 1), one element each
   if (a.redo_cap == 0) {
     asm volatile("bar.sync 1, %0;" ::"n"(PIPE_CONSUMERS) : "memory");
@@ -451,24 +474,32 @@ bool fast_f32_applicable(const ForwardArgs<float>& a, uint32_t flags) {
   return true;  // every layout has a fast-math kernel; pipe_ok() picks which
 }
 
-template <int SEM, int OUT>
-static int launch_pipe_one(const ForwardArgs<float>& a, const PipeSrc& src, dim3 grid,
+template <int SEM, int OUT, bool SWN>
+static int launch_pipe_swn(const ForwardArgs<float>& a, const PipeSrc& src, dim3 grid,
                            size_t smem, cudaStream_t st) {
   static bool configured = false;  // per instantiation; the attribute is per function
   if (!configured) {
     M16_CUDA_CHECK(cudaFuncSetAttribute(
-        forward_pipe_kernel<SEM, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        forward_pipe_kernel<SEM, OUT, SWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
         PIPE_STAGES * PIPE_SUB * (PIPE_MAX_ARR - 1) * PIPE_TILE * (int)sizeof(float)));
     configured = true;
   }
   if (a.redo_cap > 0) M16_CUDA_CHECK(cudaMemsetAsync(a.redo_ws, 0, 8, st));
-  forward_pipe_kernel<SEM, OUT><<<grid, PIPE_THREADS, smem, st>>>(a, src);
+  forward_pipe_kernel<SEM, OUT, SWN><<<grid, PIPE_THREADS, smem, st>>>(a, src);
   M16_CUDA_CHECK(cudaGetLastError());
   if (a.redo_cap > 0) {
     redo_queue_kernel<SEM, OUT><<<148 * 2, 128, 0, st>>>(a);
     M16_CUDA_CHECK(cudaGetLastError());
   }
   return MOD16_OK;
+}
+
+template <int SEM, int OUT>
+static int launch_pipe_one(const ForwardArgs<float>& a, const PipeSrc& src, dim3 grid,
+                           size_t smem, cudaStream_t st) {
+  // (a dense sw_rad_night array is a twelfth stream; every reference caller passes 0)
+  if (src.n_arr == PIPE_MAX_ARR) return launch_pipe_swn<SEM, OUT, true>(a, src, grid, smem, st);
+  return launch_pipe_swn<SEM, OUT, false>(a, src, grid, smem, st);
 }
 
 // Grid of the pipelined kernel: one block per 480-pixel tile and time chunk; the chunk is

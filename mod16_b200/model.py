@@ -12,12 +12,13 @@ inputs), ``gate`` (see ``run_forward``), ``device`` / ``stream``.
 '''
 import numpy as np
 
+from .components import ComponentMixin
 from .forward import run_forward
 
 PFT_VALID = (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12)
 
 
-class MOD16(object):
+class MOD16(ComponentMixin):
     '''
     The MODIS MxD16 evapotranspiration model, B200 backend.
 

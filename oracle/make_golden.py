@@ -366,6 +366,99 @@ def random_fixture(bplut, tag, T, N, seed, kind, dtype, nan_frac, fill_frac):
     return T * N
 
 
+def components_fixture(bplut):
+    '''
+    Every component method / helper of the public API on seeded random inputs, with and
+    without the optional arguments, NaN injected -- evaluated by the REFERENCE; the oracle
+    must agree bit for bit.
+    '''
+    rng = np.random.default_rng(16110)
+    n = 64
+    P = params_for(bplut, 7)
+    m, o = ref.MOD16(P), orc.InstanceModel(P)
+    u = lambda lo, hi: rng.uniform(lo, hi, n)
+    x = dict(pressure=u(7e4, 1.0134e5), temp_k=u(255, 305), vpd=u(0, 3400), fpar=u(0.02, 0.89),
+             lai=u(0, 5.3), rad_soil=u(-50, 300), rad_canopy=u(-50, 300), tmin=u(252, 298),
+             r_corr=u(0.8, 1.4), lhv=u(2.4e6, 2.55e6), rh=u(0, 1), fw=u(0, 1),
+             lw_d=u(-100, 0), lw_n=u(-50, 0), sw_d=u(0, 360), sw_n=u(0, 1e-5), alb=u(0.1, 0.22),
+             t_d=u(255, 305), t_ann=u(265, 300), qv=u(0.001, 0.02), elev=u(-100, 5000),
+             sw=u(0, 5000))
+    x['t_n'] = x['t_d'] - u(0, 15)
+    x['lai'][:4] = 0.0
+    x['fw'][4:8] = 0.0
+    x['vpd'][8:10] = 0.0
+    for k in ('temp_k', 'vpd', 'lai', 'rad_canopy', 'tmin', 'pressure', 'fpar'):
+        x[k][rng.integers(10, n)] = np.nan
+    out = dict(('in_' + k, v) for k, v in x.items())
+    out['params'] = np.array([P[k] for k in ORDER], np.float64)
+
+    def both(tag, rfn, ofn, *args, **kw):
+        with np.errstate(all='ignore'):
+            r, q = rfn(*args, **kw), ofn(*args, **kw)
+        if isinstance(r, (tuple, list)):
+            for i, (a, b) in enumerate(zip(r, q)):
+                check('component %s[%d]' % (tag, i), a, b)
+                out['%s_%d' % (tag, i)] = np.asarray(a, np.float64)
+        else:
+            check('component ' + tag, r, q)
+            out[tag] = np.asarray(r, np.float64)
+
+    a5 = (x['pressure'], x['temp_k'], x['vpd'], x['fpar'], x['rad_soil'])
+    both('evaporation_soil', m.evaporation_soil, o.evaporation_soil, *a5)
+    both('evaporation_soil_opt', m.evaporation_soil, o.evaporation_soil, *a5, x['r_corr'],
+         x['lhv'], x['rh'], x['fw'])
+    bp = (P['vpd_open'], P['vpd_close'], P['rbl_min'], P['rbl_max'])
+    both('potential_soil_evaporation', ref.MOD16.potential_soil_evaporation,
+         orc.InstanceModel.potential_soil_evaporation, *a5, None, None, None, None, *bp)
+    both('potential_soil_evaporation_opt', ref.MOD16.potential_soil_evaporation,
+         orc.InstanceModel.potential_soil_evaporation, *a5, x['r_corr'], x['lhv'], x['rh'],
+         x['fw'], *bp)
+    a6 = (x['pressure'], x['temp_k'], x['vpd'], x['lai'], x['fpar'], x['rad_canopy'])
+    both('evaporation_wet_canopy', m.evaporation_wet_canopy, o.evaporation_wet_canopy, *a6)
+    both('evaporation_wet_canopy_opt', m.evaporation_wet_canopy, o.evaporation_wet_canopy, *a6,
+         x['lhv'], x['rh'], x['fw'])
+    for day in (True, False):
+        tag = 'transpiration_%s' % ('day' if day else 'night')
+        both(tag, m.transpiration, o.transpiration, *a6, x['tmin'], daytime=day)
+        both(tag + '_opt', m.transpiration, o.transpiration, *a6, x['tmin'], x['r_corr'],
+             x['lhv'], x['rh'], x['fw'], daytime=day)
+    both('surface_conductance', m.surface_conductance, o.surface_conductance, x['tmin'], x['vpd'])
+    a9 = (x['lw_d'], x['lw_n'], x['sw_d'], x['sw_n'], x['alb'], x['t_d'], x['t_n'], x['t_ann'],
+          x['fpar'])
+    both('radiation_soil', m.radiation_soil, o.radiation_soil, *a9)
+    rad_d = x['sw_d'] * (1 - x['alb']) + x['lw_d']
+    both('soil_heat_flux', m.soil_heat_flux, o.soil_heat_flux, rad_d, x['lw_n'], x['t_d'],
+         x['t_n'], x['t_ann'])
+    a7 = (x['lw_d'], x['sw_d'], x['alb'], x['pressure'], x['temp_k'], x['vpd'], x['fpar'])
+    both('potential_transpiration', ref.MOD16.potential_transpiration,
+         orc.InstanceModel.potential_transpiration, *a7)
+    both('potential_transpiration_opt', ref.MOD16.potential_transpiration,
+         orc.InstanceModel.potential_transpiration, *a7, x['rh'], x['fw'], 1.1)
+    both('svp', ref.svp, orc.svp, x['temp_k'])
+    both('svp_slope', ref.svp_slope, orc.svp_slope, x['temp_k'])
+    both('svp_slope_opt', ref.svp_slope, orc.svp_slope, x['temp_k'], x['lhv'] * 1e-3)
+    both('lhv', ref.latent_heat_vaporization, orc.lhv, x['temp_k'])
+    both('psychrometric', ref.psychrometric_constant, orc.psychrometric_constant, x['pressure'],
+         x['temp_k'])
+    both('air_density', ref.MOD16.air_density, orc.air_density, x['temp_k'], x['pressure'],
+         x['rh'])
+    both('rhumidity', ref.MOD16.rhumidity, orc.rhumidity_clamped, x['temp_k'], x['vpd'])
+    both('vpd', ref.MOD16.vpd, orc.vpd_from_qv, x['qv'], x['pressure'], x['temp_k'])
+    both('air_pressure', ref.MOD16.air_pressure, orc.air_pressure, x['elev'])
+    both('radiation_net', ref.radiation_net, orc.radiation_net, x['sw'], x['alb'], x['temp_k'])
+    # the reference's own known answers for radiation_net (tests/tests.py:217-226)
+    swrad = np.array((500, 5000, 500, 5000, 500, 5000, 500, 5000.))
+    albedo = np.array((0.4, 0.4, 0.8, 0.8, 0.4, 0.4, 0.8, 0.8))
+    tk = 273.15 + np.array((10, 10, 10, 10, 25, 25, 25, 25.))
+    r = ref.radiation_net(swrad, albedo, tk)
+    assert list(r.round(1)) == [223.3, 2923.3, 23.3, 923.3, 241.8, 2941.8, 41.8, 941.8]
+    check('radiation_net known', r, orc.radiation_net(swrad, albedo, tk))
+    out['radiation_net_known_in'] = np.stack([swrad, albedo, tk])
+    out['radiation_net_known'] = r
+    np.savez_compressed(os.path.join(GOLDEN, 'components.npz'), **out)
+    return len(out)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     bplut = bplut_c51()
@@ -373,6 +466,7 @@ def main():
     report['unit_tests'] = unit_tests_fixture()
     report['verify'] = verify_fixture(bplut)
     report['tables'] = table_fixture(bplut)
+    report['components'] = components_fixture(bplut)
     report['rand_phys_f64'] = random_fixture(
         bplut, 'rand_phys_f64', 24, 96, 16101, 'physical', np.float64, 0.0, 0.0)
     report['rand_phys_fill_f64'] = random_fixture(

@@ -100,6 +100,14 @@ def air_pressure(elevation_m):
     return 101325.0 * np.power(ratio, rate)
 
 
+def radiation_net(sw_rad, sw_albedo, temp_k):
+    'DEPRECATED net radiation of Cleugh et al. 2007 (mod16/__init__.py:1333-1337).'
+    emis_surface = 0.97
+    emis_atmos = 1 - 0.26 * np.exp(-7.77e-4 * np.power(temp_k - 273.15, 2))
+    return sw_rad * (1 - sw_albedo) + \
+        SIGMA * (emis_atmos - emis_surface) * np.power(temp_k, 4)
+
+
 def ramp_up(x, xmin, xmax):
     '''
     ``mod17.linear_constraint(xmin, xmax)`` -- EXTERNAL to /root/reference
@@ -346,6 +354,20 @@ class InstanceModel(object):
                 rho * CP_AIR * (1 - fpar) * (vpd / r_as))
             denom = (s + gamma * (r_tot / r_as))
             return ((numer * fw) / denom, (numer * (1 - fw)) / denom)
+
+    # :547-602
+    @staticmethod
+    def potential_transpiration(lw_net, sw_rad, sw_albedo, pressure, temp_k,
+                                vpd, fpar, rh=None, fw=None, alpha=1.26):
+        if rh is None:
+            rh = rhumidity_clamped(temp_k, vpd)
+        if fw is None:
+            fw = f_wet_of(rh)
+        rad_net = sw_rad * (1 - sw_albedo) + lw_net
+        rad_canopy = fpar * rad_net
+        s = svp_slope(temp_k)
+        gamma = psychrometric_constant(pressure, temp_k)
+        return (alpha * (s * rad_canopy) * (1 - fw)) / (s + gamma)
 
     # :795-864
     def evaporation_soil(self, pressure, temp_k, vpd, fpar, rad_soil,
