@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 4
+#define MOD16_ABI_VERSION 5
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -172,6 +172,10 @@ typedef struct mod16_objective {
   int32_t* gate;           /* device (D,) or NULL: 1 where any g_surf > 0 for the draw */
   void* workspace;         /* device scratch, 256-byte aligned */
   int64_t workspace_bytes; /* >= mod16_objective_workspace_bytes(T, N, D, f32) */
+  double* raw;             /* device (D, 5) or NULL: the un-gated statistics sse_open, n_open,
+                              sse_closed, n_closed, any(g_surf > 0) of THIS call's elements.
+                              A site-sharded multi-GPU batch all-reduces them (sum) and then
+                              applies each draw's gate over all shards (any > 0). */
 } mod16_objective_t;
 
 int64_t mod16_objective_workspace_bytes(int64_t T, int64_t N, int64_t D, int is_f32);

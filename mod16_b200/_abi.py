@@ -19,7 +19,7 @@ FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                         'libmod16_b200.so')
 
@@ -60,7 +60,7 @@ class Objective(ctypes.Structure):
     _fields_ = [('draws', ctypes.c_void_p), ('observed', Driver), ('weights', Driver),
                 ('sse', ctypes.c_void_p), ('count', ctypes.c_void_p),
                 ('gate', ctypes.c_void_p), ('workspace', ctypes.c_void_p),
-                ('workspace_bytes', ctypes.c_int64)]
+                ('workspace_bytes', ctypes.c_int64), ('raw', ctypes.c_void_p)]
 
 
 MAX_OP_INPUTS = 12

@@ -67,6 +67,7 @@ struct ObjArgs {
   double* sse;
   double* count;
   int32_t* gate_out;
+  double* raw;             // (D, 5) un-gated statistics, or NULL
 };
 
 template <typename R>
@@ -333,7 +334,13 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 __device__ __forceinline__ void finish_draw(int gate_mode, bool is_static, double sse_o,
                                             double n_o, double sse_c, double n_c, bool any,
-                                            double& sse, double& cnt, int& gate) {
+                                            double& sse, double& cnt, int& gate,
+                                            double* raw = nullptr) {
+  if (raw) {
+    raw[0] = sse_o; raw[1] = n_o;
+    raw[2] = is_static ? sse_c : sse_o; raw[3] = is_static ? n_c : n_o;
+    raw[4] = any ? 1.0 : 0.0;
+  }
   bool open = true;
   if (is_static) open = gate_mode == 1 || (gate_mode == 0 && any);
   sse = open ? sse_o : sse_c;
@@ -405,7 +412,7 @@ objective_exact_kernel(const __grid_constant__ ObjArgs<R> a, const int mode) {
         double sse, cnt;
         int gate;
         finish_draw(a.gate_mode, SEM == SEM_STATIC, tot[0], tot[1], tot[2], tot[3], tot[4] > 0.0,
-                    sse, cnt, gate);
+                    sse, cnt, gate, a.raw ? a.raw + d * 5 : nullptr);
         a.sse[d] = sse;
         a.count[d] = cnt;
         if (a.gate_out) a.gate_out[d] = gate;
@@ -449,7 +456,8 @@ objective_reduce_kernel(const __grid_constant__ ObjArgs<float> a, const int is_s
   }
   double sse, cnt;
   int gate;
-  finish_draw(a.gate_mode, is_static != 0, sse_o, n_o, sse_c, n_c, any, sse, cnt, gate);
+  finish_draw(a.gate_mode, is_static != 0, sse_o, n_o, sse_c, n_c, any, sse, cnt, gate,
+              a.raw ? a.raw + d * 5 : nullptr);
   a.sse[d] = sse;
   a.count[d] = cnt;
   if (a.gate_out) a.gate_out[d] = gate;
@@ -532,7 +540,7 @@ static int fill_obj_args(const mod16_drivers_t* drv, const mod16_objective_t* ob
   a.bad_list = (int32_t*)(ws + p.off_bad);
   a.nf_chunks = p.nf_chunks;
   a.ne_slots = p.fast ? 1 : p.ne_chunks;
-  a.sse = ob->sse; a.count = ob->count; a.gate_out = ob->gate;
+  a.sse = ob->sse; a.count = ob->count; a.gate_out = ob->gate; a.raw = ob->raw;
   return MOD16_OK;
 }
 
@@ -571,6 +579,7 @@ static int run_objective(const mod16_drivers_t* drv, const mod16_objective_t* ob
     M16_CUDA_CHECK(cudaMemsetAsync(ob->sse, 0, 8 * D, st));
     M16_CUDA_CHECK(cudaMemsetAsync(ob->count, 0, 8 * D, st));
     if (ob->gate) M16_CUDA_CHECK(cudaMemsetAsync(ob->gate, 0, 4 * D, st));
+    if (ob->raw) M16_CUDA_CHECK(cudaMemsetAsync(ob->raw, 0, 8 * 5 * D, st));
     return MOD16_OK;
   }
 #define M16_EXACT(MODE, GRID)                                                              \

@@ -82,6 +82,37 @@ def forward_global_gate(drivers, *, group=None, forward=run_forward, device=None
     return outs
 
 
+def objective_site_sharded(backend, draws, group=None):
+    '''
+    Objective batch with the SITES (elements) sharded across ranks: ``backend`` is this rank's
+    ``ObjectiveBackend`` over its own sites, every rank passes the same (D, 11) ``draws``.
+    One all-reduce(sum) of the (D, 5) un-gated statistics; each draw's gate is then taken
+    over all shards, exactly as one reference call per draw on the whole data set would
+    (``np.any(g_surf > 0)``, reference mod16/__init__.py:343).  Returns (sse, count) tensors.
+    '''
+    from .objective import finish_raw
+    raw = backend(draws, raw=True)
+    rank, size = world(group)
+    if size > 1:
+        dist.all_reduce(raw, op=dist.ReduceOp.SUM, group=group)
+    sse, cnt, _ = finish_raw(raw, backend.semantics, backend.gate)
+    return sse, cnt
+
+
+def objective_draw_sharded(backend, draws, group=None):
+    '''
+    Objective batch with the DRAWS sharded across ranks (every rank holds all sites): rank r
+    evaluates ``draw_range(D, r, world)``; the per-draw results are all-gathered.  No
+    data-path collective.  Returns (sse, count) tensors of D entries on every rank.
+    '''
+    rank, size = world(group)
+    D = len(draws)
+    lo, hi = draw_range(D, rank, size)
+    sse, cnt = backend(draws[lo:hi], as_torch=True)
+    both = gather_draws(torch.stack([sse, cnt], dim=1), D, group)
+    return both[:, 0], both[:, 1]
+
+
 def reduce_objective(sse, count, group=None):
     '''
     Site-sharded objective batch: sums the per-draw partials (float64 tensors of D entries)

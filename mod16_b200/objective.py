@@ -83,8 +83,15 @@ class ObjectiveBackend(object):
                     len(self.full_shape))
             self._staged = st  # keeps the device copies alive
         self._ws = None
+        self.semantics, self.gate = semantics, gate
 
-    def __call__(self, draws, stream=None, return_gate=False, as_torch=False):
+    def __call__(self, draws, stream=None, return_gate=False, as_torch=False, raw=False):
+        '''
+        Returns ``(sse, count)`` (+ ``gate`` with ``return_gate``) for the (D, 11) ``draws``.
+        ``raw=True`` returns instead the (D, 5) CUDA tensor of un-gated statistics
+        [sse_open, n_open, sse_closed, n_closed, any(g_surf > 0)] of this backend's elements
+        (see ``finish_raw`` and ``distributed.objective_site_sharded``).
+        '''
         dev = self.device
         with torch.cuda.device(dev):
             d = _draw_matrix(draws, dev)
@@ -98,7 +105,9 @@ class ObjectiveBackend(object):
             sse = torch.empty(D, device=dev, dtype=torch.float64)
             cnt = torch.empty(D, device=dev, dtype=torch.float64)
             gate = torch.empty(D, device=dev, dtype=torch.int32) if return_gate else None
+            raw_t = torch.empty((D, 5), device=dev, dtype=torch.float64) if raw else None
             co = self.co
+            co.raw = raw_t.data_ptr() if raw else None
             co.draws = d.data_ptr()
             co.sse = sse.data_ptr()
             co.count = cnt.data_ptr()
@@ -113,6 +122,8 @@ class ObjectiveBackend(object):
             if stream is not None and s != torch.cuda.current_stream(dev):
                 for t in (d, sse, cnt, ws):
                     t.record_stream(s)
+            if raw:
+                return raw_t
             if as_torch:
                 return (sse, cnt, gate) if return_gate else (sse, cnt)
             out = (sse.cpu().numpy(), cnt.cpu().numpy())
@@ -125,9 +136,27 @@ class ObjectiveBackend(object):
         return -rmsd(sse, cnt)
 
 
+def finish_raw(raw, semantics='static', gate='global'):
+    '''
+    Applies each draw's transpiration gate to (summed) un-gated statistics ``raw`` (D, 5):
+    returns (sse, count, gate_open) tensors.  The same selection the reduce kernel makes.
+    '''
+    any_pos = raw[:, 4] > 0
+    if semantics != 'static' or gate == 'open':
+        use_open = torch.ones_like(any_pos)
+    elif gate == 'closed':
+        use_open = torch.zeros_like(any_pos)
+    else:
+        use_open = any_pos
+    sse = torch.where(use_open, raw[:, 0], raw[:, 2])
+    cnt = torch.where(use_open, raw[:, 1], raw[:, 3])
+    return sse, cnt, any_pos
+
+
 def objective_batch(draws, drivers, observed, weights=None, **kw):
     'One-shot form of ``ObjectiveBackend``: returns (sse, count) per draw.'
-    call_kw = dict((k, kw.pop(k)) for k in ('stream', 'return_gate', 'as_torch') if k in kw)
+    call_kw = dict((k, kw.pop(k)) for k in ('stream', 'return_gate', 'as_torch', 'raw')
+                   if k in kw)
     return ObjectiveBackend(drivers, observed, weights, **kw)(draws, **call_kw)
 
 

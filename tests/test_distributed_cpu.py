@@ -88,6 +88,80 @@ def _worker(rank, size, port, case, q):
         dist.destroy_process_group()
 
 
+class _OracleBackend(object):
+    'Stands in for ObjectiveBackend: un-gated (D, 5) statistics from the oracle, one call per draw.'
+    semantics, gate = 'static', 'global'
+
+    def __init__(self, drv, obs):
+        self.drv, self.obs = drv, obs
+
+    def _raw(self, draws):
+        rows = []
+        for x in draws:
+            x = list(np.asarray(x, np.float64))
+            with np.errstate(all='ignore'):
+                so, no = orc.objective_stats(orc.static_et(x, *self.drv, gate='open'), self.obs)
+                sc, nc = orc.objective_stats(orc.static_et(x, *self.drv, gate='closed'), self.obs)
+                g = (x[7] * orc.ramp_up(self.drv[8] - 273.15, x[0], x[1]) *
+                     orc.ramp_down(self.drv[9], x[2], x[3])) / orc.r_correction(
+                         self.drv[11], self.drv[5])
+            rows.append([so, no, sc, nc, float(np.any(g > 0))])
+        return torch.tensor(rows, dtype=torch.float64)
+
+    def __call__(self, draws, raw=False, as_torch=False):
+        r = self._raw(draws)
+        if raw:
+            return r
+        from mod16_b200.objective import finish_raw
+        sse, cnt, _ = finish_raw(r)
+        return sse, cnt
+
+
+def _objective_worker(rank, size, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    try:
+        T, N, nd = 5, 48, 7
+        d = synthetic.host_drivers(T, N, 91)
+        d['tmin'] = d['tmin'].copy()
+        d['tmin'][:, :N // 2] = 230.0            # rank 0's sites never open the Tmin ramp
+        drv = [d[k] for k in NAMES]
+        draws = synthetic.host_param_draws(nd, 5, bplut_column=np.array(BPLUT7))
+        draws[2, 7] = 0.0                        # csl = 0: closed on every shard
+        with np.errstate(all='ignore'):
+            obs = orc.static_et(BPLUT7, *drv) + 3.0
+        ref = [orc.objective_stats(orc.static_et(list(x), *drv), obs) for x in draws]
+        ref_sse = np.array([r[0] for r in ref])
+        ref_cnt = np.array([r[1] for r in ref])
+        lo, hi = D.pixel_range(N, rank, size)
+        mine = _OracleBackend(D.shard_pixels(drv, lo, hi), obs[:, lo:hi])
+        sse, cnt = D.objective_site_sharded(mine, draws)
+        ok = np.allclose(sse.numpy(), ref_sse, rtol=1e-12) and np.array_equal(cnt.numpy(), ref_cnt)
+        everything = _OracleBackend(drv, obs)
+        sse, cnt = D.objective_draw_sharded(everything, draws)
+        ok = ok and np.allclose(sse.numpy(), ref_sse, rtol=1e-12) and \
+            np.array_equal(cnt.numpy(), ref_cnt)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_objective_sharded_by_site_and_by_draw_world2():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_objective_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)], res
+
+
 @pytest.mark.parametrize('case', ['open', 'closed', 'one_shard_open'])
 def test_gate_protocol_and_reductions_world2(case):
     with socket.socket() as s:

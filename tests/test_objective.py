@@ -255,3 +255,39 @@ def test_objective_batch_sobol_sized_slice(cuda_lib):
     assert np.all(np.abs(r32 - r64) <= np.maximum(1e-5 * r64, 1e-3)), np.abs(r32 - r64).max()
     ref_sse, ref_cnt, tol = _reference_stats(d64, draws[:2], obs, w)
     _check(s32[:2], c32[:2], ref_sse, ref_cnt, tol, np.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_raw_statistics_and_site_sharding_on_one_gpu(cuda_lib, dtype):
+    '''
+    The un-gated (D, 5) statistics: finishing them reproduces (sse, count), and summing the
+    statistics of two site shards before the gate is applied equals the unsharded call --
+    including a draw whose gate is open on one shard only.
+    '''
+    import torch
+    from mod16_b200.objective import ObjectiveBackend, finish_raw
+    T, N, D = 9, 256, 40
+    drv, d64, draws, obs, w = _problem(T, N, D, 52, dtype=dtype, fixed=False)
+    drv[8] = drv[8].copy()
+    drv[8][:, :N // 2] = 230.0                 # shard 0 never opens the Tmin ramp (< -35 C)
+    draws[3, 7] = 0.0                          # csl = 0: closed everywhere
+    whole = ObjectiveBackend(drv, obs, w, dtype=dtype)
+    sse, cnt, gate = whole(draws, return_gate=True)
+    raw = whole(draws, raw=True)
+    s2, c2, g2 = finish_raw(raw)
+    assert np.array_equal(s2.cpu().numpy(), sse) and np.array_equal(c2.cpu().numpy(), cnt)
+    assert np.array_equal(g2.cpu().numpy(), gate) and not gate[3]
+    parts = []
+    for lo, hi in ((0, N // 2), (N // 2, N)):
+        sl = [v[:, lo:hi] if isinstance(v, np.ndarray) and v.ndim == 2 else
+              (v[lo:hi] if isinstance(v, np.ndarray) and v.ndim == 1 else v) for v in drv]
+        parts.append(ObjectiveBackend(sl, obs[:, lo:hi], w[:, lo:hi], dtype=dtype)(draws, raw=True))
+    assert float(parts[0][:, 4].max()) == 0.0 and float(parts[1][:, 4].max()) == 1.0
+    s3, c3, _ = finish_raw(parts[0] + parts[1])
+    assert np.array_equal(c3.cpu().numpy(), cnt)
+    assert np.allclose(s3.cpu().numpy(), sse, rtol=1e-6 if dtype == np.float32 else 1e-12)
+    # gating each shard on its own would be wrong for shard 0 (it would drop transpiration)
+    s0, _, _ = finish_raw(parts[0])
+    assert not np.allclose(s0.cpu().numpy() + finish_raw(parts[1])[0].cpu().numpy(), sse,
+                           rtol=1e-6)
