@@ -150,7 +150,7 @@ def test_medium_grid_against_oracle(cuda_lib, dtype, kind, nan):
         ref = orc.static_et(vec, *as_f64(drv))
     got = MOD16._et_by_pft(table, pft, *drv, dtype=dtype)
     m = parity.assert_parity(got, ref, dtype, what='%s %s' % (kind, np.dtype(dtype).name),
-                             allow_fail=0 if dtype == np.float64 else 2)
+                             allow_fail=0)
     print('medium grid', np.dtype(dtype).name, kind, m)
 
 
