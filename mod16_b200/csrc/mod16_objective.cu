@@ -7,7 +7,7 @@
 //   2. obj_scan_kernel      exclusive scan of the per-block counts (deterministic, stable
 //                           compaction -- the summation order never depends on timing)
 //   3. obj_pack_kernel      writes the draw-independent coefficients of every fast element
-//                           (obj::ElemRec, 192 B) and the index list of the exact elements
+//                           (obj::ElemRec, 160 B) and the index list of the exact elements
 //   4. objective_fast_kernel  the hot loop.  Thread = two draws (the two lanes of the
 //                           packed-FP32 instructions), block = 512 draws x one chunk of the
 //                           element stream.  A producer warp streams the records through a
@@ -16,7 +16,7 @@
 //                           record with warp-uniform 128-bit loads, so an element's
 //                           coefficients are scalar operands and element properties are
 //                           uniform branches.  Bound: FP32 issue (~65 lane-operations and 6
-//                           MUFU per draw-element; nothing is re-read from HBM but 192 B per
+//                           MUFU per draw-element; nothing is re-read from HBM but 160 B per
 //                           512 draw-elements).
 //      objective_exact_kernel  the exact elements x all draws, op-for-op in double
 //   5. objective_reduce_kernel  per draw: sums the chunk partials in a fixed order, applies
@@ -39,7 +39,7 @@ constexpr int OBJ_CONSUMER_WARPS = 8;
 constexpr int OBJ_CONSUMERS = OBJ_CONSUMER_WARPS * 32;
 constexpr int OBJ_THREADS = OBJ_CONSUMERS + 32;
 constexpr int OBJ_DRAWS_PER_BLOCK = OBJ_CONSUMERS * 2;
-constexpr int OBJ_TILE = 32;    // elements per stage (6 KB)
+constexpr int OBJ_TILE = 32;    // elements per stage (5 KB)
 constexpr int OBJ_STAGES = 4;
 constexpr int OBJ_CLS_THREADS = 256;
 constexpr int OBJ_EX_THREADS = 128;
@@ -221,6 +221,10 @@ obj_pack_kernel(const __grid_constant__ ObjArgs<float> a) {
 #define M16_OBJ_UNROLL 1
 #endif
 constexpr int OBJ_UNROLL = M16_OBJ_UNROLL;
+// MODE 0: gate-open sums only (a draw whose gate turns out closed is redone by the exact
+// kernel: it needs csl == 0 or a Tmin ramp above every Tmin); 1: gate-closed sums only
+// (MOD16_GATE_CLOSED); 2: both (the un-gated statistics of a site-sharded batch).
+template <int MODE>
 __global__ void __launch_bounds__(OBJ_THREADS, M16_OBJ_BLOCKS)
 objective_fast_kernel(const __grid_constant__ ObjArgs<float> a) {
   __shared__ __align__(128) ElemRec ring[OBJ_STAGES][OBJ_TILE];
@@ -299,10 +303,12 @@ objective_fast_kernel(const __grid_constant__ ObjArgs<float> a) {
       const F2 tot = obj::objective_step<F2>(e, dc, tr, gs);
       gmax = fast::vmax(gmax, gs);
       const float w = e.w;
-      const F2 eo = (tot - e.obs) * w;            // (pred - obs) w, gate open
-      const F2 ec = fast::vfma(-tr, w, eo);       // the same without transpiration
-      acc_o = fast::vfma(eo, eo, acc_o);
-      acc_c = fast::vfma(ec, ec, acc_c);
+      const F2 eo = fast::vfma(tot, w, -e.obs_w);  // (pred - obs) w, gate open
+      if (MODE != 1) acc_o = fast::vfma(eo, eo, acc_o);
+      if (MODE != 0) {
+        const F2 ec = fast::vfma(-tr, w, eo);      // the same without transpiration
+        acc_c = fast::vfma(ec, ec, acc_c);
+      }
     }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(empty0 + 8 * stage);
@@ -428,7 +434,7 @@ objective_exact_kernel(const __grid_constant__ ObjArgs<R> a, const int mode) {
 // ---- 5: per-draw reduction of the partials -------------------------------------------------
 __global__ void __launch_bounds__(256)
 objective_reduce_kernel(const __grid_constant__ ObjArgs<float> a, const int is_static,
-                        const int use_fast) {
+                        const int use_fast, const int fast_mode) {
   const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= a.D) return;
   double sse_o = 0.0, sse_c = 0.0, n_o = 0.0, n_c = 0.0;
@@ -454,6 +460,8 @@ objective_reduce_kernel(const __grid_constant__ ObjArgs<float> a, const int is_s
     sse_o += p[0]; n_o += p[1]; sse_c += p[2]; n_c += p[3];
     any = any || p[4] > 0.0;
   }
+  // the fast kernel did not accumulate the sums this draw's gate selects: exact kernel
+  if (use_fast && fast_mode == 0 && is_static && a.gate_mode == 0 && !any) bad = true;
   double sse, cnt;
   int gate;
   finish_draw(a.gate_mode, is_static != 0, sse_o, n_o, sse_c, n_c, any, sse, cnt, gate,
@@ -575,6 +583,7 @@ static int run_objective(const mod16_drivers_t* drv, const mod16_objective_t* ob
     if (rc != MOD16_OK) return rc;
   }
   const unsigned draw_rows = (unsigned)(D < 32768 ? D : 32768);
+  const int fast_mode = ob->raw ? 2 : (a.gate_mode == 2 ? 1 : 0);
   if (p.E == 0) {
     M16_CUDA_CHECK(cudaMemsetAsync(ob->sse, 0, 8 * D, st));
     M16_CUDA_CHECK(cudaMemsetAsync(ob->count, 0, 8 * D, st));
@@ -598,15 +607,17 @@ static int run_objective(const mod16_drivers_t* drv, const mod16_objective_t* ob
       M16_CUDA_CHECK(cudaGetLastError());
       const dim3 grid((unsigned)((D + OBJ_DRAWS_PER_BLOCK - 1) / OBJ_DRAWS_PER_BLOCK),
                       (unsigned)p.nf_chunks);
-      objective_fast_kernel<<<grid, OBJ_THREADS, 0, st>>>(a);
+      if (fast_mode == 0) objective_fast_kernel<0><<<grid, OBJ_THREADS, 0, st>>>(a);
+      else if (fast_mode == 1) objective_fast_kernel<1><<<grid, OBJ_THREADS, 0, st>>>(a);
+      else objective_fast_kernel<2><<<grid, OBJ_THREADS, 0, st>>>(a);
       M16_CUDA_CHECK(cudaGetLastError());
     }
     M16_EXACT(1, dim3(1, draw_rows));
   } else {
     M16_EXACT(0, dim3((unsigned)p.ne_chunks, draw_rows));
   }
-  objective_reduce_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(ar, is_static ? 1 : 0,
-                                                                      p.fast ? 1 : 0);
+  objective_reduce_kernel<<<(unsigned)((D + 255) / 256), 256, 0, st>>>(
+      ar, is_static ? 1 : 0, p.fast ? 1 : 0, fast_mode);
   M16_CUDA_CHECK(cudaGetLastError());
   if (p.fast) M16_EXACT(2, dim3(1, (unsigned)(D < 1024 ? D : 1024)));
 #undef M16_EXACT

@@ -28,30 +28,27 @@ namespace obj {
 using fast::F2;
 using fast::M2;
 
-// ---- per-element record (48 floats = 12 quads, read with uniform 128-bit loads) ---------
-// SAs0 / SAs1: S x radiation reaching the soil with the soil heat flux G = 0 / G computed;
-// which one applies depends on the draw (annual-temperature window, :230-233).
+// ---- per-element record (40 floats = 10 quads, read with uniform 128-bit loads) ---------
+// The element's coefficients are pre-multiplied as far as the draw-dependent algebra allows:
+//   transpiration   num = gl_sh KfX + KfBSA,  G Yd = gl_sh GX + GB          (Yd = gl_sh X + B)
+//   bare soil       q = (r P1X + P2X) / (r (r Q1 + Q2)),  r = r_tot / r_corr
+//                   P1 = S As + Ko B, P2 = Ko X, Q1 = G B, Q2 = (S + G) X    (W = r B + X)
+//   wet canopy      num = gl_sh Kfu + KfBSA,  G Y = gl_sh Gu + GB            (Y = gl_sh u + B)
+// P1X0 / P1X1: with the soil heat flux G = 0 / G computed; which one applies depends on the
+// draw (annual-temperature window, :230-233).
 struct alignas(16) ElemRec {
-  // quad 0
-  float obs, w, tann_eff, tminc;
-  // quads 1-4: day, always needed
-  float d_vpd, d_inv_rc, d_lo, d_X;
-  float d_B, d_Kf, d_SA, d_SGX;
-  float d_G, d_oX, d_SAs0, d_SAs1;
-  float d_Ko, d_SX, d_vl, d_omfw;
-  // quad 5: day wet canopy (f_wet > 0 only); d_fw doubles as the branch condition
-  float d_fw, d_u, d_Su, d_fwu;
-  // quads 6-8: night, always needed
-  float n_vpd, n_inv_rc, n_X, n_B;
-  float n_G, n_SAs0, n_SAs1, n_Ko;
-  float n_SX, n_vl, n_omfw, n_fw;
-  // quads 9-10: night wet canopy
-  float n_Kf, n_SA, n_u, n_Su;
-  float n_fwu, pad0, pad1, pad2;
-  // quad 11: spare (keeps the record at 192 bytes, a multiple of 64)
-  float pad3, pad4, pad5, pad6;
+  float obs_w, w, tann_eff, tminc;          // obs * w, w, window temperature, Tmin - 273.15
+  float d_vpd, d_inv_rc, d_lo, d_KfX;       // day, always needed
+  float d_KfBSA, d_GX, d_GB, d_SGX;
+  float d_oX, d_P1X0, d_P1X1, d_P2X;
+  float d_Q1, d_vl, d_omfw, d_fw;           // d_fw doubles as the wet-canopy branch condition
+  float d_Kfu, d_Gu, d_Su, d_fwu;           // day wet canopy (f_wet > 0 only)
+  float n_vpd, n_inv_rc, n_P1X0, n_P1X1;    // night, always needed
+  float n_P2X, n_Q1, n_Q2, n_vl;
+  float n_omfw, n_fw, n_KfBSA, n_GB;        // (the last two: night wet canopy)
+  float n_Kfu, n_Gu, n_Su, n_fwu;           // night wet canopy
 };
-static_assert(sizeof(ElemRec) == 192, "ElemRec layout");
+static_assert(sizeof(ElemRec) == 160, "ElemRec layout");
 
 // Element coefficients of one half-day; same expressions as fast::half_fast.
 struct HalfCoef {
@@ -121,26 +118,35 @@ M16_HD bool make_elem_rec(const fast::StepIn& in, float obs, float w, ElemRec& r
     as_d[k] = omf * r_d;
     as_n[k] = omf * r_n;
   }
-  r.obs = obs; r.w = w;
+  r.obs_w = obs * w; r.w = w;
   // the window's draw-dependent side is t_ann > 273.15 + tmin_open (:233): elements whose
   // other two conditions fail can never satisfy it
   r.tann_eff = (dt_ok && below) ? in.t_ann : -1.0e30f;
   r.tminc = celsius<float>(in.tmin);
   const float fpar = in.fpar;
   // day
-  r.d_vpd = in.vpd_d; r.d_inv_rc = d.inv_rc; r.d_lo = in.lai * d.omfw; r.d_X = d.X;
-  r.d_B = d.B; r.d_Kf = d.Kv * fpar; r.d_SA = d.S * (fpar * a_d); r.d_SGX = (d.S + d.G) * d.X;
-  r.d_G = d.G; r.d_oX = d.omfw * d.X; r.d_SAs0 = d.S * as_d[0]; r.d_SAs1 = d.S * as_d[1];
-  r.d_Ko = d.Kv * omf; r.d_SX = d.S * d.X; r.d_vl = d.vl; r.d_omfw = d.omfw;
-  r.d_fw = d.fw; r.d_u = (in.lai * d.fw) * d.X; r.d_Su = d.S * r.d_u; r.d_fwu = d.fw * r.d_u;
+  const float d_Kf = d.Kv * fpar, d_Ko = d.Kv * omf, d_SA = d.S * (fpar * a_d);
+  r.d_vpd = in.vpd_d; r.d_inv_rc = d.inv_rc; r.d_lo = in.lai * d.omfw;
+  r.d_KfX = d_Kf * d.X; r.d_KfBSA = fmaf(d_Kf, d.B, d_SA);
+  r.d_GX = d.G * d.X; r.d_GB = d.G * d.B; r.d_SGX = (d.S + d.G) * d.X;
+  r.d_oX = d.omfw * d.X;
+  r.d_P1X0 = fmaf(d_Ko, d.B, d.S * as_d[0]) * d.X;
+  r.d_P1X1 = fmaf(d_Ko, d.B, d.S * as_d[1]) * d.X;
+  r.d_P2X = (d_Ko * d.X) * d.X;
+  r.d_Q1 = r.d_GB; r.d_vl = d.vl; r.d_omfw = d.omfw; r.d_fw = d.fw;
+  const float d_u = (in.lai * d.fw) * d.X;
+  r.d_Kfu = d_Kf * d_u; r.d_Gu = d.G * d_u; r.d_Su = d.S * d_u; r.d_fwu = d.fw * d_u;
   // night
-  r.n_vpd = in.vpd_n; r.n_inv_rc = n.inv_rc; r.n_X = n.X; r.n_B = n.B;
-  r.n_G = n.G; r.n_SAs0 = n.S * as_n[0]; r.n_SAs1 = n.S * as_n[1]; r.n_Ko = n.Kv * omf;
-  r.n_SX = n.S * n.X; r.n_vl = n.vl; r.n_omfw = n.omfw; r.n_fw = n.fw;
-  r.n_Kf = n.Kv * fpar; r.n_SA = n.S * (fpar * a_nc); r.n_u = (in.lai * n.fw) * n.X;
-  r.n_Su = n.S * r.n_u;
-  r.n_fwu = n.fw * r.n_u;
-  r.pad0 = r.pad1 = r.pad2 = r.pad3 = r.pad4 = r.pad5 = r.pad6 = 0.0f;
+  const float n_Kf = n.Kv * fpar, n_Ko = n.Kv * omf, n_SA = n.S * (fpar * a_nc);
+  r.n_vpd = in.vpd_n; r.n_inv_rc = n.inv_rc;
+  r.n_P1X0 = fmaf(n_Ko, n.B, n.S * as_n[0]) * n.X;
+  r.n_P1X1 = fmaf(n_Ko, n.B, n.S * as_n[1]) * n.X;
+  r.n_P2X = (n_Ko * n.X) * n.X;
+  r.n_Q1 = n.G * n.B; r.n_Q2 = (n.S + n.G) * n.X; r.n_vl = n.vl;
+  r.n_omfw = n.omfw; r.n_fw = n.fw;
+  r.n_KfBSA = fmaf(n_Kf, n.B, n_SA); r.n_GB = r.n_Q1;
+  const float n_u = (in.lai * n.fw) * n.X;
+  r.n_Kfu = n_Kf * n_u; r.n_Gu = n.G * n_u; r.n_Su = n.S * n_u; r.n_fwu = n.fw * n_u;
   return true;
 }
 
@@ -184,23 +190,24 @@ M16_HD DrawConstV<F2> pair_draws(const DrawConstV<float>& a, const DrawConstV<fl
 }
 
 // scalar-on-the-left forms used below (the element coefficient is the scalar)
-M16_HD float bsub(float a, float b) { return a - b; }
-M16_HD F2 bsub(float a, F2 b) { return a - b; }
 M16_HD float bsel(bool m, float a, float b) { return m ? a : b; }
 M16_HD F2 bsel(M2 m, float a, float b) { return F2{m.x ? a : b, m.y ? a : b}; }
 M16_HD bool bgt(float a, float b) { return a > b; }
 M16_HD M2 bgt(float a, F2 b) { return M2{a > b.x, a > b.y}; }
 
 // One element for one draw (or draw pair).  Returns day + night with the transpiration
-// gate OPEN; `tr` is the day transpiration (so the caller can form the gate-closed total
-// as well) and `gs` the gate quantity csl m_tmin m_vpd (> 0 <=> g_surf > 0, :343).
+// gate OPEN; `tr` is the day transpiration (the gate-closed total is the result minus tr)
+// and `gs` the gate quantity csl m_tmin m_vpd (> 0 <=> g_surf > 0, :343).
+// (Measured and rejected: sharing one reciprocal between the day's transpiration and soil
+// terms, a / b + c / d = (a d + c b) / (b d), is slower -- 413 vs 461 G draw-elements/s --
+// the FMA pipe, not the MUFU pipe, is what the loop saturates.)
 template <class V>
 M16_HD V objective_step(const ElemRec& e, const DrawConstV<V>& c, V& tr, V& gs) {
   using namespace fast;
   typedef typename MaskOf<V>::type M;
   const M win = bgt(e.tann_eff, c.tann_lo);                                  // :233
   // ---- day
-  const V m_t = vsat(bsub(e.tminc, c.tmin_close) * c.inv_dtmin);             // :325
+  const V m_t = vsat((e.tminc - c.tmin_close) * c.inv_dtmin);                // :325
   const V m_vd = vsat((c.vpd_close - e.d_vpd) * c.inv_dvpd);                 // :326
   gs = (c.csl * m_t) * m_vd;                                                 // :327
   V tot;
@@ -208,44 +215,37 @@ M16_HD V objective_step(const ElemRec& e, const DrawConstV<V>& c, V& tr, V& gs) 
     const V sc = (c.g_cut + gs) * e.d_inv_rc;                                // :328-329
     const V gbl = c.gl_sh * e.d_lo;                                          // :333
     const V prod = gbl * sc, sum = gbl + sc;                                 // :334-335
-    const V Yd = vfma(c.gl_sh, e.d_X, e.d_B);                                // :340
-    const V num = vfma(e.d_Kf, Yd, e.d_SA);
-    const V den = vfma(e.d_SGX * prod, splat<V>(1.0f), (e.d_G * Yd) * sum);
-    tr = (num * (e.d_oX * prod)) * vrcp(den);                                // :344-346
+    const V num = vfma(c.gl_sh, e.d_KfX, e.d_KfBSA);                         // :344-345
+    const V gyd = vfma(c.gl_sh, e.d_GX, e.d_GB);
+    const V den = vfma(e.d_SGX, prod, gyd * sum);                            // :346
+    const V nt = num * (e.d_oX * prod);
     // bare soil (:357-376)
     const V r_t = vfma(-c.rbl_delta, m_vd, c.rbl_max) * e.d_inv_rc;
-    const V W = vfma(r_t, e.d_B, e.d_X);
-    const V sas = bsel(win, e.d_SAs1, e.d_SAs0);
-    const V nums = vfma(sas, r_t, e.d_Ko * W);
-    const V dens = r_t * vfma(e.d_G, W, e.d_SX);
-    const V qn = (nums * e.d_X) * vrcp(dens);
+    const V nx = vfma(r_t, bsel(win, e.d_P1X1, e.d_P1X0), e.d_P2X);
+    const V dens = r_t * vfma(r_t, e.d_Q1, e.d_SGX);
     const V pw = vex2(c.inv_beta * e.d_vl);
     const V mix = vfma(e.d_omfw, pw, e.d_fw);
-    tot = vfma(qn, mix, tr);
+    tr = nt * vrcp(den);
+    tot = vfma(nx * vrcp(dens), mix, tr);
   }
   if (e.d_fw > 0.0f) {  // wet canopy (:305-320); uniform branch
-    const V Y = vfma(c.gl_sh, e.d_u, e.d_B);
-    const V num = vfma(e.d_Kf, Y, e.d_SA);
-    const V den = vfma(c.gl_wv, e.d_Su, e.d_G * Y);
+    const V num = vfma(c.gl_sh, e.d_Kfu, e.d_KfBSA);
+    const V den = vfma(c.gl_wv, e.d_Su, vfma(c.gl_sh, e.d_Gu, e.d_GB));
     tot = vfma(num * (c.gl_wv * e.d_fwu), vrcp(den), tot);
   }
   // ---- night (static: no transpiration, :323-348)
   {
     const V m_vn = vsat((c.vpd_close - e.n_vpd) * c.inv_dvpd);
     const V r_t = vfma(-c.rbl_delta, m_vn, c.rbl_max) * e.n_inv_rc;
-    const V W = vfma(r_t, e.n_B, e.n_X);
-    const V sas = bsel(win, e.n_SAs1, e.n_SAs0);
-    const V nums = vfma(sas, r_t, e.n_Ko * W);
-    const V dens = r_t * vfma(e.n_G, W, e.n_SX);
-    const V qn = (nums * e.n_X) * vrcp(dens);
+    const V nx = vfma(r_t, bsel(win, e.n_P1X1, e.n_P1X0), e.n_P2X);
+    const V dens = r_t * vfma(r_t, e.n_Q1, e.n_Q2);
     const V pw = vex2(c.inv_beta * e.n_vl);
     const V mix = vfma(e.n_omfw, pw, e.n_fw);
-    tot = vfma(qn, mix, tot);
+    tot = vfma(nx * vrcp(dens), mix, tot);
   }
   if (e.n_fw > 0.0f) {
-    const V Y = vfma(c.gl_sh, e.n_u, e.n_B);
-    const V num = vfma(e.n_Kf, Y, e.n_SA);
-    const V den = vfma(c.gl_wv, e.n_Su, e.n_G * Y);
+    const V num = vfma(c.gl_sh, e.n_Kfu, e.n_KfBSA);
+    const V den = vfma(c.gl_wv, e.n_Su, vfma(c.gl_sh, e.n_Gu, e.n_GB));
     tot = vfma(num * (c.gl_wv * e.n_fwu), vrcp(den), tot);
   }
   return tot;

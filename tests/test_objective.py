@@ -276,7 +276,10 @@ def test_raw_statistics_and_site_sharding_on_one_gpu(cuda_lib, dtype):
     sse, cnt, gate = whole(draws, return_gate=True)
     raw = whole(draws, raw=True)
     s2, c2, g2 = finish_raw(raw)
-    assert np.array_equal(s2.cpu().numpy(), sse) and np.array_equal(c2.cpu().numpy(), cnt)
+    # (a draw whose gate is closed takes the double kernel in the plain call and the float
+    # kernel's closed sums in the raw call: equal to float32 rounding, not bit for bit)
+    assert np.allclose(s2.cpu().numpy(), sse, rtol=1e-6 if dtype == np.float32 else 0, atol=0)
+    assert np.array_equal(c2.cpu().numpy(), cnt)
     assert np.array_equal(g2.cpu().numpy(), gate) and not gate[3]
     parts = []
     for lo, hi in ((0, N // 2), (N // 2, N)):
