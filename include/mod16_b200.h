@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 5
+#define MOD16_ABI_VERSION 6
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -217,6 +217,10 @@ int mod16_objective_batch_f64(const mod16_drivers_t* drivers, const mod16_object
  *                                   opt[0] = daytime (0 / 1), opt[1] = tiny         kg m-2 s-1
  *   POTENTIAL_TRANSPIRATION :547    lw_net, sw_rad, sw_albedo, pressure, temp_k, vpd,
  *                                   fpar, [rhumidity], [f_wet]; opt[0] = alpha      W m-2
+ *   DAYLENGTH_COMPOSITE  tests/verification/verify2.py:112-115
+ *                                   pred_day, pred_night [kg m-2 s-1], daylength [h];
+ *                                   opt[0] = days per composite (8):
+ *                                   day dl n 3600 + night (24 - dl) n 3600          kg m-2 (n d)-1
  */
 enum {
   MOD16_OP_SVP = 0, MOD16_OP_SVP_SLOPE, MOD16_OP_LHV, MOD16_OP_PSYCHROMETRIC,
@@ -224,7 +228,7 @@ enum {
   MOD16_OP_RADIATION_NET, MOD16_OP_SOIL_HEAT_FLUX, MOD16_OP_RADIATION_SOIL,
   MOD16_OP_POTENTIAL_SOIL_EVAPORATION, MOD16_OP_EVAPORATION_SOIL,
   MOD16_OP_EVAPORATION_WET_CANOPY, MOD16_OP_SURFACE_CONDUCTANCE, MOD16_OP_TRANSPIRATION,
-  MOD16_OP_POTENTIAL_TRANSPIRATION, MOD16_OP_COUNT
+  MOD16_OP_POTENTIAL_TRANSPIRATION, MOD16_OP_DAYLENGTH_COMPOSITE, MOD16_OP_COUNT
 };
 #define MOD16_MAX_OP_INPUTS 12
 

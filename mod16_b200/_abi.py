@@ -19,7 +19,7 @@ FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                         'libmod16_b200.so')
 
@@ -67,7 +67,8 @@ MAX_OP_INPUTS = 12
 OPS = ('svp', 'svp_slope', 'lhv', 'psychrometric', 'air_density', 'rhumidity', 'vpd',
        'air_pressure', 'radiation_net', 'soil_heat_flux', 'radiation_soil',
        'potential_soil_evaporation', 'evaporation_soil', 'evaporation_wet_canopy',
-       'surface_conductance', 'transpiration', 'potential_transpiration')
+       'surface_conductance', 'transpiration', 'potential_transpiration',
+       'daylength_composite')
 
 
 class Elementwise(ctypes.Structure):

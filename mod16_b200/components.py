@@ -93,6 +93,18 @@ def svp_slope(temp_k, s=None, **kw):
     return elementwise('svp_slope', [temp_k, s], **kw)
 
 
+def daylength_composite(pred_day, pred_night, daylength_hours, days=8, **kw):
+    '''
+    Day and night rates [kg m-2 s-1] to the water mass of a ``days``-day composite period
+    [kg m-2], weighting each by its share of the day, as the reference's product comparison
+    does (tests/verification/verify2.py:112-115):
+    ``day * dl * days * 3600 + night * (24 - dl) * days * 3600``.  NaN day length (polar
+    day / night) propagates.  Sums over true composite periods: ``aggregate.time_aggregate``.
+    '''
+    return elementwise('daylength_composite', [pred_day, pred_night, daylength_hours],
+                       opt=(days, 0.0), **kw)
+
+
 class ComponentMixin(object):
     'The static and instance component methods of the reference ``MOD16`` class.'
 

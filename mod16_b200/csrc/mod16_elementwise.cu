@@ -203,6 +203,11 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const __grid_constant_
       o0 = (a.opt[0] * (s * rad_c) * (1.0 - m.fw)) / (s + gamma);
       break;
     }
+    case MOD16_OP_DAYLENGTH_COMPOSITE: {        // tests/verification/verify2.py:112-115
+      const double day = IN(0), night = IN(1), dl = IN(2), nd = a.opt[0];
+      o0 = (day * dl * nd * 60.0 * 60.0) + (night * (24.0 - dl) * nd * 60.0 * 60.0);
+      break;
+    }
   }
 #undef IN
   if (a.out[0]) ((R*)a.out[0])[e] = (R)o0;
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const __grid_constant_
 static const int kOpInputs[MOD16_OP_COUNT][2] = {
     // required, total (required + optional)
     {1, 1}, {1, 2}, {1, 1}, {2, 2}, {3, 3}, {2, 2}, {3, 3}, {1, 1}, {3, 3},
-    {5, 5}, {9, 9}, {5, 9}, {5, 9}, {6, 9}, {2, 2}, {7, 11}, {7, 9}};
+    {5, 5}, {9, 9}, {5, 9}, {5, 9}, {6, 9}, {2, 2}, {7, 11}, {7, 9}, {3, 3}};
 
 template <typename R>
 static int run_elementwise(const mod16_elementwise_t* ew, int64_t T, int64_t N,

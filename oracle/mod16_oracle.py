@@ -512,6 +512,15 @@ def nse_from_stats(sse, obs, norm=True):
     return 1 / (2 - nse) if norm else nse
 
 
+def daylength_composite(pred_day, pred_night, updown, days=8):
+    '''
+    Mass of water per composite period from day / night rates and day length in hours
+    (tests/verification/verify2.py:112-115).
+    '''
+    return ((pred_day * updown * days * 60 * 60) +
+            (pred_night * (24 - updown) * days * 60 * 60))
+
+
 # --------------------------------------------------------------------------
 # Annual sums of the calibration's precipitation constraint
 # --------------------------------------------------------------------------

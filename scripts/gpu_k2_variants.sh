@@ -3,7 +3,7 @@
 tag=$1; D=$2; shift; shift
 out=gpurun_out; mkdir -p $out
 for v in "$@"; do
-  MOD16_B200_LIB=$PWD/mod16_b200/lib/variants/lib$v.so timeout 600 python scripts/bench_objective.py --config calibration --draws $D --steps 3 --cpu-draws 1 > $out/k2_${tag}_$v.json 2> $out/k2_${tag}_$v.err; echo "k2 $v exit $?"
+  MOD16_B200_LIB=$PWD/mod16_b200/lib/variants/lib$v.so timeout 600 python bench.py --workload calibration --draws $D --steps 3 --cpu-draws 1 > $out/k2_${tag}_$v.json 2> $out/k2_${tag}_$v.err; echo "k2 $v exit $?"
   python - <<PY
 import json
 try:

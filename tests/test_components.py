@@ -214,6 +214,27 @@ def test_reads_like_the_reference_unit_tests(cuda_lib):
 
 
 @pytest.mark.gpu
+def test_daylength_composite(cuda_lib):
+    'verify2.py:101-115: instance day / night rates to kg m-2 per 8 days.'
+    from mod16_b200 import MOD16, synthetic
+    from mod16_b200.components import daylength_composite
+    T, N = 46, 33
+    d = synthetic.host_drivers(T, N, 12)
+    drv = [d[k] for k in synthetic.DRIVER_NAMES]
+    P = dict(zip(orc.PARAM_ORDER, [-8., 8.8, 650., 4400., .02, .02, 1e-5, .0055, 60., 95., 250.]))
+    day, night = MOD16(P).evapotranspiration(*drv)
+    with np.errstate(all='ignore'):
+        rd, rn = orc.InstanceModel(P).evapotranspiration(*drv)
+    rng = np.random.default_rng(4)
+    updown = rng.uniform(4, 20, (T, 1)) + np.zeros((T, N))
+    updown[3] = np.nan                                  # polar night: sunrise_sunset gave none
+    got = daylength_composite(day, night, updown)
+    ref = orc.daylength_composite(rd, rn, updown)
+    parity.assert_parity(got, ref, np.float64, 1e-3, what='8-day composite')
+    assert np.isnan(got[3]).all()
+
+
+@pytest.mark.gpu
 def test_component_errors_and_shapes(cuda_lib):
     import torch
     from mod16_b200 import MOD16, _abi, components, svp
