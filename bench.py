@@ -539,6 +539,7 @@ def main():
                            bytes_per_unit * units_per_rank / 1e9)},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                         'frac_of_spec_8tbs': achieved / 8000.0,
                          'kernel': {'pipe': 'forward_pipe_kernel',
                                     'generic': 'forward_strided_fast_kernel',
                                     'mirror': 'forward_strided_kernel<float>'}[args.kernel]
