@@ -381,6 +381,8 @@ def main():
                          'for the CPU arm')
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
+    from mod16_b200.streaming import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
     _abi.load()
@@ -517,7 +519,8 @@ def main():
                'd2h_bytes_per_step': runner.d2h_bytes // reps,
                'sample': '%d steps x %d pixels per GPU from pinned host memory through '
                          'mod16_b200.streaming.StreamedForward (4 slabs, copies overlapped '
-                         'with the kernel)' % (Te, N)}
+                         'with the kernel)%s' % (Te, N, '' if numa is None else
+                                                 '; rank bound to NUMA node %d' % numa)}
         assert np.isfinite(out_host[:1, :4096].numpy()).all()
 
     cpu = None

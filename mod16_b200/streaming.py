@@ -18,6 +18,36 @@ from .synthetic import DRIVER_NAMES, PER_PIXEL
 _PER_STEP = [k for k in DRIVER_NAMES if k not in PER_PIXEL and k != 'sw_rad_night']
 
 
+def bind_to_gpu_numa_node(device_index):
+    '''
+    Restricts this process to the CPU cores of the NUMA node the GPU hangs off (sysfs), so
+    that pinned staging buffers allocated afterwards are node-local (first touch) and
+    host<->device copies of several ranks do not cross the socket interconnect.  Returns the
+    node, or None when the topology cannot be read (single-socket hosts: nothing to do).
+    '''
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), 'pci_domain_id', 0)
+        dev_id = getattr(torch.cuda.get_device_properties(device_index), 'pci_device_id', 0)
+        path = '/sys/bus/pci/devices/%04x:%02x:%02x.0' % (dom, bus, dev_id)
+        node = int(open(path + '/numa_node').read())
+        if node < 0:
+            return None
+        cpus = open('/sys/devices/system/node/node%d/cpulist' % node).read().strip()
+        cores = set()
+        for part in cpus.split(','):
+            a, _, b = part.partition('-')
+            cores.update(range(int(a), int(b or a) + 1))
+        allowed = cores & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 class StreamedForward(object):
     '''
     Parameters
