@@ -4,8 +4,10 @@
 // (/root/reference/mod16/calibration.py:783-790).  HBM-bound: each element is read once
 // (4 or 8 bytes, + the divisor), accumulation is in double.
 //
-// Layout: one thread per pixel (a warp reads 128 contiguous bytes of every row), a slice
-// of time steps per block row; partial sums are flushed with double atomics whenever the
+// Layout: one thread per 16 bytes of a row (4 float / 2 double pixels; one pixel per thread
+// for ragged or unaligned rows), a slice of time steps per block row walked in batches of 8
+// steps whose loads are all issued before the first is used (memory-level parallelism
+// instead of occupancy); partial sums are flushed with double atomics whenever the
 // group index changes (group[t] is uniform across the block, so the flush is
 // warp-uniform).  The domain total per group is a warp-shuffle reduction of the flushed
 // values followed by one atomic per warp.
@@ -33,39 +35,82 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-template <typename R>
-__global__ void __launch_bounds__(256)
+// VEC pixels per thread (one 16-byte load per step and field), AGG_UNROLL steps in flight.
+// 8 steps in flight per thread (16 without a divisor spills at 3 blocks/SM: 2.3 vs 4.3 TB/s)
+
+template <typename R, int VEC>
+struct alignas(sizeof(R) * VEC) Pack { R v[VEC]; };
+
+template <typename R, int VEC, bool HAS_DIV>
+__global__ void __launch_bounds__(256, HAS_DIV ? 2 : 3)
 time_aggregate_kernel(const __grid_constant__ AggArgs<R> a) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  typedef Pack<R, VEC> P;
+  const int64_t n0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   const int64_t t0 = (int64_t)blockIdx.y * a.t_chunk;
   int64_t t1 = t0 + a.t_chunk;
   if (t1 > a.T) t1 = a.T;
-  const bool live = n < a.N;
-  double acc = 0.0;
+  constexpr int AGG_UNROLL = 8;
+  const bool live = n0 < a.N;   // (VEC > 1 only when N % VEC == 0: the whole pack is live)
+  double acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.0;
   int cur = -1;
   auto flush = [&](int g) {  // block-uniform call
     if (g >= 0 && g < a.n_groups) {
-      if (live) atomicAdd(a.out + (int64_t)g * a.N + n, acc);
+      double mine = 0.0;
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          atomicAdd(a.out + (int64_t)g * a.N + n0 + k, acc[k]);
+          mine += acc[k];
+        }
+      }
       if (a.total) {
-        const double w = warp_sum(live ? acc : 0.0);
+        const double w = warp_sum(mine);
         if ((threadIdx.x & 31) == 0) atomicAdd(a.total + g, w);
       }
     }
-    acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.0;
   };
-  for (int64_t t = t0; t < t1; ++t) {
-    const int g = a.group ? __ldg(a.group + t) : 0;
-    if (g != cur) {
-      if (cur != -1) flush(cur);
-      cur = g;
+  for (int64_t tb = t0; tb < t1; tb += AGG_UNROLL) {
+    // issue the loads of the whole batch first: AGG_UNROLL x (1 or 2) 16-byte loads in flight
+    P xs[AGG_UNROLL], ds[HAS_DIV ? AGG_UNROLL : 1];
+    int gs[AGG_UNROLL];
+#pragma unroll
+    for (int u = 0; u < AGG_UNROLL; ++u) {
+      const int64_t t = tb + u;
+      gs[u] = -2;
+      if (t < t1) {
+        gs[u] = a.group ? __ldg(a.group + t) : 0;
+        if (live && gs[u] >= 0 && gs[u] < a.n_groups) {
+          xs[u] = *reinterpret_cast<const P*>(a.x + t * a.N + n0);
+          if (HAS_DIV) ds[u] = *reinterpret_cast<const P*>(a.div + t * a.N + n0);
+        }
+      }
     }
-    if (live && g >= 0 && g < a.n_groups) {
-      double v = (double)__ldg(a.x + t * a.N + n);
-      if (a.div) v = (v * a.scale) / (double)__ldg(a.div + t * a.N + n);  // :783
-      else v = v * a.scale;
-      if (a.clamp_neg) v = v < 0.0 ? 0.0 : v;                             // :784
-      if (a.skip_nan) v = v != v ? 0.0 : v;
-      acc += v;
+#pragma unroll
+    for (int u = 0; u < AGG_UNROLL; ++u) {
+      const int g = gs[u];
+      if (g == -2) break;  // past the end of the chunk (block-uniform)
+      if (g != cur) {
+        if (cur != -1) flush(cur);
+        cur = g;
+      }
+      if (live && g >= 0 && g < a.n_groups) {
+        // the term in the arithmetic of the entry (numpy evaluates float32 arrays in
+        // float32, :783), the accumulation in double
+        const R scale = (R)a.scale;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          R v = xs[u].v[k];
+          if (HAS_DIV) v = (v * scale) / ds[u].v[k];           // :783
+          else v = v * scale;
+          if (a.clamp_neg) v = v < R(0) ? R(0) : v;            // :784
+          if (a.skip_nan) v = v != v ? R(0) : v;
+          acc[k] += (double)v;
+        }
+      }
     }
   }
   if (cur != -1) flush(cur);
@@ -89,7 +134,12 @@ static int run_aggregate(const mod16_aggregate_t* g, int64_t T, int64_t N, uint3
   a.clamp_neg = (flags & MOD16_AGG_CLAMP_NEG) ? 1 : 0;
   a.skip_nan = (flags & MOD16_AGG_SKIP_NAN) ? 1 : 0;
   const int threads = 256;
-  const int64_t bx = (N + threads - 1) / threads;
+  // 16-byte loads when the rows allow them (N a multiple of the pack, aligned bases)
+  constexpr int VEC = 16 / (int)sizeof(R);
+  const bool vec = N % VEC == 0 && (reinterpret_cast<uintptr_t>(g->x) & 15) == 0 &&
+                   (!g->divisor || (reinterpret_cast<uintptr_t>(g->divisor) & 15) == 0);
+  const int64_t per_block = (int64_t)threads * (vec ? VEC : 1);
+  const int64_t bx = (N + per_block - 1) / per_block;
   if (bx > 2147483647LL) return MOD16_ERR_SHAPE;
   // time slices: enough block rows for several waves of 148 SMs x 8 resident blocks
   int64_t want_rows = (148 * 8 * 2 + bx - 1) / bx;
@@ -99,7 +149,11 @@ static int run_aggregate(const mod16_aggregate_t* g, int64_t T, int64_t N, uint3
   int64_t by = (T + chunk - 1) / chunk;
   while (by > 65535) { chunk *= 2; by = (T + chunk - 1) / chunk; }
   a.t_chunk = (int)chunk;
-  time_aggregate_kernel<R><<<dim3((unsigned)bx, (unsigned)by), threads, 0, st>>>(a);
+  const dim3 grid((unsigned)bx, (unsigned)by);
+  if (vec && a.div) time_aggregate_kernel<R, VEC, true><<<grid, threads, 0, st>>>(a);
+  else if (vec) time_aggregate_kernel<R, VEC, false><<<grid, threads, 0, st>>>(a);
+  else if (a.div) time_aggregate_kernel<R, 1, true><<<grid, threads, 0, st>>>(a);
+  else time_aggregate_kernel<R, 1, false><<<grid, threads, 0, st>>>(a);
   M16_CUDA_CHECK(cudaGetLastError());
   return MOD16_OK;
 }
