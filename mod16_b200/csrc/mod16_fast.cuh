@@ -387,8 +387,11 @@ M16_HD HalfV<V> half_fast(V t, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V
 
 // Physical domain of the fast formulas.  NaN anywhere fails it (fminf / fmaxf drop a NaN
 // operand, hence the self-comparison of the sums).
+// `nan_probe` receives a value that is NaN exactly when one of the ten per-step drivers of
+// the masked-driver rule (every per-step driver except sw_rad_night and Tmin, see
+// nan_halves below) is NaN: a sum of absolute values, so infinities cannot cancel into NaN.
 template <class V>
-M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in) {
+M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in, V& nan_probe) {
   // radiation terms and Tmin: finite and not a fill value (-9999, -32768, 1e20 ...)
   const V r = vmax(vmax(vabs(in.lw_d), vabs(in.lw_n)),
                    vmax(vmax(vabs(in.sw_d), vabs(in.sw_n)), vabs(in.tmin)));
@@ -396,11 +399,20 @@ M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in) {
   const V lo = vmin(vmin(vmin(in.lai, in.fpar), vmin(in.vpd_d, in.vpd_n)), in.alb);
   const V hi = vmax(vmax(vmax(in.lai, in.fpar), vmax(in.vpd_d, in.vpd_n)), in.alb);
   const V tl = vmin(in.t_d, in.t_n), th = vmax(in.t_d, in.t_n);
-  const V s1 = ((in.lw_d + in.lw_n) + (in.sw_d + in.sw_n)) + in.tmin;
-  const V s2 = ((in.lai + in.fpar) + (in.vpd_d + in.vpd_n)) + ((in.alb + in.t_d) + in.t_n);
+  const V sa = (vabs(in.lw_d) + vabs(in.lw_n)) + vabs(in.sw_d);
+  const V sb = vabs(in.sw_n) + vabs(in.tmin);
+  const V s2 = ((vabs(in.lai) + vabs(in.fpar)) + (vabs(in.vpd_d) + vabs(in.vpd_n))) +
+               ((vabs(in.alb) + vabs(in.t_d)) + vabs(in.t_n));
+  nan_probe = sa + s2;
+  const V s1 = nan_probe + sb;
   return mand(mand(mand(vlt(r, splat<V>(9000.0f)), vge(lo, splat<V>(0.0f))),
                    mand(vlt(hi, splat<V>(1.0e5f)), vgt(tl, splat<V>(200.0f)))),
-              mand(vlt(th, splat<V>(340.0f)), mand(veq(s1, s1), veq(s2, s2))));
+              mand(vlt(th, splat<V>(340.0f)), veq(s1, s1)));
+}
+template <class V>
+M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in) {
+  V probe;
+  return in_domain<V>(in, probe);
 }
 
 // Draw-independent part of step_fast()'s guards, for batches that evaluate MANY parameter
@@ -436,9 +448,10 @@ M16_HD bool element_needs_exact(const StepInV<float>& in, float p) {
 template <class V, int SEM, bool HAS_RC>
 M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,
                                           const PixConstV<V>& x, int gate, StepOutV<V>& o,
-                                          typename MaskOf<V>::type& g_pos, V& gs_day) {
+                                          typename MaskOf<V>::type& g_pos, V& gs_day,
+                                          V& nan_probe) {
   typedef typename MaskOf<V>::type M;
-  M need = mnot(mand(x.ok, in_domain<V>(in)));
+  M need = mnot(mand(x.ok, in_domain<V>(in, nan_probe)));
   const V oma = 1.0f - in.alb;
   const V a_d = vfma(in.sw_d, oma, in.lw_d);            // :225
   const V a_n = in.lw_n;                                 // :226
@@ -484,8 +497,15 @@ template <class V, int SEM, bool HAS_RC>
 M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,
                                           const PixConstV<V>& x, int gate, StepOutV<V>& o,
                                           typename MaskOf<V>::type& g_pos) {
-  V gs_day;
-  return step_fast<V, SEM, HAS_RC>(in, c, x, gate, o, g_pos, gs_day);
+  V gs_day, probe;
+  return step_fast<V, SEM, HAS_RC>(in, c, x, gate, o, g_pos, gs_day, probe);
+}
+template <class V, int SEM, bool HAS_RC>
+M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,
+                                          const PixConstV<V>& x, int gate, StepOutV<V>& o,
+                                          typename MaskOf<V>::type& g_pos, V& gs_day) {
+  V probe;
+  return step_fast<V, SEM, HAS_RC>(in, c, x, gate, o, g_pos, gs_day, probe);
 }
 
 // ---- scalar interface used by the strided kernel, the fix-up and the host harness -------
@@ -534,17 +554,72 @@ M16_HD StepInV<float> to_v(const StepIn& in) {
   return v;
 }
 
+// ---- masked (NaN) drivers ------------------------------------------------------------------
+// Real tiles carry masked pixels (water, fill) as NaN drivers at every step; sending each of
+// them through the double-precision code just to obtain NaN costs two orders of magnitude
+// (measured: 1 % masked pixels took the tile from 95 to 6 G units/s).  Reading the op-for-op
+// code (mod16_math.cuh), a NaN in one of these drivers makes the half-day TOTAL NaN whatever
+// the other drivers and (finite) parameters are, through a term no mask can remove:
+//   static   day:   lw_net_day, sw_rad_day, sw_albedo, temp_day, vpd_day -> soil numerator
+//                   (:253, :367); pressure -> gamma, rho; fpar -> soil; lai -> r_h of the
+//                   wet canopy, whose mask `lai * f_wet <= tiny` is False for NaN (:305-320)
+//            night: lw_net_night, temp_night, vpd_night, pressure, fpar, lai
+//   instance day:   the same without lai (NaN lai zeroes canopy and transpiration, :961,
+//                   :1258: finite result); night: lw_net_night, temp_night, vpd_night,
+//                   pressure, fpar
+// (sw_rad_night, tmin and temp_annual are not in the lists: their NaN can be masked away.)
+// nan_halves() returns bit 0 / bit 1 when the day / night total is NaN by this rule (the other
+// drivers then do not matter for that half: NaN + x = NaN).  `g_pos` is the element's gate
+// predicate g_surf > 0 (:343), which a NaN total does not prevent; it is formed from Tmin,
+// VPD_day, T_day and pressure alone: a NaN among them makes g_surf NaN (False), otherwise
+// they must be inside the fast domain for the float ramps to decide like the double code --
+// if not, 0 is returned and the double code evaluates the element.
+template <int SEM>
+M16_HD int nan_halves(const StepIn& in, const PftConstV<float>& c, bool has_rc, bool& g_pos) {
+  g_pos = false;
+  if (has_rc) return 0;
+  const bool n_t_d = in.t_d != in.t_d, n_vpd_d = in.vpd_d != in.vpd_d, n_p = in.p != in.p,
+             n_fpar = in.fpar != in.fpar;
+  const bool n_lai = SEM == SEM_STATIC && in.lai != in.lai;
+  const bool day = in.lw_d != in.lw_d || in.sw_d != in.sw_d || in.alb != in.alb || n_t_d ||
+                   n_vpd_d || n_p || n_fpar || n_lai;
+  const bool night = in.lw_n != in.lw_n || in.t_n != in.t_n || in.vpd_n != in.vpd_n || n_p ||
+                     n_fpar || n_lai;
+  if (!(day || night)) return 0;
+  if (SEM == SEM_STATIC && !(n_t_d || n_p || n_vpd_d || in.tmin != in.tmin)) {
+    if (c.ok == 0.0f) return 0;
+    const bool sane = in.t_d > 200.0f && in.t_d < 340.0f && in.p >= 3.0e4f && in.p <= 1.2e5f &&
+                      in.vpd_d >= 0.0f && in.vpd_d < 1.0e5f && fabsf(in.tmin) < 9000.0f;
+    if (!sane) return 0;
+    // g_surf = csl m_tmin m_vpd / r_corr, r_corr > 0 here (:325-328)
+    const float m_t = vsat((celsius<float>(in.tmin) - c.tmin_close) * c.inv_dtmin);
+    const float m_v = vsat((c.vpd_close - in.vpd_d) * c.inv_dvpd);
+    g_pos = (c.csl * m_t) * m_v > 0.0f;
+  }
+  return (day ? 1 : 0) | (night ? 2 : 0);
+}
+
 // Fast evaluation of one pixel-timestep with the exact re-evaluation done in place.
 // `guarded` (optional) reports whether the element took the double path.
 template <int SEM, typename ColFn>
 M16_HD void pixel_step_fast(const StepIn& in, const PftConst& c, const PixConst& x,
                             ColFn col, bool has_rc, int gate, StepOut& o, bool& g_pos,
-                            bool* guarded = nullptr) {
+                            bool* guarded = nullptr, int out_mode = 2) {
   StepOutV<float> r;
   const StepInV<float> v = to_v(in);
   const bool need = has_rc ? step_fast<float, SEM, true>(v, c, x, gate, r, g_pos)
                            : step_fast<float, SEM, false>(v, c, x, gate, r, g_pos);
   if (guarded) *guarded = need;
+  if (need && out_mode != 2) {  // masked drivers: NaN totals without the double code
+    const int h = nan_halves<SEM>(in, c, has_rc, g_pos);
+    if (out_mode == 0 ? h != 0 : h == 3) {
+      const float qnan = (float)NAN;
+      o.day.canopy = o.day.soil = o.day.trans = qnan;
+      o.night.canopy = o.night.soil = o.night.trans = qnan;
+      o.tot_day = o.tot_night = o.tot = qnan;
+      return;
+    }
+  }
   if (need) {
     double cc[11];
     for (int k = 0; k < 11; ++k) cc[k] = col(k);

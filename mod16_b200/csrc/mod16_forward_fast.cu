@@ -95,6 +95,35 @@ __device__ __noinline__ bool fix_exact_one(const ForwardArgs<float>& a, const Sh
   return g_pos;
 }
 
+// fast::nan_halves() for ONE flagged element, out of line and self-contained like
+// fix_exact_one (the hot loop keeps no inputs alive for it).
+template <int SEM>
+__device__ __noinline__ int nan_halves_one(const ForwardArgs<float>& a, const SharedLut& lut,
+                                           int64_t t, int64_t n, bool& g_pos) {
+  int code = 0;
+  if (a.par_mode == 1) {
+    code = (int)__ldg(a.pft + n);
+    code = code < MOD16_N_PFT ? code : MOD16_N_PFT;
+  }
+  StepIn in;
+  in.lw_d = a.drv[MOD16_D_LW_NET_DAY].at(t, n);
+  in.lw_n = a.drv[MOD16_D_LW_NET_NIGHT].at(t, n);
+  in.sw_d = a.drv[MOD16_D_SW_RAD_DAY].at(t, n);
+  in.sw_n = a.drv[MOD16_D_SW_RAD_NIGHT].at(t, n);
+  in.alb = a.drv[MOD16_D_SW_ALBEDO].at(t, n);
+  in.t_d = a.drv[MOD16_D_TEMP_DAY].at(t, n);
+  in.t_n = a.drv[MOD16_D_TEMP_NIGHT].at(t, n);
+  in.t_ann = 0.0f;
+  in.tmin = a.drv[MOD16_D_TMIN].at(t, n);
+  in.vpd_d = a.drv[MOD16_D_VPD_DAY].at(t, n);
+  in.vpd_n = a.drv[MOD16_D_VPD_NIGHT].at(t, n);
+  in.p = a.drv[MOD16_D_PRESSURE].at(t, n);
+  in.fpar = a.drv[MOD16_D_FPAR].at(t, n);
+  in.lai = a.drv[MOD16_D_LAI].at(t, n);
+  in.rc_d = in.rc_n = 0.0f;
+  return fast::nan_halves<SEM>(in, lut.pc[code], a.has_rc != 0, g_pos);
+}
+
 // ---- forward_pipe_kernel ------------------------------------------------------------------
 // Warp specialisation: warp 15 is the PRODUCER; for every pair of time steps its elected
 // lane waits until a stage is free, arms the stage's `full` mbarrier with the byte count
@@ -280,8 +309,8 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     if (warp_lead) mbar_arrive(empty0 + 8 * stage);  // this warp has read the stage
     fast::StepOutV<F2> r;
     M2 g_pos;
-    F2 gs;
-    M2 need = fast::step_fast<F2, SEM, false>(in, pc, px, gate, r, g_pos, gs);
+    F2 gs, nan_probe;
+    M2 need = fast::step_fast<F2, SEM, false>(in, pc, px, gate, r, g_pos, gs, nan_probe);
     need.x = need.x && live;
     need.y = need.y && live && TWO;
     F2 res[6];
@@ -314,6 +343,30 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       for (int j = 0; j < PIPE_SUB; ++j) {
         if (j == 0 ? need.x : need.y) {
           const int64_t t = t0 + i * PIPE_SUB + j;
+          if (OUT != 2) {  // masked (NaN) drivers: the total is NaN without the double code
+            bool gp;
+            // static `_et` total: NaN as soon as one driver of the masked-driver rule is NaN
+            // (the probe of step_fast, or the pixel's pressure); decided from registers --
+            // a masked pixel is masked at every step, its warp must not stall on re-reads.
+            // The gate predicate is the hot path's own (g_surf > 0 from Tmin, VPD, T, P).
+            if (OUT == 0 && SEM == SEM_STATIC && pc.ok.x != 0.0f) {
+              const float probe = j == 0 ? nan_probe.x : nan_probe.y;
+              if (probe != probe || px.pa.x != px.pa.x) {
+                st_stream1(a.out[0] + off + j * t_stride, __int_as_float(0x7fc00000));
+                any_pos |= j == 0 ? g_pos.x : g_pos.y;
+                continue;
+              }
+            }
+            const int h = nan_halves_one<SEM>(a, lut, t, n, gp);
+
+            if (OUT == 0 ? h != 0 : h == 3) {
+              const float qnan = __int_as_float(0x7fc00000);
+              st_stream1(a.out[0] + off + j * t_stride, qnan);
+              if (OUT == 1) st_stream1(a.out[1] + off + j * t_stride, qnan);
+              any_pos |= gp;
+              continue;
+            }
+          }
           bool queued = false;
           if (a.redo_cap > 0) {  // global queue, evaluated by redo_queue_kernel
             const unsigned long long slot = atomicAdd(a.redo_ws, 1ULL);
@@ -403,7 +456,8 @@ forward_strided_fast_kernel(const __grid_constant__ ForwardArgs<float> a) {
       fast::StepOut r;
       bool g_pos;
       fast::pixel_step_fast<SEM>(
-          in, pc, px, [&](int k) { return col[k]; }, a.has_rc != 0, a.gate, r, g_pos);
+          in, pc, px, [&](int k) { return col[k]; }, a.has_rc != 0, a.gate, r, g_pos, nullptr,
+          OUT);
       any_pos |= g_pos;
       const int64_t o = t * a.N + n;
       if (OUT == 0) {

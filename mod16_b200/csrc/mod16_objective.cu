@@ -114,7 +114,17 @@ obj_classify_kernel(const __grid_constant__ ObjArgs<float> a) {
     load_element<float>(a, e, d, ob, w);
     if (ob == ob && w == w) {
       ElemRec r;
-      c = obj::make_elem_rec(to_step_in(d), (float)ob, (float)w, r) ? 1 : 2;
+      const fast::StepIn in = to_step_in(d);
+      c = obj::make_elem_rec(in, (float)ob, (float)w, r) ? 1 : 2;
+      if (c == 2) {
+        // masked (NaN) drivers: the prediction is NaN for every draw, so the pair is not
+        // valid for any of them -- same as a missing observation
+        fast::PftConstV<float> sane;
+        sane.tmin_close = -8.0f; sane.inv_dtmin = 0.1f; sane.vpd_close = 3000.0f;
+        sane.inv_dvpd = 1e-3f; sane.csl = 0.0f; sane.ok = 1.0f;
+        bool gp;
+        if (fast::nan_halves<SEM_STATIC>(in, sane, false, gp) != 0) c = 0;
+      }
     }
     a.cls[e] = (uint8_t)c;
   }

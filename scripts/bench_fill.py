@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+'''K1 on a tile where a fraction of the PIXELS is masked (NaN fPAR / LAI at every step, as
+ocean / fill pixels of a MODIS tile are after masking): python scripts/bench_fill.py [frac]'''
+import json, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mod16_b200 import MOD16, synthetic, utils
+from mod16_b200.forward import run_forward
+frac = float(sys.argv[1]) if len(sys.argv) > 1 else 0.3
+T, N = 64, 2400 * 2400
+dev = torch.device('cuda', 0)
+d = synthetic.device_drivers(T, N, 1, dev)
+mask = torch.rand(N, device=dev) < frac
+for k in ('fpar', 'lai'):
+    d[k][:, mask] = float('nan')
+table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51), MOD16.required_parameters, default_beta=250.0)
+pft = torch.from_numpy(synthetic.host_pft_map(N, 2)).to(dev)
+drv = [d[k] for k in synthetic.DRIVER_NAMES]
+out = torch.empty((T, N), device=dev)
+flag = torch.zeros(1, device=dev, dtype=torch.int32)
+f = lambda: run_forward(drv, pft=pft, table=table, semantics='static', out_mode='sum', gate='global',
+                        dtype=np.float32, device=dev, gate_flag=flag, out=[out])
+for _ in range(2): f()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(3): f()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 3
+nan_out = float(torch.isnan(out).float().mean())
+print(json.dumps({'masked_pixel_fraction': frac, 'ms': ms, 'G units/s': T * N / ms / 1e6, 'nan_fraction_out': nan_out}))

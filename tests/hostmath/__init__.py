@@ -108,3 +108,23 @@ def objective(draws, drivers, pair=False):
     rs = lambda a: a.reshape((D,) + shape)
     return dict(tot=rs(tot), tr=rs(tr), gs=rs(gs), fast=(cls == 1).reshape(shape),
                 draw_ok=ok.astype(bool))
+
+
+def nan_halves(params, drivers, semantics='static'):
+    '''
+    The masked-driver rule of the fast path: returns (h, g_pos) with h bit 0 / 1 set where the
+    day / night total is NaN by the rule (0: the rule does not decide).
+    '''
+    allv, shape = _flat(list(drivers), np.float32)
+    n = allv.shape[1]
+    drv = np.ascontiguousarray(allv[:14])
+    par = np.ascontiguousarray(np.stack([
+        np.broadcast_to(np.asarray(p, np.float64), shape).ravel() for p in params]))
+    h = np.zeros(n, np.uint8)
+    g = np.zeros(n, np.uint8)
+    fn = lib().hm_nan_halves
+    fn.restype = None
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    fn(ctypes.c_int({'static': 0, 'instance': 1}[semantics]), p(drv), p(par), ctypes.c_int64(n),
+       p(h), p(g))
+    return h.reshape(shape), g.reshape(shape).astype(bool)

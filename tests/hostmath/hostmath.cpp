@@ -136,8 +136,30 @@ static void run_objective(const float* drv, const double* draws, int64_t D, int6
 }
 #endif
 
+#ifdef HM_WITH_FAST
+// the masked-driver rule: per element, bit 0 / 1 = day / night total NaN by the rule (0: not
+// decided), and the gate predicate the rule reports
+static void run_nan_halves(int sem, const float* drv, const double* par, int64_t n, uint8_t* h,
+                           uint8_t* gpos) {
+  for (int64_t i = 0; i < n; ++i) {
+    fast::StepIn in = load_in(drv, nullptr, 0, n, i);
+    double col[11];
+    for (int k = 0; k < 11; ++k) col[k] = par[k * n + i];
+    const fast::PftConst pc = fast::make_pft_const(col, sem);
+    bool g = false;
+    h[i] = (uint8_t)(sem == SEM_STATIC ? fast::nan_halves<SEM_STATIC>(in, pc, false, g)
+                                       : fast::nan_halves<SEM_INSTANCE>(in, pc, false, g));
+    gpos[i] = g ? 1 : 0;
+  }
+}
+#endif
+
 extern "C" {
 #ifdef HM_WITH_FAST
+void hm_nan_halves(int sem, const float* drv, const double* par, int64_t n, uint8_t* h,
+                   uint8_t* gpos) {
+  run_nan_halves(sem, drv, par, n, h, gpos);
+}
 void hm_objective_f32(const float* drv, const double* draws, int64_t D, int64_t n, int pair,
                       float* tot, float* tr, float* gs, uint8_t* cls, uint8_t* draw_ok) {
   run_objective(drv, draws, D, n, pair, tot, tr, gs, cls, draw_ok);

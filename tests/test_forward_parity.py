@@ -154,6 +154,58 @@ def test_medium_grid_against_oracle(cuda_lib, dtype, kind, nan):
     print('medium grid', np.dtype(dtype).name, kind, m)
 
 
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_masked_pixels(cuda_lib, dtype):
+    '''
+    A tile with masked pixels (NaN fPAR / LAI / albedo at every step, NaN pressure on a few,
+    single NaNs elsewhere): the float32 kernels answer NaN totals from the masked-driver rule
+    without the double code; masks and values must still be the reference's, for every
+    entry point and output mode.
+    '''
+    T, N = 23, 4 * 977
+    rng = np.random.default_rng(77)
+    d = synthetic.host_drivers(T, N, 606, dtype=dtype)
+    masked = rng.random(N) < 0.3
+    for k in ('fpar', 'lai', 'sw_albedo'):
+        d[k][:, masked] = np.nan
+    d['pressure'][rng.random(N) < 0.02] = np.nan
+    for k in ('lw_net_night', 'temp_day', 'vpd_night', 'tmin', 'lai'):
+        d[k][rng.random((T, N)) < 0.003] = np.nan
+    d['temp_night'][rng.random((T, N)) < 0.002] = -9999.0
+    drv = [d[k] for k in NAMES]
+    d64 = as_f64(drv)
+    pft = synthetic.host_pft_map(N, 8)
+    table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51),
+                              MOD16.required_parameters, default_beta=250.0)
+    vec = [table[i][pft].reshape(1, N) for i in range(11)]
+    with np.errstate(all='ignore'):
+        rd, rn = orc.static_evapotranspiration(vec, *d64)
+    got = MOD16._et_by_pft(table, pft, *drv, dtype=dtype)
+    m = parity.assert_parity(got, rd + rn, dtype, what='masked _et')
+    assert 0.3 < np.isnan(got).mean() < 0.4
+    gd, gn = MOD16._evapotranspiration(vec, *drv, dtype=dtype)
+    parity.assert_parity(gd, rd, dtype, what='masked day')
+    parity.assert_parity(gn, rn, dtype, what='masked night')
+    col = list(table[:, 7])
+    model = MOD16(dict(zip(MOD16.required_parameters, col)))
+    with np.errstate(all='ignore'):
+        ref = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, col))).evapotranspiration(*d64)
+        sep = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, col))).evapotranspiration(
+            *d64, separate=True)
+    day, night = model.evapotranspiration(*drv, dtype=dtype)
+    parity.assert_parity(day, ref[0], dtype, parity.MASS_SCALE, what='masked inst day')
+    parity.assert_parity(night, ref[1], dtype, parity.MASS_SCALE, what='masked inst night')
+    cd, cn = model.evapotranspiration(*drv, separate=True, dtype=dtype)
+    for c in range(3):
+        parity.assert_parity(cd[c], sep[0][c], dtype, parity.MASS_SCALE, what='masked comp d')
+        parity.assert_parity(cn[c], sep[1][c], dtype, parity.MASS_SCALE, what='masked comp n')
+    # ragged N / strided kernel
+    sl = [v[:, :1001] if isinstance(v, np.ndarray) and v.ndim == 2 else
+          (v[:1001] if isinstance(v, np.ndarray) else v) for v in drv]
+    got = MOD16._et([v[:, :1001] for v in vec], *sl, dtype=dtype)
+    parity.assert_parity(got, (rd + rn)[:, :1001], dtype, what='masked strided')
+
+
 def test_input_kinds_and_broadcasting(cuda_lib):
     'python scalars, (N,), (1, N), (T, 1), (T, N), int16 zeros, torch CUDA tensors.'
     T, N = 5, 64

@@ -201,3 +201,50 @@ def test_fast_f32_guard_rate_is_small():
         rate = r['guarded'].mean()
         print('guard rate', kind, rate)
         assert rate < limit, (kind, rate)
+
+
+@pytest.mark.parametrize('semantics', ['static', 'instance'])
+def test_masked_driver_rule_is_sound(semantics):
+    '''
+    Where the rule says a half-day total is NaN, the float64 oracle's is NaN; it decides for
+    (almost) every element whose only defect is a NaN in fPAR / LAI / albedo ..., i.e. masked
+    pixels never reach the double-precision code; its gate predicate is the oracle's.
+    '''
+    T, N = 30, 2000
+    rng = np.random.default_rng(8)
+    d = synthetic.host_drivers(T, N, 55, dtype=np.float32)
+    truth = dict((k, v.copy()) for k, v in d.items() if isinstance(v, np.ndarray))
+    names2d = [k for k in NAMES if isinstance(d[k], np.ndarray) and d[k].ndim == 2]
+    for k in names2d:                       # single NaNs in every per-step driver
+        d[k][rng.random((T, N)) < 0.004] = np.nan
+    d['pressure'][rng.random(N) < 0.01] = np.nan
+    masked = rng.random(N) < 0.2            # whole masked pixels, as on a real tile
+    for k in ('fpar', 'lai', 'sw_albedo'):
+        d[k][:, masked] = np.nan
+    d['temp_day'][rng.random((T, N)) < 0.002] = -9999.0   # fills must NOT be decided here
+    drv = [d[k] for k in NAMES]
+    d64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
+    table = _table()
+    col = list(table[:, 7])
+    h, g = hostmath.nan_halves(col, drv, semantics)
+    with np.errstate(all='ignore'):
+        if semantics == 'static':
+            day, night = orc.static_evapotranspiration(col, *d64, gate='open')
+        else:
+            day, night = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, col))).evapotranspiration(*d64)
+    assert np.isnan(day[(h & 1) > 0]).all() and np.isnan(night[(h & 2) > 0]).all()
+    # a fill value in a driver the gate predicate reads is left to the double code
+    if semantics == 'static':
+        assert not (h[(d['temp_day'] == -9999.0) & ~np.isnan(d['vpd_day']) &
+                      ~np.isnan(np.broadcast_to(d['pressure'], (T, N)))] > 0).any()
+    only_masked = np.broadcast_to(masked, (T, N)).copy()
+    for k in names2d:
+        if k not in ('fpar', 'lai', 'sw_albedo'):
+            only_masked &= ~np.isnan(d[k])
+    only_masked &= ~np.isnan(np.broadcast_to(d['pressure'], (T, N))) & (d['temp_day'] != -9999.0)
+    assert (h[only_masked] == 3).all()
+    if semantics == 'static':
+        with np.errstate(all='ignore'):
+            g_surf = (col[7] * orc.ramp_up(d64[8] - 273.15, col[0], col[1]) *
+                      orc.ramp_down(d64[9], col[2], col[3])) / orc.r_correction(d64[11], d64[5])
+        assert np.array_equal(g[h > 0], (g_surf > 0)[h > 0])
