@@ -344,27 +344,24 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
         if (j == 0 ? need.x : need.y) {
           const int64_t t = t0 + i * PIPE_SUB + j;
           if (OUT != 2) {  // masked (NaN) drivers: the total is NaN without the double code
-            bool gp;
-            // static `_et` total: NaN as soon as one driver of the masked-driver rule is NaN
-            // (the probe of step_fast, or the pixel's pressure); decided from registers --
-            // a masked pixel is masked at every step, its warp must not stall on re-reads.
-            // The gate predicate is the hot path's own (g_surf > 0 from Tmin, VPD, T, P).
-            if (OUT == 0 && SEM == SEM_STATIC && pc.ok.x != 0.0f) {
-              const float probe = j == 0 ? nan_probe.x : nan_probe.y;
-              if (probe != probe || px.pa.x != px.pa.x) {
-                st_stream1(a.out[0] + off + j * t_stride, __int_as_float(0x7fc00000));
-                any_pos |= j == 0 ? g_pos.x : g_pos.y;
+            // The probe of step_fast (or the pixel's pressure) is NaN exactly when a driver of
+            // the masked-driver rule is.  Static `_et` total: NaN follows at once, decided
+            // from registers -- a masked pixel is masked at every step, its warp must not
+            // stall on re-reads -- with the hot path's own gate predicate (g_surf > 0 from
+            // Tmin, VPD, T, P).  Other modes: the out-of-line rule says which halves.
+            const float probe = j == 0 ? nan_probe.x : nan_probe.y;
+            if (probe != probe || px.pa.x != px.pa.x) {
+              bool gp = j == 0 ? g_pos.x : g_pos.y;
+              int h = 3;
+              if (!(OUT == 0 && SEM == SEM_STATIC && pc.ok.x != 0.0f))
+                h = nan_halves_one<SEM>(a, lut, t, n, gp);
+              if (OUT == 0 ? h != 0 : h == 3) {
+                const float qnan = __int_as_float(0x7fc00000);
+                st_stream1(a.out[0] + off + j * t_stride, qnan);
+                if (OUT == 1) st_stream1(a.out[1] + off + j * t_stride, qnan);
+                any_pos |= gp;
                 continue;
               }
-            }
-            const int h = nan_halves_one<SEM>(a, lut, t, n, gp);
-
-            if (OUT == 0 ? h != 0 : h == 3) {
-              const float qnan = __int_as_float(0x7fc00000);
-              st_stream1(a.out[0] + off + j * t_stride, qnan);
-              if (OUT == 1) st_stream1(a.out[1] + off + j * t_stride, qnan);
-              any_pos |= gp;
-              continue;
             }
           }
           bool queued = false;
@@ -542,7 +539,7 @@ static int launch_pipe_swn(const ForwardArgs<float>& a, const PipeSrc& src, dim3
   forward_pipe_kernel<SEM, OUT, SWN><<<grid, PIPE_THREADS, smem, st>>>(a, src);
   M16_CUDA_CHECK(cudaGetLastError());
   if (a.redo_cap > 0) {
-    redo_queue_kernel<SEM, OUT><<<148 * 2, 128, 0, st>>>(a);
+    redo_queue_kernel<SEM, OUT><<<148 * 4, 128, 0, st>>>(a);  // 126 registers: 4 blocks per SM
     M16_CUDA_CHECK(cudaGetLastError());
   }
   return MOD16_OK;

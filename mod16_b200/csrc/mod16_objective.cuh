@@ -15,8 +15,8 @@
 // (f_wet == 0: no wet canopy) is a warp-uniform branch.
 //
 // Static semantics only (`_et`): that is what both callers pass.  Elements for which the
-// rearranged float algebra is not trusted for EVERY draw (fast::element_needs_exact, plus
-// lai == 0 and rh == 1) are not given a record; the kernels evaluate them with the
+// rearranged float algebra is not trusted for EVERY draw (fast::element_needs_exact) are not
+// given a record; the kernels evaluate them with the
 // op-for-op double code for every draw.
 // Citations are file:line under /root/reference/mod16/__init__.py.
 #pragma once
@@ -90,10 +90,8 @@ M16_HD bool make_elem_rec(const fast::StepIn& in, float obs, float w, ElemRec& r
   using namespace fast;
   const StepInV<float> v = to_v(in);
   if (element_needs_exact(v, in.p)) return false;
-  if (!(in.lai > 0.0f)) return false;  // g_canopy switches to 1e-7 (:336-337)
   const HalfCoef d = half_coef(in.t_d, in.vpd_d, in.p);
   const HalfCoef n = half_coef(in.t_n, in.vpd_n, in.p);
-  if (!(d.omfw > 0.0f) || !(n.omfw > 0.0f)) return false;  // rh == 1: same switch
   const float oma = 1.0f - in.alb;
   const float a_d = fmaf(in.sw_d, oma, in.lw_d);   // :225
   const float a_n = in.lw_n;                        // :226
@@ -214,7 +212,11 @@ M16_HD V objective_step(const ElemRec& e, const DrawConstV<V>& c, V& tr, V& gs) 
   {
     const V sc = (c.g_cut + gs) * e.d_inv_rc;                                // :328-329
     const V gbl = c.gl_sh * e.d_lo;                                          // :333
-    const V prod = gbl * sc, sum = gbl + sc;                                 // :334-335
+    // lai == 0 or f_wet == 1: g_canopy is the constant 1e-7 (:336-337); a property of the
+    // element, hence a uniform select
+    const bool lo_pos = e.d_lo > 0.0f;
+    const V prod = lo_pos ? gbl * sc : splat<V>(1.0e-7f);                    // :334-335
+    const V sum = lo_pos ? gbl + sc : splat<V>(1.0f);
     const V num = vfma(c.gl_sh, e.d_KfX, e.d_KfBSA);                         // :344-345
     const V gyd = vfma(c.gl_sh, e.d_GX, e.d_GB);
     const V den = vfma(e.d_SGX, prod, gyd * sum);                            // :346

@@ -7,12 +7,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mod16_b200 import MOD16, synthetic, utils
 from mod16_b200.forward import run_forward
 frac = float(sys.argv[1]) if len(sys.argv) > 1 else 0.3
+mode = sys.argv[2] if len(sys.argv) > 2 else 'masked'   # masked | negvpd | fill
 T, N = 64, 2400 * 2400
 dev = torch.device('cuda', 0)
 d = synthetic.device_drivers(T, N, 1, dev)
-mask = torch.rand(N, device=dev) < frac
-for k in ('fpar', 'lai'):
-    d[k][:, mask] = float('nan')
+if mode == 'masked':       # whole pixels masked (NaN fPAR / LAI at every step)
+    mask = torch.rand(N, device=dev) < frac
+    for k in ('fpar', 'lai'):
+        d[k][:, mask] = float('nan')
+elif mode == 'negvpd':     # scattered supersaturated elements (negative VPD): double code
+    d['vpd_day'][torch.rand((T, N), device=dev) < frac] = -50.0
+else:                      # unmasked fill values on whole pixels: double code, garbage out
+    mask = torch.rand(N, device=dev) < frac
+    d['fpar'][:, mask] = 2.55
+    d['lai'][:, mask] = -9999.0
 table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51), MOD16.required_parameters, default_beta=250.0)
 pft = torch.from_numpy(synthetic.host_pft_map(N, 2)).to(dev)
 drv = [d[k] for k in synthetic.DRIVER_NAMES]
@@ -28,4 +36,4 @@ for _ in range(3): f()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 nan_out = float(torch.isnan(out).float().mean())
-print(json.dumps({'masked_pixel_fraction': frac, 'ms': ms, 'G units/s': T * N / ms / 1e6, 'nan_fraction_out': nan_out}))
+print(json.dumps({'mode': mode, 'fraction': frac, 'ms': ms, 'G units/s': T * N / ms / 1e6, 'nan_fraction_out': nan_out}))

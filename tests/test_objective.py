@@ -92,11 +92,34 @@ def test_factorised_math_matches_oracle_per_draw(kind, fixed, pair):
                              what='K2 gate-closed pred draw %d' % i)
 
 
+def test_bare_and_saturated_elements_stay_on_the_fast_path():
+    'lai == 0 and rh == 1 switch g_canopy to the constant 1e-7 (:336-337): handled, not exact.'
+    T, N = 6, 400
+    d = synthetic.host_drivers(T, N, 6, dtype=np.float32)
+    d['lai'][0] = 0.0
+    d['lai'][1, ::3] = 0.0
+    d['fpar'][0] = 0.0
+    d['vpd_day'][2] = 0.0       # rh == 1 by day
+    d['vpd_night'][3] = 0.0
+    drv = [d[k] for k in NAMES]
+    d64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
+    draws = synthetic.host_param_draws(5, 3, bplut_column=_column(), fixed=())
+    for pair in (False, True):
+        r = hostmath.objective(draws, drv, pair=pair)
+        assert r['fast'][:4].mean() > 0.99
+        for i, x in enumerate(draws):
+            with np.errstate(all='ignore'):
+                ref = orc.static_et(list(x), *d64, gate='open')
+                closed = orc.static_et(list(x), *d64, gate='closed')
+            m = r['fast']
+            parity.assert_parity(r['tot'][i][m], ref[m], np.float32, what='bare/saturated %d' % i)
+            parity.assert_parity((r['tot'][i] - r['tr'][i])[m], closed[m], np.float32,
+                                 what='bare/saturated closed %d' % i)
+
+
 def test_elements_outside_the_fast_domain_get_no_record():
     T, N = 6, 400
     d = synthetic.host_drivers(T, N, 5, dtype=np.float32, nan_frac=0.01, fill_frac=0.01)
-    d['lai'][0, :7] = 0.0       # g_canopy switches to 1e-7 (:336-337)
-    d['vpd_day'][1, :5] = 0.0   # rh == 1
     drv = [d[k] for k in NAMES]
     r = hostmath.objective(_column()[None], drv)
     bad = np.zeros((T, N), bool)
@@ -105,7 +128,6 @@ def test_elements_outside_the_fast_domain_get_no_record():
         if isinstance(d[k], np.ndarray) and k != 'temp_annual':
             bad |= np.broadcast_to(np.isnan(d[k]) | (d[k] == -9999), (T, N))
     assert not r['fast'][bad].any()
-    assert not r['fast'][0, :7].any() and not r['fast'][1, :5].any()
     assert r['fast'].mean() > 0.7
 
 
