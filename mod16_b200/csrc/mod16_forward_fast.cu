@@ -401,8 +401,80 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   }
 }
 
+// The BPLUT column of pixel n in double, for any parameter source.
+__device__ __forceinline__ void load_column(const ForwardArgs<float>& a, int64_t n,
+                                            double col[MOD16_N_PARAMS]) {
+  if (a.par_mode == 2) {
+#pragma unroll
+    for (int k = 0; k < MOD16_N_PARAMS; ++k)
+      col[k] = (double)__ldg(a.par_arr[k] + n * a.par_stride[k]);
+  } else {
+    int code = 0;
+    if (a.par_mode == 1) code = (int)__ldg(a.pft + n);
+    // numpy fancy indexing would raise on a code > 12; the kernels yield NaN parameters
+#pragma unroll
+    for (int k = 0; k < MOD16_N_PARAMS; ++k)
+      col[k] = code < MOD16_N_PFT ? a.table[k][code] : __longlong_as_double(0x7ff8000000000000LL);
+  }
+}
+
+__device__ __forceinline__ StepIn load_step(const ForwardArgs<float>& a, int64_t t, int64_t n) {
+  StepIn in;
+  in.lw_d = a.drv[MOD16_D_LW_NET_DAY].at(t, n);
+  in.lw_n = a.drv[MOD16_D_LW_NET_NIGHT].at(t, n);
+  in.sw_d = a.drv[MOD16_D_SW_RAD_DAY].at(t, n);
+  in.sw_n = a.drv[MOD16_D_SW_RAD_NIGHT].at(t, n);
+  in.alb = a.drv[MOD16_D_SW_ALBEDO].at(t, n);
+  in.t_d = a.drv[MOD16_D_TEMP_DAY].at(t, n);
+  in.t_n = a.drv[MOD16_D_TEMP_NIGHT].at(t, n);
+  in.t_ann = a.drv[MOD16_D_TEMP_ANNUAL].at(t, n);
+  in.tmin = a.drv[MOD16_D_TMIN].at(t, n);
+  in.vpd_d = a.drv[MOD16_D_VPD_DAY].at(t, n);
+  in.vpd_n = a.drv[MOD16_D_VPD_NIGHT].at(t, n);
+  in.p = a.drv[MOD16_D_PRESSURE].at(t, n);
+  in.fpar = a.drv[MOD16_D_FPAR].at(t, n);
+  in.lai = a.drv[MOD16_D_LAI].at(t, n);
+  in.rc_d = a.has_rc ? a.rc[0].at(t, n) : 0.0f;
+  in.rc_n = a.has_rc ? a.rc[1].at(t, n) : 0.0f;
+  return in;
+}
+
+// The rare element of the strided kernel that step_fast() flagged: masked-driver rule first,
+// else the op-for-op double code.  Out of line and self-contained (re-reads its inputs), so
+// that the double code costs the loop no registers.  Writes the outputs; returns g_surf > 0.
 template <int SEM, int OUT>
-__global__ void __launch_bounds__(256)
+__device__ __noinline__ bool strided_rare_one(const ForwardArgs<float>& a, int64_t t, int64_t n) {
+  double col[MOD16_N_PARAMS];
+  load_column(a, n, col);
+  const StepIn in = load_step(a, t, n);
+  const int64_t o = t * a.N + n;
+  bool g_pos = false;
+  if (OUT != 2) {
+    const PftConst pc = fast::make_pft_const(col, SEM);
+    const int h = fast::nan_halves<SEM>(in, pc, a.has_rc != 0, g_pos);
+    if (OUT == 0 ? h != 0 : h == 3) {
+      const float qnan = __int_as_float(0x7fc00000);
+      a.out[0][o] = qnan;
+      if (OUT == 1) a.out[1][o] = qnan;
+      return g_pos;
+    }
+  }
+  fast::StepOut r;
+  fast::pixel_step_exact<SEM>(in, col, a.has_rc != 0, a.gate, r, g_pos);
+  if (OUT == 0) {
+    a.out[0][o] = r.tot;
+  } else if (OUT == 1) {
+    a.out[0][o] = r.tot_day;
+    a.out[1][o] = r.tot_night;
+  } else {
+    a.out[0][o] = r.day.canopy;   a.out[1][o] = r.day.soil;   a.out[2][o] = r.day.trans;
+    a.out[3][o] = r.night.canopy; a.out[4][o] = r.night.soil; a.out[5][o] = r.night.trans;
+  }
+  return g_pos;
+}
+
+template <int SEM, int OUT>
+__global__ void __launch_bounds__(256, 4)
 forward_strided_fast_kernel(const __grid_constant__ ForwardArgs<float> a) {
   if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -411,60 +483,39 @@ forward_strided_fast_kernel(const __grid_constant__ ForwardArgs<float> a) {
   if (t1 > a.T) t1 = a.T;
   bool any_pos = false;
   if (n < a.N) {
-    double col[MOD16_N_PARAMS];
-    if (a.par_mode == 2) {
-#pragma unroll
-      for (int k = 0; k < MOD16_N_PARAMS; ++k)
-        col[k] = (double)__ldg(a.par_arr[k] + n * a.par_stride[k]);
-    } else {
-      int code = 0;
-      if (a.par_mode == 1) {
-        code = (int)__ldg(a.pft + n);
-      }
-#pragma unroll
-      for (int k = 0; k < MOD16_N_PARAMS; ++k)
-        col[k] = code < MOD16_N_PFT ? a.table[k][code]
-                                    : __longlong_as_double(0x7ff8000000000000LL);
+    PftConst pc;
+    {
+      double col[MOD16_N_PARAMS];
+      load_column(a, n, col);
+      pc = fast::make_pft_const(col, SEM);
     }
-    const PftConst pc = fast::make_pft_const(col, SEM);
     const bool pix_static = a.drv[MOD16_D_PRESSURE].ts == 0 &&
                             a.drv[MOD16_D_TEMP_ANNUAL].ts == 0;
     PixConst px = fast::make_pix_const(a.drv[MOD16_D_PRESSURE].at(t0, n),
                                        a.drv[MOD16_D_TEMP_ANNUAL].at(t0, n), pc, SEM);
+    const bool has_rc = a.has_rc != 0;
     for (int64_t t = t0; t < t1; ++t) {
-      StepIn in;
-      in.lw_d = a.drv[MOD16_D_LW_NET_DAY].at(t, n);
-      in.lw_n = a.drv[MOD16_D_LW_NET_NIGHT].at(t, n);
-      in.sw_d = a.drv[MOD16_D_SW_RAD_DAY].at(t, n);
-      in.sw_n = a.drv[MOD16_D_SW_RAD_NIGHT].at(t, n);
-      in.alb = a.drv[MOD16_D_SW_ALBEDO].at(t, n);
-      in.t_d = a.drv[MOD16_D_TEMP_DAY].at(t, n);
-      in.t_n = a.drv[MOD16_D_TEMP_NIGHT].at(t, n);
-      in.t_ann = a.drv[MOD16_D_TEMP_ANNUAL].at(t, n);
-      in.tmin = a.drv[MOD16_D_TMIN].at(t, n);
-      in.vpd_d = a.drv[MOD16_D_VPD_DAY].at(t, n);
-      in.vpd_n = a.drv[MOD16_D_VPD_NIGHT].at(t, n);
-      in.p = a.drv[MOD16_D_PRESSURE].at(t, n);
-      in.fpar = a.drv[MOD16_D_FPAR].at(t, n);
-      in.lai = a.drv[MOD16_D_LAI].at(t, n);
-      in.rc_d = a.has_rc ? a.rc[0].at(t, n) : 0.0f;
-      in.rc_n = a.has_rc ? a.rc[1].at(t, n) : 0.0f;
+      const StepIn in = load_step(a, t, n);
       if (!pix_static) px = fast::make_pix_const(in.p, in.t_ann, pc, SEM);
-      fast::StepOut r;
+      fast::StepOutV<float> r;
       bool g_pos;
-      fast::pixel_step_fast<SEM>(
-          in, pc, px, [&](int k) { return col[k]; }, a.has_rc != 0, a.gate, r, g_pos, nullptr,
-          OUT);
-      any_pos |= g_pos;
-      const int64_t o = t * a.N + n;
-      if (OUT == 0) {
-        a.out[0][o] = r.tot;
-      } else if (OUT == 1) {
-        a.out[0][o] = r.tot_day;
-        a.out[1][o] = r.tot_night;
+      const fast::StepInV<float> v = fast::to_v(in);
+      const bool need = has_rc ? fast::step_fast<float, SEM, true>(v, pc, px, a.gate, r, g_pos)
+                               : fast::step_fast<float, SEM, false>(v, pc, px, a.gate, r, g_pos);
+      if (need) {
+        any_pos |= strided_rare_one<SEM, OUT>(a, t, n);
       } else {
-        a.out[0][o] = r.day.canopy;   a.out[1][o] = r.day.soil;   a.out[2][o] = r.day.trans;
-        a.out[3][o] = r.night.canopy; a.out[4][o] = r.night.soil; a.out[5][o] = r.night.trans;
+        any_pos |= g_pos;
+        const int64_t o = t * a.N + n;
+        if (OUT == 0) {
+          a.out[0][o] = r.tot;
+        } else if (OUT == 1) {
+          a.out[0][o] = r.tot_day;
+          a.out[1][o] = r.tot_night;
+        } else {
+          a.out[0][o] = r.day.canopy;   a.out[1][o] = r.day.soil;   a.out[2][o] = r.day.trans;
+          a.out[3][o] = r.night.canopy; a.out[4][o] = r.night.soil; a.out[5][o] = r.night.trans;
+        }
       }
     }
   }
