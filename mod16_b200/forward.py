@@ -13,7 +13,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _abi
+from . import _abi, hostcopy
 
 _TORCH_DT = {np.dtype('float32'): torch.float32, np.dtype('float64'): torch.float64}
 
@@ -209,6 +209,15 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     with torch.cuda.device(dev):
         st = _Staged(dev, np_dtype)
         st.full_shape = full_shape
+        s = stream if stream is not None else torch.cuda.current_stream(dev)
+        # large pageable numpy drivers: chunked, threaded staging through pinned buffers
+        big = [k for k, v in enumerate(drivers)
+               if hostcopy.worthwhile(v) and v.dtype == np_dtype] \
+            if hasattr(s, 'wait_event') else []
+        if big:
+            for k, t in zip(big, hostcopy.upload([drivers[k] for k in big], dev, s)):
+                drivers[k] = t
+                st.keep.append(t)
         cd = _abi.Drivers()
         for k, v in enumerate(drivers):
             st.fill(cd.drv[k], v, T, N, len(full_shape))
@@ -271,7 +280,6 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
         if gate_flag is None:
             gate_flag = torch.zeros(1, device=dev, dtype=torch.int32)
         co.gate_flag = gate_flag.data_ptr()
-        s = stream if stream is not None else torch.cuda.current_stream(dev)
         handle = s.cuda_stream if hasattr(s, 'cuda_stream') else int(s)
         if np_dtype == np.dtype('float32'):
             ws = workspace if workspace is not None else _workspace(dev, handle, lib, T * N)
@@ -288,7 +296,9 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
                 for t in st.keep + outs:
                     t.record_stream(s)
             return outs
-        res = [o.cpu().numpy() for o in outs]  # synchronises
+        res = [hostcopy.download(o, s) if (o.numel() * o.element_size() >=
+                                           hostcopy.THRESHOLD_BYTES and hasattr(s, 'wait_event'))
+               else o.cpu().numpy() for o in outs]  # synchronises
         if full_shape == ():
             res = [r[()] for r in res]
         return res

@@ -285,3 +285,25 @@ def test_errors_are_loud(cuda_lib):
         MOD16._et(BPLUT7, *([np.zeros((2, 3))] + [np.zeros((2, 4))] * 13))
     with pytest.raises(_abi.Mod16Error):
         _abi.load('/nonexistent/libmod16_b200.so')
+
+
+def test_large_host_arrays_take_the_threaded_staging_path(cuda_lib):
+    'Plain numpy inputs above the staging threshold: same bits as the device-resident call.'
+    from mod16_b200 import hostcopy
+    T, N = 5, 4 * 1024 * 1024 + 4          # 80 MB per driver, ragged chunk at the end
+    dev = torch.device('cuda', 0)
+    d = synthetic.device_drivers(T, N, 31, dev)
+    d['lai'][2, 1000:2000] = float('nan')
+    drv_dev = [d[k] for k in NAMES]
+    host = [v.cpu().numpy() if isinstance(v, torch.Tensor) else v for v in drv_dev]
+    assert hostcopy.worthwhile(host[0])
+    p7 = [-8., 8.8, 650., 4400., .02, .02, 1e-5, .0055, 60., 95., 250.]
+    ref = MOD16._et(p7, *drv_dev, dtype=np.float32).cpu().numpy()
+    got = MOD16._et(p7, *host, dtype=np.float32)
+    assert isinstance(got, np.ndarray) and got.shape == (T, N)
+    assert np.array_equal(got.view(np.int32), ref.view(np.int32))
+    # round trip of the staging helpers alone, float64, non-multiple of the chunk size
+    a = np.random.default_rng(0).normal(size=(3, 3_000_001))
+    s = torch.cuda.current_stream(dev)
+    t = hostcopy.upload([a], dev, s)[0]
+    assert np.array_equal(hostcopy.download(t, s), a)
