@@ -211,11 +211,14 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
         st.full_shape = full_shape
         s = stream if stream is not None else torch.cuda.current_stream(dev)
         # large pageable numpy drivers: chunked, threaded staging through pinned buffers
-        big = [k for k, v in enumerate(drivers)
-               if hostcopy.worthwhile(v) and v.dtype == np_dtype] \
+        # (a float64 array headed for the float32 path is converted on the device)
+        big = [k for k, v in enumerate(drivers) if hostcopy.worthwhile(v)] \
             if hasattr(s, 'wait_event') else []
         if big:
             for k, t in zip(big, hostcopy.upload([drivers[k] for k in big], dev, s)):
+                if t.dtype != st.t_dtype:
+                    with torch.cuda.stream(s):
+                        t = t.to(st.t_dtype)
                 drivers[k] = t
                 st.keep.append(t)
         cd = _abi.Drivers()

@@ -302,6 +302,11 @@ def test_large_host_arrays_take_the_threaded_staging_path(cuda_lib):
     got = MOD16._et(p7, *host, dtype=np.float32)
     assert isinstance(got, np.ndarray) and got.shape == (T, N)
     assert np.array_equal(got.view(np.int32), ref.view(np.int32))
+    # float64 arrays headed for the float32 path are converted on the device
+    host64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in host]
+    got64 = MOD16._et(p7, *host64, dtype=np.float32)
+    assert got64.dtype == np.float32
+    assert np.array_equal(got64.view(np.int32), ref.view(np.int32))
     # round trip of the staging helpers alone, float64, non-multiple of the chunk size
     a = np.random.default_rng(0).normal(size=(3, 3_000_001))
     s = torch.cuda.current_stream(dev)
