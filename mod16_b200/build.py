@@ -23,7 +23,7 @@ NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
     '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xptxas', '-v',
-    '--fmad=true', '-shared',
+    '--fmad=true', '-shared', '--threads', '0',
 ]
 
 
