@@ -225,7 +225,7 @@ obj_pack_kernel(const __grid_constant__ ObjArgs<float> a) {
 
 // ---- 4: the hot loop ----------------------------------------------------------------------
 #ifndef M16_OBJ_BLOCKS
-#define M16_OBJ_BLOCKS 3
+#define M16_OBJ_BLOCKS 4
 #endif
 #ifndef M16_OBJ_UNROLL
 #define M16_OBJ_UNROLL 1
