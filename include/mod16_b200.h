@@ -159,9 +159,12 @@ int mod16_forward_f64(const mod16_drivers_t* drivers, const mod16_params_t* para
  * NSE = 1 - sse / sum((obs - mean(obs))^2) with unit weights.
  *
  * The static path's batch-global transpiration gate `if np.any(g_surf > 0)` (:343) is
- * evaluated PER DRAW over all its elements, as one reference call per draw would
- * (MOD16_GATE_GLOBAL); MOD16_GATE_OPEN / MOD16_GATE_CLOSED fix it.  r_corr_list is not
- * supported.  All reductions are deterministic (no floating-point atomics).
+ * evaluated PER DRAW over the elements that enter its sums, as one reference call per draw
+ * on the NaN-filtered drivers would (mod16/calibration.py:887-891 removes the rows without an
+ * observation before the model sees them) (MOD16_GATE_GLOBAL); MOD16_GATE_OPEN /
+ * MOD16_GATE_CLOSED fix it.  Elements whose drivers make the prediction NaN for every draw
+ * (masked pixels) count like missing observations.  r_corr_list is not supported.  All
+ * reductions are deterministic (no floating-point atomics).
  */
 typedef struct mod16_objective {
   const double* draws;     /* device (D, 11) row-major, order of required_parameters */
