@@ -29,7 +29,16 @@ def _is_scalar(x):
 
 
 def _shape(x):
-    return () if _is_scalar(x) else tuple(x.shape)
+    if _is_scalar(x):
+        return ()
+    return tuple(x.shape) if hasattr(x, 'shape') else tuple(np.shape(x))
+
+
+def _arrayish(x):
+    'python sequences (lists, tuples) and array-likes without .shape become numpy arrays.'
+    if _is_scalar(x) or isinstance(x, (np.ndarray, torch.Tensor)):
+        return x
+    return np.asarray(x)
 
 
 def result_dtype(values, dtype=None):
@@ -185,11 +194,11 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     a CUDA tensor or ``as_torch`` is set).
     '''
     lib = _abi.load()
-    drivers = list(drivers)
+    drivers = [_arrayish(v) for v in drivers]
     if len(drivers) != _abi.N_DRIVERS:
         raise TypeError('expected 14 drivers, got %d' % len(drivers))
-    extra = list(r_corr_list) if r_corr_list is not None else []
-    plist = list(params) if params is not None else []
+    extra = [_arrayish(v) for v in r_corr_list] if r_corr_list is not None else []
+    plist = [_arrayish(v) for v in params] if params is not None else []
     if params is not None and len(plist) != _abi.N_PARAMS:
         raise TypeError('expected 11 parameters, got %d' % len(plist))
     everything = drivers + extra + plist

@@ -251,6 +251,19 @@ def test_input_kinds_and_broadcasting(cuda_lib):
     parity.assert_parity(MOD16._et(BPLUT7, *tr), ref2, np.float64, what='fortran order')
 
 
+def test_python_sequences_as_inputs(cuda_lib):
+    'Lists and tuples broadcast like the arrays numpy would make of them.'
+    p7 = [-8., 8.8, 650., 4400., .02, .02, 1e-5, .0055, 60., 95., 250.]
+    drv = [-50, -30, [150, 160, 170], 0, 0.3, (293, 294, 295), 285, 285, 285, 1000, 500, 1e5,
+           0.5, [1.5, 1.0, 0.5]]
+    arr = [np.asarray(v, np.float64) if isinstance(v, (list, tuple)) else v for v in drv]
+    with np.errstate(all='ignore'):
+        ref = orc.static_et(p7, *arr)
+    got = MOD16._et(p7, *drv)
+    assert got.shape == (3,)
+    parity.assert_parity(got, ref, np.float64, what='list inputs')
+
+
 def test_empty_and_ragged(cuda_lib):
     d = synthetic.host_drivers(3, 0, 1)
     got = MOD16._et(BPLUT7, *[d[k] for k in NAMES])
