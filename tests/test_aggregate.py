@@ -69,3 +69,22 @@ def test_aggregate_of_forward_output_is_the_annual_et(cuda_lib):
     ref = orc.annual_mass_sums(ref_et, np.zeros(T, np.int32),
                                orc.lhv(d['temp_day'].astype(np.float64)))
     np.testing.assert_allclose(got, ref, rtol=2e-5)
+
+
+def test_aggregate_outputs_stay_inside_their_buffers(cuda_lib):
+    import ctypes
+    from mod16_b200 import _abi
+    lib = _abi.load()
+    for T, N in ((9, 1000), (9, 1001), (3, 4)):
+        x = torch.rand((T, N), device='cuda')
+        pad = 256
+        big = torch.full((2 * N + 2 * pad,), -5.0, device='cuda', dtype=torch.float64)
+        grp = torch.tensor([0, 1] * T, dtype=torch.int32, device='cuda')[:T]
+        ag = _abi.Aggregate()
+        ag.x, ag.scale, ag.group, ag.n_groups = x.data_ptr(), 1.0, grp.data_ptr(), 2
+        ag.out = big.data_ptr() + 8 * pad
+        _abi.check(lib.mod16_time_aggregate_f32(ctypes.byref(ag), T, N, 0, None))
+        torch.cuda.synchronize()
+        assert bool((big[:pad] == -5.0).all()) and bool((big[pad + 2 * N:] == -5.0).all())
+        ref = torch.stack([x[0::2].double().sum(0), x[1::2].double().sum(0)]).reshape(-1)
+        assert torch.allclose(big[pad:pad + 2 * N], ref, rtol=1e-12)

@@ -325,3 +325,25 @@ def test_large_host_arrays_take_the_threaded_staging_path(cuda_lib):
     s = torch.cuda.current_stream(dev)
     t = hostcopy.upload([a], dev, s)[0]
     assert np.array_equal(hostcopy.download(t, s), a)
+
+
+@pytest.mark.parametrize('N', [480 * 3, 480 * 3 + 4, 1001, 4])
+def test_outputs_stay_inside_their_buffers(cuda_lib, N):
+    'Canaries around every output of K1 (bulk-copy and strided kernels, ragged last tile).'
+    from mod16_b200.forward import run_forward
+    T = 7
+    dev = torch.device('cuda', 0)
+    d = synthetic.device_drivers(T, N, 9, dev)
+    d['lai'][3, N // 2] = float('nan')
+    drv = [d[k] for k in NAMES]
+    p7 = [-8., 8.8, 650., 4400., .02, .02, 1e-5, .0055, 60., 95., 250.]
+    pad = 1024
+    for sem, mode, n_out in (('static', 'sum', 1), ('static', 'day_night', 2),
+                             ('instance', 'components', 6)):
+        big = torch.full((n_out, T * N + 2 * pad), -12345.0, device=dev)
+        outs = [big[k, pad:pad + T * N].view(T, N) for k in range(n_out)]
+        run_forward(drv, params=p7, semantics=sem, out_mode=mode, dtype=np.float32, device=dev,
+                    out=outs)
+        torch.cuda.synchronize()
+        assert bool((big[:, :pad] == -12345.0).all()) and bool((big[:, pad + T * N:] == -12345.0).all())
+        assert not bool((big[:, pad:pad + T * N] == -12345.0).any())
