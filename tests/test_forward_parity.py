@@ -347,3 +347,30 @@ def test_outputs_stay_inside_their_buffers(cuda_lib, N):
         torch.cuda.synchronize()
         assert bool((big[:, :pad] == -12345.0).all()) and bool((big[:, pad + T * N:] == -12345.0).all())
         assert not bool((big[:, pad:pad + T * N] == -12345.0).any())
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_dense_sw_rad_night(cuda_lib, dtype):
+    '''
+    Every reference caller passes sw_rad_night = 0, but the signature takes an array: the
+    twelfth stream of the bulk-copy kernel (one stage fewer), odd T, masked values.
+    '''
+    T, N = 11, 4 * 700
+    rng = np.random.default_rng(12)
+    d = synthetic.host_drivers(T, N, 808, dtype=dtype, sw_rad_night='array')
+    d['sw_rad_night'] = rng.uniform(0, 40, (T, N)).astype(dtype)   # twilight: make it matter
+    d['sw_rad_night'][rng.random((T, N)) < 0.01] = np.nan
+    d['fpar'][:, ::7] = np.nan
+    drv = [d[k] for k in NAMES]
+    d64 = as_f64(drv)
+    with np.errstate(all='ignore'):
+        rd, rn = orc.static_evapotranspiration(BPLUT7, *d64)
+        inst = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, BPLUT7))).evapotranspiration(*d64)
+    gd, gn = MOD16._evapotranspiration(BPLUT7, *drv, dtype=dtype)
+    parity.assert_parity(gd, rd, dtype, what='swn day')
+    parity.assert_parity(gn, rn, dtype, what='swn night')
+    parity.assert_parity(MOD16._et(BPLUT7, *drv, dtype=dtype), rd + rn, dtype, what='swn sum')
+    day, night = MOD16(dict(zip(MOD16.required_parameters, BPLUT7))).evapotranspiration(
+        *drv, dtype=dtype)
+    parity.assert_parity(day, inst[0], dtype, parity.MASS_SCALE, what='swn inst day')
+    parity.assert_parity(night, inst[1], dtype, parity.MASS_SCALE, what='swn inst night')
