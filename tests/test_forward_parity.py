@@ -374,3 +374,42 @@ def test_dense_sw_rad_night(cuda_lib, dtype):
         *drv, dtype=dtype)
     parity.assert_parity(day, inst[0], dtype, parity.MASS_SCALE, what='swn inst day')
     parity.assert_parity(night, inst[1], dtype, parity.MASS_SCALE, what='swn inst night')
+
+
+def test_streamed_forward_from_pinned_host_buffers(cuda_lib):
+    'The end-to-end path of bench.py: double-buffered slabs, ragged last slab, bit-identical.'
+    from mod16_b200.streaming import StreamedForward
+    T, N = 11, 4 * 5000
+    dev = torch.device('cuda', 0)
+    d = synthetic.host_drivers(T, N, 515, dtype=np.float32, nan_frac=0.002)
+    table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51),
+                              MOD16.required_parameters, default_beta=250.0)
+    pft = synthetic.host_pft_map(N, 9)
+    host = dict((k, torch.from_numpy(v).pin_memory() if isinstance(v, np.ndarray) else v)
+                for k, v in d.items())
+    out_host = torch.empty((T, N), dtype=torch.float32).pin_memory()
+    runner = StreamedForward(N, 4, table, pft, device=dev, dtype=np.float32, gate='open')
+    runner.run(host, out_host)
+    ref = MOD16._et_by_pft(table, pft, *[d[k] for k in NAMES], dtype=np.float32, gate='open')
+    assert np.array_equal(out_host.numpy().view(np.int32), ref.view(np.int32))
+    assert runner.h2d_bytes == 11 * T * N * 4 + 2 * N * 4 and runner.d2h_bytes == T * N * 4
+    runner.run(host, out_host)          # buffers are reusable
+    assert np.array_equal(out_host.numpy().view(np.int32), ref.view(np.int32))
+
+
+def test_global_gate_helper_and_mirror_flag(cuda_lib):
+    from mod16_b200 import distributed as D
+    T, N = 6, 257
+    d = synthetic.host_drivers(T, N, 21)
+    d['tmin'] = np.full((T, N), 230.0)           # nobody transpires: the gate is closed
+    drv = [d[k] for k in NAMES]
+    with np.errstate(all='ignore'):
+        ref = orc.static_et(BPLUT7, *drv)
+        ref_open = orc.static_et(BPLUT7, *drv, gate='open')
+    assert np.abs(ref - ref_open).max() > 1e-3
+    out = D.forward_global_gate(drv, params=BPLUT7)[0].cpu().numpy()   # world size 1
+    parity.assert_parity(out, ref, np.float64, what='open_track + fixup')
+    # the float32 op-for-op kernel (testing flag): float32 arithmetic, so only close
+    d32 = [v.astype(np.float32) if isinstance(v, np.ndarray) else v for v in drv]
+    got = MOD16._et(BPLUT7, *d32, dtype=np.float32, force=_abi.FORCE_MIRROR)
+    assert np.allclose(got, ref, rtol=2e-3, atol=2e-2)
