@@ -228,7 +228,7 @@ obj_pack_kernel(const __grid_constant__ ObjArgs<float> a) {
 #define M16_OBJ_BLOCKS 4
 #endif
 #ifndef M16_OBJ_UNROLL
-#define M16_OBJ_UNROLL 1
+#define M16_OBJ_UNROLL 2
 #endif
 constexpr int OBJ_UNROLL = M16_OBJ_UNROLL;
 // MODE 0: gate-open sums only (a draw whose gate turns out closed is redone by the exact
