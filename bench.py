@@ -404,9 +404,9 @@ def main():
     drv_list = [drv[k] for k in synthetic.DRIVER_NAMES]
     out = torch.empty((T, N), device=device, dtype=t_dtype)
     flag = torch.zeros(1, device=device, dtype=torch.int32)
-    # per `_et` call: forward kernel + redo-queue kernel (f32 pipeline), twice when the call-exact
-    # global gate adds its fix-up pass
-    launches_per_step = ((2 if (np_dtype == np.float32 and args.kernel == 'pipe') else 1) *
+    # per `_et` call: forward kernel + redo-queue kernel + overflow sweep (f32 pipeline), twice
+    # when the call-exact global gate adds its fix-up pass
+    launches_per_step = ((3 if (np_dtype == np.float32 and args.kernel == 'pipe') else 1) *
                          (2 if args.gate == 'global' else 1))
 
     force = {'pipe': 0, 'generic': _abi.FORCE_GENERIC,

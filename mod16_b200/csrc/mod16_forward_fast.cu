@@ -153,6 +153,7 @@ constexpr int PIPE_TILE = PIPE_CONSUMERS;  // pixels per block
 constexpr int PIPE_SUB = 2;                // time steps per stage (the two FFMA2 lanes)
 constexpr int PIPE_STAGES = M16_PIPE_STAGES;
 constexpr int PIPE_MAX_ARR = 12;
+constexpr int REDO_MARK = 0x7fc0dead;  // a NaN no arithmetic produces: "evaluate me exactly"
 constexpr int PIPE_QCAP = 512;             // deferred exact re-evaluations per block
 
 struct PipeSrc {  // per-step arrays in stage order
@@ -374,8 +375,16 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
             queued = slot < PIPE_QCAP;
             if (queued) redo_q[slot] = (uint32_t)(i * PIPE_SUB + j) << 10 | (uint32_t)tid;
           }
-          // queue full (fill-heavy data): evaluate in place
-          if (!queued) any_pos |= fix_exact_one<SEM, OUT>(a, lut, t, n);
+          if (!queued) {
+            if (a.redo_cap > 0) {
+              // global queue full (fill-heavy data): leave a marker in the first output; the
+              // sweep kernel finds and evaluates it (the counter past the capacity tells it
+              // to run).  One in-place double evaluation here would hold the whole block.
+              st_stream1(a.out[0] + off + j * t_stride, __int_as_float(REDO_MARK));
+            } else {
+              any_pos |= fix_exact_one<SEM, OUT>(a, lut, t, n);  // no workspace at all
+            }
+          }
         }
       }
     }
@@ -545,6 +554,47 @@ redo_queue_kernel(const __grid_constant__ ForwardArgs<float> a) {
   }
 }
 
+// Third launch of the float32 path; returns at once unless the queue overflowed.  Scans the
+// first output for the marker the main kernel left and evaluates those elements exactly.
+// A block collects the marked indices of a chunk into shared memory first and then works
+// through them one element per thread: the double code runs on full warps however sparse the
+// marks are.
+constexpr int SWEEP_THREADS = 128;
+constexpr int SWEEP_CHUNK = SWEEP_THREADS * 16;
+
+template <int SEM, int OUT>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+redo_sweep_kernel(const __grid_constant__ ForwardArgs<float> a) {
+  __shared__ SharedLut lut;
+  __shared__ long long found[SWEEP_CHUNK];
+  __shared__ int n_found;
+  if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
+  if (a.redo_ws[0] <= (unsigned long long)a.redo_cap) return;
+  stage_lut<SEM>(a, lut);
+  bool any_pos = false;
+  const long long total = (long long)a.T * a.N;
+  for (long long base = (long long)blockIdx.x * SWEEP_CHUNK; base < total;
+       base += (long long)gridDim.x * SWEEP_CHUNK) {
+    if (threadIdx.x == 0) n_found = 0;
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < SWEEP_CHUNK / SWEEP_THREADS; ++k) {
+      const long long e = base + k * SWEEP_THREADS + threadIdx.x;
+      if (e < total && __float_as_int(__ldg(a.out[0] + e)) == REDO_MARK)
+        found[atomicAdd(&n_found, 1)] = e;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_found; k += SWEEP_THREADS) {
+      const long long e = found[k];
+      any_pos |= fix_exact_one<SEM, OUT>(a, lut, e / a.N, e % a.N);
+    }
+    __syncthreads();
+  }
+  if (a.track_gate) {
+    if (__any_sync(0xffffffffu, any_pos) && (threadIdx.x & 31) == 0) *a.gate_flag = 1;
+  }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // The pipelined kernel needs: N % 4 == 0 and 16-byte aligned bases (every bulk copy is a
@@ -591,6 +641,8 @@ static int launch_pipe_swn(const ForwardArgs<float>& a, const PipeSrc& src, dim3
   M16_CUDA_CHECK(cudaGetLastError());
   if (a.redo_cap > 0) {
     redo_queue_kernel<SEM, OUT><<<148 * 4, 128, 0, st>>>(a);  // 126 registers: 4 blocks per SM
+    M16_CUDA_CHECK(cudaGetLastError());
+    redo_sweep_kernel<SEM, OUT><<<148 * 4, SWEEP_THREADS, 0, st>>>(a);
     M16_CUDA_CHECK(cudaGetLastError());
   }
   return MOD16_OK;

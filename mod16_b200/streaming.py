@@ -120,7 +120,8 @@ class StreamedForward(object):
                                 out_mode='sum', gate=self.gate, dtype=self.np_dtype,
                                 device=dev, stream=self.s_run, gate_flag=self.flags[b],
                                 out=[buf['out'][:rows]])
-                    self.launches += 2 if self.gate == 'global' else 1
+                    self.launches += (2 if self.gate == 'global' else 1) * \
+                        (3 if self.np_dtype == np.float32 else 1)
                     ev_run[b] = torch.cuda.Event()
                     ev_run[b].record(self.s_run)
                 with torch.cuda.stream(self.s_out):

@@ -413,3 +413,37 @@ def test_global_gate_helper_and_mirror_flag(cuda_lib):
     d32 = [v.astype(np.float32) if isinstance(v, np.ndarray) else v for v in drv]
     got = MOD16._et(BPLUT7, *d32, dtype=np.float32, force=_abi.FORCE_MIRROR)
     assert np.allclose(got, ref, rtol=2e-3, atol=2e-2)
+
+
+def test_double_queue_overflow_takes_the_sweep(cuda_lib):
+    '''
+    More out-of-domain elements than the queue holds (unmasked fill values, negative VPD): the
+    main kernel leaves markers, the sweep kernel evaluates them; results are the oracle's.
+    '''
+    from mod16_b200.forward import run_forward
+    T, N = 12, 4 * 480 * 3
+    d = synthetic.host_drivers(T, N, 99, dtype=np.float32)
+    rng = np.random.default_rng(5)
+    d['vpd_day'][rng.random((T, N)) < 0.05] = -40.0
+    d['lai'][:, ::11] = -9999.0
+    d['tmin'][rng.random((T, N)) < 0.01] = np.nan
+    drv = [d[k] for k in NAMES]
+    with np.errstate(all='ignore'):
+        rd, rn = orc.static_evapotranspiration(BPLUT7, *as_f64(drv))
+    tiny = torch.zeros(1 + 64, dtype=torch.int64, device='cuda')     # room for 64 entries
+    for mode, ref in (('sum', [rd + rn]), ('day_night', [rd, rn])):
+        got = run_forward(drv, params=BPLUT7, semantics='static', out_mode=mode,
+                          dtype=np.float32, workspace=tiny)
+        for g, r in zip(got, ref):
+            parity.assert_parity(g, r, np.float32, what='overflow ' + mode)
+    with np.errstate(all='ignore'):
+        ro = orc.static_et(BPLUT7, *as_f64(drv), gate='open')
+    got = run_forward(drv, params=BPLUT7, semantics='static', out_mode='sum', gate='open',
+                      dtype=np.float32, workspace=tiny)[0]
+    assert int(tiny[0].item()) > 64                                   # it did overflow
+    parity.assert_parity(got, ro, np.float32, what='overflow open')
+    # (no workspace at all: block-local queue, in-place evaluation beyond it)
+    none = torch.zeros(1, dtype=torch.int64, device='cuda')
+    got = run_forward(drv, params=BPLUT7, semantics='static', out_mode='sum', dtype=np.float32,
+                      workspace=none)[0]
+    parity.assert_parity(got, rd + rn, np.float32, what='no workspace')
