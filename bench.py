@@ -200,7 +200,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': 'pixel-timesteps/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def workload_name(args):
@@ -319,7 +319,7 @@ def run_objective_bench(args):
         cpu = {'value': args.cpu_draws * T * N / dt, 'unit': 'draw-elements/s (all elements)',
                'cores': 1, 'kind': 'port', 'sample': '%d draws' % args.cpu_draws,
                'rmsd_max_abs_diff': float(np.max(np.abs(got - np.array(ref))))}
-    print(json.dumps({
+    emit(json.dumps({
         'metric': 'draw-elements/s (objective batch)', 'value': units / (ms * 1e-3),
         'unit': 'draw-elements/s', 'n_gpus': world, 'shard': args.shard if world > 1 else None,
         'scaling': 'strong', 'steps': steps, 'warmup': warm, 'ms_per_step': ms,
@@ -328,7 +328,7 @@ def run_objective_bench(args):
         'config': {'workload': args.workload, 'draws': D, 'T': T, 'N': N,
                    'valid_elements': valid, 'all_elements': T * N},
         'rmsd_range': [float(rm.min().item()), float(rm.max().item())],
-        'cpu_baseline': cpu}), flush=True)
+        'cpu_baseline': cpu}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -358,8 +358,37 @@ def resident_drivers(T, N, seed, device, torch_dtype, kind):
     return out
 
 
+class _QuietStdout(object):
+    '''
+    Keeps stdout for the ONE JSON line: everything libraries print to file descriptor 1 in
+    between (NCCL's version banner, for one) goes to stderr.
+    '''
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.fd, (line + '\n').encode())
+
+
+_OUT = None
+
+
+def emit(line):
+    if _OUT is not None:
+        _OUT.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global _OUT
     args = parse()
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        _OUT = _QuietStdout()
     if args.impl == 'reference':
         if int(os.environ.get('RANK', '0')) == 0:
             run_reference(args)
@@ -552,7 +581,7 @@ def main():
             'clocks': clocks, 'cpu_baseline': cpu,
             'wall_s_timed_region': t_wall,
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
