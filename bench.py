@@ -553,7 +553,7 @@ def main():
         assert np.isfinite(out_host[:1, :4096].numpy()).all()
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:   # (reported at N = 1 only)
         cpu = cpu_single(min(T, YEAR_T), args.cpu_pixels, args.kind)
     sampler.stop()
     clocks = sampler.summary()
