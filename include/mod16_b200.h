@@ -124,10 +124,14 @@ typedef struct mod16_params {
 typedef struct mod16_out {
   void* out[6];       /* device (T, N) row-major, dense; see MOD16_OUT_* */
   int32_t* gate_flag; /* device int; required by GATE_GLOBAL / OPEN_TRACK / FIXUP */
-  /* Optional device scratch of the float32 path (8-byte aligned, mod16_workspace_bytes()
-     recommended): the rare elements that must be re-evaluated in double precision are
-     queued here and evaluated by a second, tiny launch.  NULL / too small: they are
-     evaluated inside the main kernel (same results, slower).  Contents are scratch. */
+  /* Optional device scratch of the float32 path (8-byte aligned): the rare elements that must
+     be re-evaluated in double precision are queued here (8 bytes each after an 8-byte
+     counter) and evaluated by a second launch.  mod16_workspace_bytes() is the minimum worth
+     passing; 8 bytes per 64 elements of the call holds every data set measured so far
+     (physical drivers queue 5e-5 of their elements, unmasked fill values or negative VPD
+     more).  A queue that fills up costs speed only: the surplus is marked in out[0] and
+     found again by a third launch.  NULL / tiny: a small per-block queue, then evaluation
+     inside the main kernel (same results, slow).  Contents are scratch. */
   void* workspace;
   int64_t workspace_bytes;
 } mod16_out_t;
