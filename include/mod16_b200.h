@@ -255,7 +255,9 @@ int mod16_elementwise_f64(const mod16_elementwise_t* ew, int64_t T, int64_t N, v
  * constraint, mod16/calibration.py:783-790: mass = x * 86400 / lhv, negatives dropped,
  * summed per year).  term(t, n) = x * scale / divisor (divisor NULL: x * scale);
  * out[g][n] = sum of the terms of the steps whose group index is g; total[g] = sum over n.
- * Accumulation is in double; NaN terms propagate like numpy's sum unless SKIP_NAN. */
+ * Accumulation is in double, in time order, by the one thread that owns the pixel (no
+ * floating-point atomics; `total` is a fixed-order second pass): results are bit-reproducible
+ * run to run.  NaN terms propagate like numpy's sum unless SKIP_NAN. */
 #define MOD16_AGG_CLAMP_NEG 0x1u /* negative terms count as 0 (calibration.py:784) */
 #define MOD16_AGG_SKIP_NAN 0x2u  /* NaN terms count as 0 (nansum) */
 

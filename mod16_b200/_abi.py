@@ -128,6 +128,12 @@ def load(path=None):
         raise Mod16Error(
             'CUDA library %s is not built; run `python -m mod16_b200.build` '
             '(there is no CPU fallback)' % path)
+    if path == LIB_PATH:
+        from . import build as _build
+        if _build.is_stale():
+            raise Mod16Error(
+                '%s was not built from the sources in this tree; run `python -m '
+                'mod16_b200.build`' % path)
     lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in EXPORTS.items():
         fn = getattr(lib, name)

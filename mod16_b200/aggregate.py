@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from .forward import pick_device
+from .forward import hand_over, launch_stream, pick_device
 
 _TORCH_DT = {np.dtype('float32'): torch.float32, np.dtype('float64'): torch.float64}
 
@@ -42,7 +42,7 @@ def time_aggregate(x, group=None, n_groups=None, divisor=None, scale=1.0, clamp_
         np_dt = np.dtype('float64')
     if np.ndim(x) != 2:
         raise ValueError('x must be (T, N)')
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), launch_stream(dev, stream) as (s, caller_stream):
         xt = _dev(x, dev, _TORCH_DT[np_dt])
         T, N = xt.shape
         keep = [xt]
@@ -72,13 +72,11 @@ def time_aggregate(x, group=None, n_groups=None, divisor=None, scale=1.0, clamp_
             tot = torch.empty((ag.n_groups,), device=dev, dtype=torch.float64)
             ag.total = tot.data_ptr()
         flags = (_abi.AGG_CLAMP_NEG if clamp_neg else 0) | (_abi.AGG_SKIP_NAN if skip_nan else 0)
-        s = stream if stream is not None else torch.cuda.current_stream(dev)
         fn = lib.mod16_time_aggregate_f32 if np_dt == np.dtype('float32') \
             else lib.mod16_time_aggregate_f64
         _abi.check(fn(ctypes.byref(ag), T, N, flags, ctypes.c_void_p(s.cuda_stream)))
         if as_torch:
-            for t in keep:
-                t.record_stream(s)
+            hand_over((out, tot), caller_stream)
             return (out, tot) if total else out
         res = out.cpu().numpy()
         return (res, tot.cpu().numpy()) if total else res

@@ -27,17 +27,34 @@ FLAGS = [
 ]
 
 
-def _stale():
-    if not os.path.exists(LIB_PATH):
+HASH_PATH = LIB_PATH + '.srchash'
+
+
+def source_hash():
+    'sha256 over the sources, headers and compiler flags the library is built from.'
+    import hashlib
+    h = hashlib.sha256(' '.join(FLAGS).encode())
+    for name in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, name), 'rb') as f:
+            h.update(name.encode() + b'\0' + f.read())
+    return h.hexdigest()
+
+
+def is_stale():
+    '''
+    True when the library is missing or was built from other sources than the ones in the
+    tree (content hash recorded next to the binary -- modification times do not survive a
+    checkout or the snapshot that carries the binary to the GPU box).
+    '''
+    if not (os.path.exists(LIB_PATH) and os.path.exists(HASH_PATH)):
         return True
-    built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
     'Compiles the library if a source is newer than it.  Returns the library path.'
-    if not force and not _stale():
+    if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [NVCC] + FLAGS + ['-o', LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
@@ -47,6 +64,8 @@ def build(force=False, verbose=False):
         f.write(' '.join(cmd) + '\n' + log)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + log[-6000:])
+    with open(HASH_PATH, 'w') as f:
+        f.write(source_hash() + '\n')
     if verbose:
         print(log)
     return LIB_PATH

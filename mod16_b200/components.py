@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 from . import _abi
-from .forward import _Staged, _shape, _view_2d, pick_device, result_dtype
+from .forward import (_Staged, _shape, _view_2d, hand_over, launch_stream, pick_device,
+                      result_dtype)
 
 _OP = dict((name, i) for i, name in enumerate(_abi.OPS))
 
@@ -32,7 +33,7 @@ def elementwise(op, args, params=None, opt=(0.0, 0.0), n_out=1, dtype=None, devi
         as_torch = any(isinstance(v, torch.Tensor) and v.device.type == 'cuda' for v in given)
     full_shape = tuple(np.broadcast_shapes(*[_shape(v) for v in given]))
     T, N = _view_2d(full_shape)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), launch_stream(dev, stream) as (s, caller_stream):
         st = _Staged(dev, np_dtype)
         st.full_shape = full_shape
         ew = _abi.Elementwise()
@@ -50,15 +51,12 @@ def elementwise(op, args, params=None, opt=(0.0, 0.0), n_out=1, dtype=None, devi
         outs = [torch.empty((T, N), device=dev, dtype=st.t_dtype) for _ in range(n_out)]
         for k, o in enumerate(outs):
             ew.out[k] = o.data_ptr()
-        s = stream if stream is not None else torch.cuda.current_stream(dev)
         fn = lib.mod16_elementwise_f32 if np_dtype == np.dtype('float32') \
             else lib.mod16_elementwise_f64
         _abi.check(fn(ctypes.byref(ew), T, N, ctypes.c_void_p(s.cuda_stream)))
         outs = [o.reshape(full_shape) for o in outs]
         if as_torch:
-            if stream is not None and s != torch.cuda.current_stream(dev):
-                for t in st.keep + outs:
-                    t.record_stream(s)
+            hand_over(outs, caller_stream)
             res = outs
         else:
             res = [o.cpu().numpy() for o in outs]

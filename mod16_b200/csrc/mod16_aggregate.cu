@@ -7,10 +7,12 @@
 // Layout: one thread per 16 bytes of a row (4 float / 2 double pixels; one pixel per thread
 // for ragged or unaligned rows), a slice of time steps per block row walked in batches of 8
 // steps whose loads are all issued before the first is used (memory-level parallelism
-// instead of occupancy); partial sums are flushed with double atomics whenever the
-// group index changes (group[t] is uniform across the block, so the flush is
-// warp-uniform).  The domain total per group is a warp-shuffle reduction of the flushed
-// values followed by one atomic per warp.
+// instead of occupancy).  Determinism: a thread owns its pixels for ALL time steps (time is
+// never split across blocks), so a partial sum is flushed with a plain read-modify-write of
+// out[g][n] whenever the group index changes -- no floating-point atomics, the summation
+// order is the time order, results are bit-reproducible run to run.  The domain total per
+// group is a second, tiny launch: one block per group sums out[g][:] in a fixed order
+// (per-thread strided partials, then a fixed shuffle / shared-memory tree).
 #include "mod16_common.cuh"
 
 namespace mod16 {
@@ -25,7 +27,6 @@ struct AggArgs {
   double* out;
   double* total;
   int64_t T, N;
-  int t_chunk;
   int clamp_neg, skip_nan;
 };
 
@@ -46,29 +47,17 @@ __global__ void __launch_bounds__(256, HAS_DIV ? 2 : 3)
 time_aggregate_kernel(const __grid_constant__ AggArgs<R> a) {
   typedef Pack<R, VEC> P;
   const int64_t n0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-  const int64_t t0 = (int64_t)blockIdx.y * a.t_chunk;
-  int64_t t1 = t0 + a.t_chunk;
-  if (t1 > a.T) t1 = a.T;
+  const int64_t t0 = 0, t1 = a.T;
   constexpr int AGG_UNROLL = 8;
   const bool live = n0 < a.N;   // (VEC > 1 only when N % VEC == 0: the whole pack is live)
   double acc[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) acc[k] = 0.0;
   int cur = -1;
-  auto flush = [&](int g) {  // block-uniform call
-    if (g >= 0 && g < a.n_groups) {
-      double mine = 0.0;
-      if (live) {
+  auto flush = [&](int g) {  // block-uniform call; this thread alone owns out[g][n0 ..]
+    if (g >= 0 && g < a.n_groups && live) {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          atomicAdd(a.out + (int64_t)g * a.N + n0 + k, acc[k]);
-          mine += acc[k];
-        }
-      }
-      if (a.total) {
-        const double w = warp_sum(mine);
-        if ((threadIdx.x & 31) == 0) atomicAdd(a.total + g, w);
-      }
+      for (int k = 0; k < VEC; ++k) a.out[(int64_t)g * a.N + n0 + k] += acc[k];
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k) acc[k] = 0.0;
@@ -80,7 +69,7 @@ time_aggregate_kernel(const __grid_constant__ AggArgs<R> a) {
 #pragma unroll
     for (int u = 0; u < AGG_UNROLL; ++u) {
       const int64_t t = tb + u;
-      gs[u] = -2;
+      gs[u] = -1;  // (steps past the end are recognised by their index, not by a sentinel)
       if (t < t1) {
         gs[u] = a.group ? __ldg(a.group + t) : 0;
         if (live && gs[u] >= 0 && gs[u] < a.n_groups) {
@@ -91,8 +80,9 @@ time_aggregate_kernel(const __grid_constant__ AggArgs<R> a) {
     }
 #pragma unroll
     for (int u = 0; u < AGG_UNROLL; ++u) {
-      const int g = gs[u];
-      if (g == -2) break;  // past the end of the chunk (block-uniform)
+      if (tb + u >= t1) break;  // past the last step (block-uniform)
+      int g = gs[u];
+      if (g < 0 || g >= a.n_groups) g = -1;  // every out-of-range group: skipped
       if (g != cur) {
         if (cur != -1) flush(cur);
         cur = g;
@@ -116,6 +106,24 @@ time_aggregate_kernel(const __grid_constant__ AggArgs<R> a) {
   if (cur != -1) flush(cur);
 }
 
+// total[g] = sum over n of out[g][n], fixed order: thread i adds elements i, i + 256, ...;
+// then a fixed shuffle tree per warp and a serial sum of the eight warp results.
+__global__ void __launch_bounds__(256)
+aggregate_total_kernel(const double* __restrict__ out, double* __restrict__ total, int64_t N) {
+  __shared__ double part[8];
+  const double* row = out + (int64_t)blockIdx.x * N;
+  double s = 0.0;
+  for (int64_t n = threadIdx.x; n < N; n += 256) s += row[n];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    total[blockIdx.x] = t;
+  }
+}
+
 template <typename R>
 static int run_aggregate(const mod16_aggregate_t* g, int64_t T, int64_t N, uint32_t flags,
                          cudaStream_t st) {
@@ -136,25 +144,24 @@ static int run_aggregate(const mod16_aggregate_t* g, int64_t T, int64_t N, uint3
   const int threads = 256;
   // 16-byte loads when the rows allow them (N a multiple of the pack, aligned bases)
   constexpr int VEC = 16 / (int)sizeof(R);
-  const bool vec = N % VEC == 0 && (reinterpret_cast<uintptr_t>(g->x) & 15) == 0 &&
+  // (small N: one pixel per thread, so that more threads share the serial walk over time)
+  const bool vec = N % VEC == 0 && N >= 148 * threads * VEC &&
+                   (reinterpret_cast<uintptr_t>(g->x) & 15) == 0 &&
                    (!g->divisor || (reinterpret_cast<uintptr_t>(g->divisor) & 15) == 0);
   const int64_t per_block = (int64_t)threads * (vec ? VEC : 1);
   const int64_t bx = (N + per_block - 1) / per_block;
   if (bx > 2147483647LL) return MOD16_ERR_SHAPE;
-  // time slices: enough block rows for several waves of 148 SMs x 8 resident blocks
-  int64_t want_rows = (148 * 8 * 2 + bx - 1) / bx;
-  if (want_rows < 1) want_rows = 1;
-  int64_t chunk = (T + want_rows - 1) / want_rows;
-  if (chunk < 1) chunk = 1;
-  int64_t by = (T + chunk - 1) / chunk;
-  while (by > 65535) { chunk *= 2; by = (T + chunk - 1) / chunk; }
-  a.t_chunk = (int)chunk;
-  const dim3 grid((unsigned)bx, (unsigned)by);
+  // (time is not split across blocks: see the note on determinism above)
+  const dim3 grid((unsigned)bx, 1);
   if (vec && a.div) time_aggregate_kernel<R, VEC, true><<<grid, threads, 0, st>>>(a);
   else if (vec) time_aggregate_kernel<R, VEC, false><<<grid, threads, 0, st>>>(a);
   else if (a.div) time_aggregate_kernel<R, 1, true><<<grid, threads, 0, st>>>(a);
   else time_aggregate_kernel<R, 1, false><<<grid, threads, 0, st>>>(a);
   M16_CUDA_CHECK(cudaGetLastError());
+  if (g->total) {
+    aggregate_total_kernel<<<g->n_groups, 256, 0, st>>>(g->out, g->total, N);
+    M16_CUDA_CHECK(cudaGetLastError());
+  }
   return MOD16_OK;
 }
 

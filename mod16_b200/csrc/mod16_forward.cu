@@ -192,7 +192,6 @@ int run_with_gate(ForwardArgs<R>& a, uint32_t flags, cudaStream_t st, PassFn pas
 }
 
 // defined in mod16_forward_fast.cu
-bool fast_f32_applicable(const ForwardArgs<float>& a, uint32_t flags);
 int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st);
 
 template int build_forward_args<float>(const mod16_drivers_t*, const mod16_params_t*,
@@ -242,7 +241,7 @@ int mod16_forward_f32(const mod16_drivers_t* drivers, const mod16_params_t* para
   int rc = mod16::build_forward_args<float>(drivers, params, out, T, N, flags, a);
   if (rc != MOD16_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool fast = !(flags & MOD16_FORCE_MIRROR) && mod16::fast_f32_applicable(a, flags);
+  const bool fast = !(flags & MOD16_FORCE_MIRROR);  // every layout has a fast-math kernel
   return mod16::run_with_gate<float>(a, flags, st, [&](mod16::ForwardArgs<float>& x) {
     return fast ? mod16::launch_fast_f32(x, flags, st)
                 : mod16::launch_strided<float>(x, flags, st);

@@ -621,21 +621,13 @@ static bool pipe_ok(const ForwardArgs<float>& a) {
   return true;
 }
 
-bool fast_f32_applicable(const ForwardArgs<float>& a, uint32_t flags) {
-  (void)a; (void)flags;
-  return true;  // every layout has a fast-math kernel; pipe_ok() picks which
-}
-
 template <int SEM, int OUT, bool SWN>
 static int launch_pipe_swn(const ForwardArgs<float>& a, const PipeSrc& src, dim3 grid,
                            size_t smem, cudaStream_t st) {
-  static bool configured = false;  // per instantiation; the attribute is per function
-  if (!configured) {
-    M16_CUDA_CHECK(cudaFuncSetAttribute(
-        forward_pipe_kernel<SEM, OUT, SWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        PIPE_STAGES * PIPE_SUB * (PIPE_MAX_ARR - 1) * PIPE_TILE * (int)sizeof(float)));
-    configured = true;
-  }
+  // (the attribute is per function AND per device: set before every launch, it is cheap)
+  M16_CUDA_CHECK(cudaFuncSetAttribute(
+      forward_pipe_kernel<SEM, OUT, SWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      PIPE_STAGES * PIPE_SUB * (PIPE_MAX_ARR - 1) * PIPE_TILE * (int)sizeof(float)));
   if (a.redo_cap > 0) M16_CUDA_CHECK(cudaMemsetAsync(a.redo_ws, 0, 8, st));
   forward_pipe_kernel<SEM, OUT, SWN><<<grid, PIPE_THREADS, smem, st>>>(a, src);
   M16_CUDA_CHECK(cudaGetLastError());

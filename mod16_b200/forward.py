@@ -9,6 +9,7 @@ input that is constant along time or along pixels is never materialised -- it is
 with a zero stride.  Inputs already resident on the GPU (torch CUDA tensors) are used in
 place; host inputs are copied to the device for the call and results are copied back.
 '''
+import contextlib
 import ctypes
 import numpy as np
 import torch
@@ -81,6 +82,38 @@ def pick_device(values, device=None):
     return torch.device('cuda', torch.cuda.current_device())
 
 
+@contextlib.contextmanager
+def launch_stream(dev, stream):
+    '''
+    Makes ``stream`` (None: the current stream; an int: a raw cudaStream_t) the current stream
+    for the body, after it has waited for the work already queued on the caller's current
+    stream.  Staging copies, dtype conversions, scratch allocation, the launches and the
+    read-back of a call are all issued inside, so they are ordered with the kernel (ADVICE r1:
+    with a foreign stream the kernel could otherwise start before its inputs had landed, and
+    a read-back could overtake it).  Yields ``(s, caller_stream)``; ``caller_stream`` is None
+    unless ``s`` is foreign.
+    '''
+    cur = torch.cuda.current_stream(dev)
+    if stream is None:
+        s = cur
+    elif isinstance(stream, int):
+        s = torch.cuda.ExternalStream(stream, device=dev)
+    else:
+        s = stream
+    if s != cur:
+        s.wait_stream(cur)
+    with torch.cuda.stream(s):
+        yield s, (cur if s != cur else None)
+
+
+def hand_over(tensors, caller_stream):
+    'Results of a call on a foreign stream will be read on the caller\'s: tell the allocator.'
+    if caller_stream is not None:
+        for t in tensors:
+            if t is not None:
+                t.record_stream(caller_stream)
+
+
 class _Staged(object):
     'Keeps device copies alive for the duration of a call and fills Driver structs.'
 
@@ -140,7 +173,9 @@ class _Staged(object):
         slot.scalar = 0.0
 
 
-_WORKSPACES = {}
+_WORKSPACES = {}          # (device index, stream handle) -> int64 scratch tensor
+_WS_MAX_BYTES = 256 << 20   # per stream; a full queue only costs speed (marker + sweep)
+_WS_MAX_STREAMS = 8         # least recently used entries beyond this are dropped
 
 
 def _workspace(dev, stream_handle, lib, units=0):
@@ -148,16 +183,25 @@ def _workspace(dev, stream_handle, lib, units=0):
     Per-device, per-stream scratch of the float32 path (the queue of elements re-evaluated in
     double precision).  Cached: calls on one stream are ordered, so they can share it.  Sized
     for 1/64 of the call's elements (the measured rates are 5e-5 on physical and 1e-3 on
-    all-uniform drivers; negative VPD or unmasked fill values raise it), at least the
-    library's recommendation, at most 2 GiB; a full queue only costs speed, never results.
+    all-uniform drivers; unmasked fill values raise it), at least the library's
+    recommendation, at most 256 MiB; a full queue only costs speed, never results.  At most
+    eight streams keep a buffer (least recently used first out); ``release_workspaces()``
+    frees them all.
     '''
     key = (dev.index, stream_handle)
-    want = max(lib.mod16_workspace_bytes() // 8, min(units // 64 + 1024, (2 << 30) // 8))
-    ws = _WORKSPACES.get(key)
+    want = max(lib.mod16_workspace_bytes() // 8, min(units // 64 + 1024, _WS_MAX_BYTES // 8))
+    ws = _WORKSPACES.pop(key, None)
     if ws is None or ws.numel() < want:
         ws = torch.empty(want, device=dev, dtype=torch.int64)
-        _WORKSPACES[key] = ws
+    _WORKSPACES[key] = ws          # (re-inserted: dicts keep insertion order = LRU order)
+    while len(_WORKSPACES) > _WS_MAX_STREAMS:
+        _WORKSPACES.pop(next(iter(_WORKSPACES)))
     return ws
+
+
+def release_workspaces():
+    'Drops every cached scratch buffer (they are re-created on demand).'
+    _WORKSPACES.clear()
 
 
 def _view_2d(shape):
@@ -215,102 +259,109 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     full_shape = tuple(np.broadcast_shapes(*shapes))
     T, N = _view_2d(full_shape)
 
-    with torch.cuda.device(dev):
-        st = _Staged(dev, np_dtype)
-        st.full_shape = full_shape
-        s = stream if stream is not None else torch.cuda.current_stream(dev)
-        # large pageable numpy drivers: chunked, threaded staging through pinned buffers
-        # (a float64 array headed for the float32 path is converted on the device)
-        big = [k for k, v in enumerate(drivers) if hostcopy.worthwhile(v)] \
-            if hasattr(s, 'wait_event') else []
-        if big:
-            for k, t in zip(big, hostcopy.upload([drivers[k] for k in big], dev, s)):
-                if t.dtype != st.t_dtype:
-                    with torch.cuda.stream(s):
-                        t = t.to(st.t_dtype)
-                drivers[k] = t
+    with torch.cuda.device(dev), launch_stream(dev, stream) as (s, caller_stream):
+        return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
+                              semantics, out_mode, gate, r_corr_list, force, as_torch,
+                              gate_flag, out, workspace, full_shape, T, N, caller_stream)
+
+
+def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, semantics,
+                   out_mode, gate, r_corr_list, force, as_torch, gate_flag, out, workspace,
+                   full_shape, T, N, caller_stream):
+    'Body of run_forward; the current stream is `s`.'
+    params = plist if plist else None
+    st = _Staged(dev, np_dtype)
+    st.full_shape = full_shape
+    # large pageable numpy drivers: chunked, threaded staging through pinned buffers
+    # (a float64 array headed for the float32 path is converted on the device)
+    big = [k for k, v in enumerate(drivers) if hostcopy.worthwhile(v)]
+    if big:
+        for k, t in zip(big, hostcopy.upload([drivers[k] for k in big], dev, s)):
+            if t.dtype != st.t_dtype:
+                t = t.to(st.t_dtype)
+            drivers[k] = t
+            st.keep.append(t)
+    cd = _abi.Drivers()
+    for k, v in enumerate(drivers):
+        st.fill(cd.drv[k], v, T, N, len(full_shape))
+    cd.has_r_corr = 1 if r_corr_list is not None else 0
+    for k, v in enumerate(extra[:2]):
+        st.fill(cd.r_corr[k], v, T, N, len(full_shape))
+
+    cp = _abi.Params()
+    if pft is not None:
+        if table is None:
+            raise TypeError('`pft` needs the 11 x 13 `table`')
+        tab = np.asarray(table, np.float64)
+        if tab.shape != (_abi.N_PARAMS, _abi.N_PFT):
+            raise ValueError('table must be 11 x 13')
+        pt = st.tensor(pft, torch.uint8).reshape(-1)
+        if pt.numel() != N:
+            raise ValueError('pft must hold one code per pixel (N = %d)' % N)
+        pt = pt.contiguous()
+        st.keep.append(pt)
+        cp.pft = pt.data_ptr()
+    else:
+        tab = np.full((_abi.N_PARAMS, _abi.N_PFT), np.nan)
+        if all(_is_scalar(v) for v in plist):
+            tab[:, 0] = [float(v) for v in plist]
+        else:
+            for k, v in enumerate(plist):
+                if _is_scalar(v):
+                    v = np.full((1,), float(v))
+                t = st.tensor(v).reshape(-1)
+                if t.numel() not in (1, N):
+                    raise ValueError(
+                        'parameter %d has %d values, expected 1 or N = %d' % (
+                            k, t.numel(), N))
+                t = t.contiguous()
                 st.keep.append(t)
-        cd = _abi.Drivers()
-        for k, v in enumerate(drivers):
-            st.fill(cd.drv[k], v, T, N, len(full_shape))
-        cd.has_r_corr = 1 if r_corr_list is not None else 0
-        for k, v in enumerate(extra[:2]):
-            st.fill(cd.r_corr[k], v, T, N, len(full_shape))
+                cp.arrays[k] = t.data_ptr()
+                cp.array_stride[k] = 0 if t.numel() == 1 else 1
+    for i in range(_abi.N_PARAMS):
+        for j in range(_abi.N_PFT):
+            cp.table[i][j] = tab[i, j]
 
-        cp = _abi.Params()
-        if pft is not None:
-            if table is None:
-                raise TypeError('`pft` needs the 11 x 13 `table`')
-            tab = np.asarray(table, np.float64)
-            if tab.shape != (_abi.N_PARAMS, _abi.N_PFT):
-                raise ValueError('table must be 11 x 13')
-            pt = st.tensor(pft, torch.uint8).reshape(-1)
-            if pt.numel() != N:
-                raise ValueError('pft must hold one code per pixel (N = %d)' % N)
-            pt = pt.contiguous()
-            st.keep.append(pt)
-            cp.pft = pt.data_ptr()
-        else:
-            tab = np.full((_abi.N_PARAMS, _abi.N_PFT), np.nan)
-            if all(_is_scalar(v) for v in plist):
-                tab[:, 0] = [float(v) for v in plist]
-            else:
-                for k, v in enumerate(plist):
-                    if _is_scalar(v):
-                        v = np.full((1,), float(v))
-                    t = st.tensor(v).reshape(-1)
-                    if t.numel() not in (1, N):
-                        raise ValueError(
-                            'parameter %d has %d values, expected 1 or N = %d' % (
-                                k, t.numel(), N))
-                    t = t.contiguous()
-                    st.keep.append(t)
-                    cp.arrays[k] = t.data_ptr()
-                    cp.array_stride[k] = 0 if t.numel() == 1 else 1
-        for i in range(_abi.N_PARAMS):
-            for j in range(_abi.N_PFT):
-                cp.table[i][j] = tab[i, j]
-
-        n_out = {'sum': 1, 'day_night': 2, 'components': 6}[out_mode]
-        flags = {'static': _abi.SEM_STATIC, 'instance': _abi.SEM_INSTANCE}[semantics]
-        flags |= {'sum': _abi.OUT_SUM, 'day_night': _abi.OUT_DAY_NIGHT,
-                  'components': _abi.OUT_COMPONENTS}[out_mode]
-        flags |= _abi.GATE_FLAGS[gate] | force
-        if out is not None:
-            outs = list(out)
-            if len(outs) != n_out or any(
-                    (not o.is_cuda) or o.dtype != st.t_dtype or o.numel() != T * N
-                    or not o.is_contiguous() for o in outs):
-                raise ValueError('`out` must be %d contiguous CUDA tensors of %d elements' % (
-                    n_out, T * N))
-            as_torch = True
-        else:
-            outs = [torch.empty((T, N), device=dev, dtype=st.t_dtype) for _ in range(n_out)]
-        co = _abi.Out()
-        for k, o in enumerate(outs):
-            co.out[k] = o.data_ptr()
-        if gate_flag is None:
-            gate_flag = torch.zeros(1, device=dev, dtype=torch.int32)
-        co.gate_flag = gate_flag.data_ptr()
-        handle = s.cuda_stream if hasattr(s, 'cuda_stream') else int(s)
-        if np_dtype == np.dtype('float32'):
-            ws = workspace if workspace is not None else _workspace(dev, handle, lib, T * N)
-            co.workspace = ws.data_ptr()
-            co.workspace_bytes = ws.numel() * ws.element_size()
-            st.keep.append(ws)
-        fn = lib.mod16_forward_f32 if np_dtype == np.dtype('float32') else lib.mod16_forward_f64
-        _abi.check(fn(ctypes.byref(cd), ctypes.byref(cp), ctypes.byref(co), T, N, flags,
-                      ctypes.c_void_p(handle)))
-        outs = [o.reshape(full_shape) for o in outs]
-        if as_torch:
-            # staged copies must outlive the asynchronous launch on a foreign stream
-            if hasattr(s, 'cuda_stream') and s != torch.cuda.current_stream(dev):
-                for t in st.keep + outs:
-                    t.record_stream(s)
-            return outs
-        res = [hostcopy.download(o, s) if (o.numel() * o.element_size() >=
-                                           hostcopy.THRESHOLD_BYTES and hasattr(s, 'wait_event'))
-               else o.cpu().numpy() for o in outs]  # synchronises
-        if full_shape == ():
-            res = [r[()] for r in res]
-        return res
+    n_out = {'sum': 1, 'day_night': 2, 'components': 6}[out_mode]
+    flags = {'static': _abi.SEM_STATIC, 'instance': _abi.SEM_INSTANCE}[semantics]
+    flags |= {'sum': _abi.OUT_SUM, 'day_night': _abi.OUT_DAY_NIGHT,
+              'components': _abi.OUT_COMPONENTS}[out_mode]
+    flags |= _abi.GATE_FLAGS[gate] | force
+    if out is not None:
+        outs = list(out)
+        if len(outs) != n_out or any(
+                (not o.is_cuda) or o.dtype != st.t_dtype or o.numel() != T * N
+                or not o.is_contiguous() for o in outs):
+            raise ValueError('`out` must be %d contiguous CUDA tensors of %d elements' % (
+                n_out, T * N))
+        as_torch = True
+    else:
+        outs = [torch.empty((T, N), device=dev, dtype=st.t_dtype) for _ in range(n_out)]
+    co = _abi.Out()
+    for k, o in enumerate(outs):
+        co.out[k] = o.data_ptr()
+    if gate_flag is None:
+        gate_flag = torch.zeros(1, device=dev, dtype=torch.int32)
+    co.gate_flag = gate_flag.data_ptr()
+    handle = s.cuda_stream
+    if np_dtype == np.dtype('float32'):
+        ws = workspace if workspace is not None else _workspace(dev, handle, lib, T * N)
+        co.workspace = ws.data_ptr()
+        co.workspace_bytes = ws.numel() * ws.element_size()
+        st.keep.append(ws)
+    fn = lib.mod16_forward_f32 if np_dtype == np.dtype('float32') else lib.mod16_forward_f64
+    _abi.check(fn(ctypes.byref(cd), ctypes.byref(cp), ctypes.byref(co), T, N, flags,
+                  ctypes.c_void_p(handle)))
+    outs = [o.reshape(full_shape) for o in outs]
+    if as_torch:
+        # Staged copies were allocated and used on `s` alone: the caching allocator's stream
+        # ordering keeps them alive.  The results belong to `s` too; the caller orders its
+        # consumers after `s` (and will most likely read them on its own stream).
+        hand_over(outs, caller_stream)
+        return outs
+    res = [hostcopy.download(o, s) if (o.numel() * o.element_size() >=
+                                       hostcopy.THRESHOLD_BYTES)
+           else o.cpu().numpy() for o in outs]  # issued on `s`; synchronises
+    if full_shape == ():
+        res = [r[()] for r in res]
+    return res

@@ -78,6 +78,11 @@ def upload(arrays, device, stream):
             jobs.append((flat_src, flat_dst, off, min(CHUNK_BYTES, a.nbytes - off)))
     done_events = []
     ev_lock = threading.Lock()
+    # The destination blocks come from the caching allocator on the CURRENT stream and may
+    # still be in use by work queued there (a previous call's kernel reading its staged
+    # drivers): the workers' DMA must not start before that work is done.
+    allocated = torch.cuda.Event()
+    allocated.record(torch.cuda.current_stream(device))
 
     def work(job):
         src, dst, off, n = job
@@ -88,6 +93,7 @@ def upload(arrays, device, stream):
             np.copyto(buf.numpy()[:n], src[off:off + n])
             s = ring.stream()
             with torch.cuda.stream(s):
+                s.wait_event(allocated)
                 dst[off:off + n].copy_(buf[:n], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(s)

@@ -22,7 +22,8 @@ import numpy as np
 import torch
 
 from . import _abi
-from .forward import _Staged, _is_scalar, _shape, _view_2d, pick_device, result_dtype
+from .forward import (_Staged, _is_scalar, _shape, _view_2d, hand_over, launch_stream,
+                      pick_device, result_dtype)
 
 
 def _draw_matrix(draws, dev):
@@ -51,7 +52,14 @@ class ObjectiveBackend(object):
     semantics : 'static' (``_et``, W m-2) or 'instance' (day + night of
         ``evapotranspiration()``, kg m-2 s-1)
     gate : 'global' -- each draw gets the batch-global transpiration gate of ITS call, as in
-        the reference (:343) --, 'open' or 'closed'
+        the reference (:343) --, 'open' or 'closed'.  The gate of a draw is taken over the
+        elements that enter its sums, i.e. those with an observation and a weight: both
+        reference callers drop the elements without an observation BEFORE the model sees
+        them (mod16/calibration.py:895-900 ``d.copy()[~np.isnan(tower_obs)]``,
+        mod16/sensitivity.py:179-186 ``drivers = [d[mask] for d in drivers]``), so their
+        ``np.any(g_surf > 0)`` never covers such elements either.  A caller that wants the
+        gate over ALL elements passes observations without NaN and a weight of 0 where the
+        observation is missing.
     dtype : np.float32 (fast path) or np.float64; default follows numpy promotion
     '''
 
@@ -93,7 +101,7 @@ class ObjectiveBackend(object):
         (see ``finish_raw`` and ``distributed.objective_site_sharded``).
         '''
         dev = self.device
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), launch_stream(dev, stream) as (s, caller_stream):
             d = _draw_matrix(draws, dev)
             D = d.shape[0]
             is_f32 = 1 if self.np_dtype == np.dtype('float32') else 0
@@ -114,14 +122,11 @@ class ObjectiveBackend(object):
             co.gate = gate.data_ptr() if gate is not None else None
             co.workspace = ws.data_ptr() + off
             co.workspace_bytes = ws.numel() * 8 - off
-            s = stream if stream is not None else torch.cuda.current_stream(dev)
             fn = self.lib.mod16_objective_batch_f32 if is_f32 else \
                 self.lib.mod16_objective_batch_f64
             _abi.check(fn(ctypes.byref(self.cd), ctypes.byref(co), self.T, self.N, D,
                           self.flags, ctypes.c_void_p(s.cuda_stream)))
-            if stream is not None and s != torch.cuda.current_stream(dev):
-                for t in (d, sse, cnt, ws):
-                    t.record_stream(s)
+            hand_over((sse, cnt, gate, raw_t), caller_stream)
             if raw:
                 return raw_t
             if as_torch:
