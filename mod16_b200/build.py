@@ -15,15 +15,14 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libmod16_b200.so')
-SOURCES = ['mod16_forward.cu', 'mod16_forward_fast.cu', 'mod16_aggregate.cu',
-           'mod16_objective.cu', 'mod16_elementwise.cu']
-HEADERS = ['mod16_math.cuh', 'mod16_fast.cuh', 'mod16_common.cuh', 'mod16_pipe.cuh',
-           'mod16_objective.cuh', os.path.join('..', '..', 'include', 'mod16_b200.h')]
+SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith('.cuh')) + [
+    os.path.join('..', '..', 'include', 'mod16_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
     '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC', '-Xptxas', '-v',
-    '--fmad=true', '-shared', '--threads', '0',
+    '--fmad=true',
 ]
 
 
@@ -57,12 +56,28 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [NVCC] + FLAGS + ['-o', LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    # one nvcc per translation unit, all at once, then one link
+    obj_dir = os.path.join(LIB_DIR, 'obj')
+    os.makedirs(obj_dir, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src[:-3] + '.o')
+        cmd = [NVCC] + FLAGS + ['-c', '-o', obj, os.path.join(CSRC, src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, ' '.join(cmd) + '\n' + res.stdout + res.stderr, res.returncode
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        done = list(pool.map(compile_one, SOURCES))
+    log = '\n'.join(d[1] for d in done)
+    failed = any(d[2] != 0 for d in done)
+    if not failed:
+        cmd = [NVCC, '-shared', '-o', LIB_PATH] + [d[0] for d in done]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += '\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr
+        failed = res.returncode != 0
     with open(os.path.join(LIB_DIR, 'build.log'), 'w') as f:
-        f.write(' '.join(cmd) + '\n' + log)
-    if res.returncode != 0:
+        f.write(log)
+    if failed:
         raise RuntimeError('nvcc failed:\n' + log[-6000:])
     with open(HASH_PATH, 'w') as f:
         f.write(source_hash() + '\n')

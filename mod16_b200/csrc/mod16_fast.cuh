@@ -168,7 +168,9 @@ constexpr double kDD0 = 264.0 * 264.0;    // (239 + Tc)^2 / kDD0 ~ 1    (:1397)
 // constants derived from one BPLUT column (computed in double, stored as float)
 template <class V>
 struct alignas(16) PftConstV {
-  V tmin_close, inv_dtmin, vpd_close, inv_dvpd;  // ramps (:325-326)
+  // ramps (:325-326) in one-FMA form: m_tmin = sat(Tmin * inv_dtmin + tmin_bias),
+  // m_vpd = sat(vpd_off - VPD * inv_dvpd)
+  V tmin_bias, inv_dtmin, vpd_off, inv_dvpd;
   V gl_sh, gl_wv, g_cut, csl;
   V rbl_max, rbl_delta, inv_beta, ok;  // r_tot = rbl_max - rbl_delta * m_vpd (:357-361)
 };
@@ -178,10 +180,10 @@ struct alignas(16) PftConst : PftConstV<float> {
 
 M16_HD PftConst make_pft_const(const double v[11], int sem) {
   PftConst c;
-  c.tmin_close = (float)v[0];
   c.inv_dtmin = (float)(1.0 / (v[1] - v[0]));
-  c.vpd_close = (float)v[3];
+  c.tmin_bias = (float)(-(273.15 + v[0]) / (v[1] - v[0]));  // Tmin in kelvin goes in (:325)
   c.inv_dvpd = (float)(1.0 / (v[3] - v[2]));
+  c.vpd_off = (float)(v[3] / (v[3] - v[2]));
   c.gl_sh = (float)v[4]; c.gl_wv = (float)v[5]; c.g_cut = (float)v[6]; c.csl = (float)v[7];
   c.rbl_max = (float)v[9];
   c.rbl_delta = (float)(v[9] - v[8]);
@@ -235,8 +237,8 @@ M16_HD PixConstV<F2> pair_pix(const PixConst& a, const PixConst& b) {
 }
 M16_HD PftConstV<F2> pair_pft(const PftConstV<float>& a, const PftConstV<float>& b) {
   PftConstV<F2> r;
-  r.tmin_close = F2{a.tmin_close, b.tmin_close}; r.inv_dtmin = F2{a.inv_dtmin, b.inv_dtmin};
-  r.vpd_close = F2{a.vpd_close, b.vpd_close};    r.inv_dvpd = F2{a.inv_dvpd, b.inv_dvpd};
+  r.tmin_bias = F2{a.tmin_bias, b.tmin_bias}; r.inv_dtmin = F2{a.inv_dtmin, b.inv_dtmin};
+  r.vpd_off = F2{a.vpd_off, b.vpd_off};    r.inv_dvpd = F2{a.inv_dvpd, b.inv_dvpd};
   r.gl_sh = F2{a.gl_sh, b.gl_sh}; r.gl_wv = F2{a.gl_wv, b.gl_wv};
   r.g_cut = F2{a.g_cut, b.g_cut}; r.csl = F2{a.csl, b.csl};
   r.rbl_max = F2{a.rbl_max, b.rbl_max}; r.rbl_delta = F2{a.rbl_delta, b.rbl_delta};
@@ -268,26 +270,45 @@ struct StepOutV {  // components and totals of one pixel-timestep (or pair)
   V tot_day, tot_night, tot;  // :380 / :792 per half, and day + night (:193)
 };
 
+// min of three / of the magnitudes of three (device: FMNMX3)
+M16_HD float vmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+M16_HD F2 vmin3(F2 a, F2 b, F2 c) {
+  return F2{fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y)};
+}
+M16_HD float vminabs3(float a, float b, float c) {
+  return fminf(fminf(fabsf(a), fabsf(b)), fabsf(c));
+}
+M16_HD F2 vminabs3(F2 a, F2 b, F2 c) {
+  return F2{fminf(fminf(fabsf(a.x), fabsf(b.x)), fabsf(c.x)),
+            fminf(fminf(fabsf(a.y), fabsf(b.y)), fabsf(c.y))};
+}
+
+// Width of every discontinuity guard after scaling: an element is re-evaluated in double
+// when one of its scaled distances to a switch is below kGuard in magnitude.
+constexpr float kGuard = 1.0e-4f;
+
 // One half-day, fast form.  STATIC night never transpires (its gate is never open).
-// Returns the three components; `need` is OR-ed with the guard predicates.
+// Returns the three components.  `guard` receives the smaller of the half's two scaled
+// distances to a discontinuity in rh (see below); the caller folds all of them into ONE
+// compare.  `need` is only touched for a supplied r_corr outside its sane range.
 template <class V, int SEM, bool DAY, bool HAS_RC>
-M16_HD HalfV<V> half_fast(V t, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V omf, V lai,
-                          const PftConstV<V>& c, const PixConstV<V>& x, int gate,
+M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V omf,
+                          V lai, const PftConstV<V>& c, const PixConstV<V>& x, int gate,
                           typename MaskOf<V>::type& g_pos, typename MaskOf<V>::type& need,
-                          V& gs_out) {
+                          V& gs_out, V& guard_a, V& guard_b) {
   typedef typename MaskOf<V>::type M;
-  const V tc = celsius<V>(t);
   // saturation vapour pressure 610.8 exp(17.27 Tc / (Tc + 237.3)) and its reciprocal (:1365)
   const V xe = ((float)(17.27 * 1.4426950408889634) * tc) * vrcp(tc + 237.3f);
   const V e = vex2(xe);                             // SVP / 610.8
   const V ies = (float)(1.0 / 610.8) * vex2(-xe);   // 1 / SVP
   V rh = vfma(-vpd, ies, 1.0f);
-  if (SEM == SEM_STATIC) rh = vmax(rh, splat<V>(0.0f));  // :280-281 (VPD >= 0 in the domain)
+  if (SEM == SEM_STATIC) rh = vmax(rh, splat<V>(0.0f));  // :280-281 (no upper clamp)
   else rh = vsat(rh);                                    // :671-673
-  // discontinuities in rh: the f_wet jump at 0.7 (:282) and rh -> 0+, where rh^(vpd/beta)
-  // is ill-conditioned (:376)
-  need = mor(need, mor(vlt(vabs(rh - 0.7f), splat<V>(4.0e-6f)),
-                       vlt(vabs(rh - 1.0e-3f), splat<V>(1.0e-3f))));
+  // discontinuities in rh: the f_wet jump at 0.7 (:282), guarded for |rh - 0.7| < 4e-6, and
+  // rh -> 0+, where rh^(vpd/beta) is ill-conditioned (:376), guarded for 0 < rh < 2e-3
+  // (rh == 0 exactly -- the clamp -- is NOT guarded: |0 - 1e-3| * 0.1 == kGuard).
+  guard_a = vfma(rh, 25.0f, -17.5f);       // (rh - 0.7) * 25      : 4e-6 -> kGuard
+  guard_b = vfma(rh, 0.1f, -kGuard);       // (rh - 1e-3) * 0.1    : 1e-3 -> kGuard
   const V rh2 = rh * rh;
   const V fw = vsel(vge(rh, splat<V>(0.7f)), rh2 * rh2, splat<V>(0.0f));  // :282
   const V omfw = 1.0f - fw;
@@ -311,7 +332,7 @@ M16_HD HalfV<V> half_fast(V t, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V
   } else {
     inv_rc = x.inv_p101 * vex2(-1.75f * vlg2(q));
   }
-  const V m_v = vsat((c.vpd_close - vpd) * c.inv_dvpd);  // reversed ramp on VPD (:326)
+  const V m_v = vsat(vfma(-vpd, c.inv_dvpd, c.vpd_off));  // reversed ramp on VPD (:326)
   const V Kf = Kv * fpar;
   const V SA = S * a_can;
   V il = splat<V>(0.0f);
@@ -339,14 +360,16 @@ M16_HD HalfV<V> half_fast(V t, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V
   if (DAY || SEM == SEM_INSTANCE) {
     V gs = splat<V>(0.0f);
     if (DAY) {
-      const V m_t = vsat((celsius<V>(tmin) - c.tmin_close) * c.inv_dtmin);      // :325
+      const V m_t = vsat(vfma(tmin, c.inv_dtmin, c.tmin_bias));                 // :325
       gs = ((c.csl * m_t) * m_v) * inv_rc;                                      // :327-328
     }
     g_pos = vgt(gs, splat<V>(0.0f));
     gs_out = gs;
     const V sc = vfma(c.g_cut, inv_rc, gs);                                     // :329
     const V gbl = (c.gl_sh * lai) * omfw;                                       // :333
-    const M ok = mand(vgt(lai, splat<V>(0.0f)), vgt(omfw, splat<V>(0.0f)));     // :336
+    // lai > 0 and 1 - f_wet > 0 (:336): with gl_sh > 0 (PftConst::ok) and lai >= 0 (domain)
+    // that is gbl > 0 -- rh > 1 (negative VPD, static) makes 1 - f_wet and gbl negative
+    const M ok = vgt(gbl, splat<V>(0.0f));
     const V prod = vsel(ok, gbl * sc, splat<V>(1e-7f));  // g_canopy = prod / tot (:334-337)
     const V tot = vsel(ok, gbl + sc, splat<V>(1.0f));
     const V Yd = vfma(c.gl_sh, X, B);                    // X / r_a_dry (:340)
@@ -385,34 +408,37 @@ M16_HD HalfV<V> half_fast(V t, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V
   return o;
 }
 
-// Physical domain of the fast formulas.  NaN anywhere fails it (fminf / fmaxf drop a NaN
-// operand, hence the self-comparison of the sums).
+// Physical domain of the fast formulas: finite drivers; radiation terms and Tmin not a fill
+// value (-9999, -32768, 1e20 ...); fPAR, LAI, albedo >= 0; VPD > -1000 Pa (a negative VPD --
+// reanalysis dew point above the air temperature -- is plain arithmetic in both semantics:
+// static rh > 1, :279-281; instance rh clamped to 1, :671-673); 206.3 K < T < 340 K.
+// Written as sums of magnitudes (packed adds) and three min / max so that the whole test
+// costs five compares per element; a NaN or an infinity anywhere fails it (every compare
+// with a NaN sum is false, fmin / fmax drop a NaN operand only next to a finite one that is
+// then caught by its sum).
 // `nan_probe` receives a value that is NaN exactly when one of the ten per-step drivers of
 // the masked-driver rule (every per-step driver except sw_rad_night and Tmin, see
 // nan_halves below) is NaN: a sum of absolute values, so infinities cannot cancel into NaN.
 template <class V>
-M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in, V& nan_probe) {
-  // radiation terms and Tmin: finite and not a fill value (-9999, -32768, 1e20 ...)
-  const V r = vmax(vmax(vabs(in.lw_d), vabs(in.lw_n)),
-                   vmax(vmax(vabs(in.sw_d), vabs(in.sw_n)), vabs(in.tmin)));
-  // non-negative quantities
-  const V lo = vmin(vmin(vmin(in.lai, in.fpar), vmin(in.vpd_d, in.vpd_n)), in.alb);
-  const V hi = vmax(vmax(vmax(in.lai, in.fpar), vmax(in.vpd_d, in.vpd_n)), in.alb);
-  const V tl = vmin(in.t_d, in.t_n), th = vmax(in.t_d, in.t_n);
+M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in, V tc_d, V tc_n, V& nan_probe) {
   const V sa = (vabs(in.lw_d) + vabs(in.lw_n)) + vabs(in.sw_d);
   const V sb = vabs(in.sw_n) + vabs(in.tmin);
   const V s2 = ((vabs(in.lai) + vabs(in.fpar)) + (vabs(in.vpd_d) + vabs(in.vpd_n))) +
-               ((vabs(in.alb) + vabs(in.t_d)) + vabs(in.t_n));
-  nan_probe = sa + s2;
-  const V s1 = nan_probe + sb;
-  return mand(mand(mand(vlt(r, splat<V>(9000.0f)), vge(lo, splat<V>(0.0f))),
-                   mand(vlt(hi, splat<V>(1.0e5f)), vgt(tl, splat<V>(200.0f)))),
-              mand(vlt(th, splat<V>(340.0f)), veq(s1, s1)));
+               vabs(in.alb);
+  nan_probe = (sa + s2) + (vabs(in.t_d) + vabs(in.t_n));
+  const V lo = vmin3(in.lai, in.fpar, in.alb);
+  const V vlo = vmin(in.vpd_d, in.vpd_n);
+  const V tmag = vmax(vabs(tc_d), vabs(tc_n));
+  // (nan_probe bounds s2 and is the one sum that sees the temperatures: fmax below would
+  // drop a NaN temperature)
+  return mand(mand(mand(vlt(sa + sb, splat<V>(9000.0f)), vlt(nan_probe, splat<V>(1.1e5f))),
+                   mand(vge(lo, splat<V>(0.0f)), vgt(vlo, splat<V>(-1000.0f)))),
+              vlt(tmag, splat<V>(66.85f)));
 }
 template <class V>
 M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in) {
   V probe;
-  return in_domain<V>(in, probe);
+  return in_domain<V>(in, celsius<V>(in.t_d), celsius<V>(in.t_n), probe);
 }
 
 // Draw-independent part of step_fast()'s guards, for batches that evaluate MANY parameter
@@ -420,14 +446,16 @@ M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in) {
 // rounding of a discontinuity for ANY parameter set -- the soil-heat-flux guard is taken for
 // both states of the (parameter-dependent) annual-temperature window.
 M16_HD bool element_needs_exact(const StepInV<float>& in, float p) {
-  bool need = !((p >= 3.0e4f) && (p <= 1.2e5f) && in_domain<float>(in));
+  // (K2's element records assume 0 <= rh <= 1: negative VPD takes its exact path)
+  bool need = !((p >= 3.0e4f) && (p <= 1.2e5f) && in_domain<float>(in)) ||
+              !(in.vpd_d >= 0.0f) || !(in.vpd_n >= 0.0f);
   const float a_d = fmaf(in.sw_d, 1.0f - in.alb, in.lw_d);
   const float a_n = in.lw_n;
   const float g_d = fmaf(celsius<float>(in.t_d), 4.73f, -20.87f);
   const float g_n = fmaf(celsius<float>(in.t_n), 4.73f, -20.87f);
   const float lim_d = fabsf(0.39f * a_d), lim_n = fabsf(0.39f * a_n);
   need = need || (fabsf(fabsf(g_d) - lim_d) <= 1.0e-4f) || (fabsf(fabsf(g_n) - lim_n) <= 1.0e-4f) ||
-         (lim_d <= 1.0e-4f) || (lim_n <= 1.0e-4f) || (fabsf(a_d) < 1.0e-4f);
+         (lim_d <= 1.0e-4f) || (lim_n <= 1.0e-4f) || (fabsf(a_d) <= 1.0e-4f);
   // (t_d - t_n) >= 5 is exact in float for inputs within a factor of two (Sterbenz)
   const float ts[2] = {in.t_d, in.t_n}, vs[2] = {in.vpd_d, in.vpd_n};
   for (int h = 0; h < 2; ++h) {
@@ -435,7 +463,7 @@ M16_HD bool element_needs_exact(const StepInV<float>& in, float p) {
     const float xe = ((float)(17.27 * 1.4426950408889634) * tc) * s_rcp(tc + 237.3f);
     const float ies = (float)(1.0 / 610.8) * s_ex2(-xe);
     const float rh = fmaxf(fmaf(-vs[h], ies, 1.0f), 0.0f);
-    need = need || (fabsf(rh - 0.7f) < 4.0e-6f) || (fabsf(rh - 1.0e-3f) < 1.0e-3f);
+    need = need || (fabsf(rh - 0.7f) <= 4.0e-6f) || (fabsf(rh - 1.0e-3f) < 1.0e-3f);
   }
   return need;
 }
@@ -451,23 +479,22 @@ M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<
                                           typename MaskOf<V>::type& g_pos, V& gs_day,
                                           V& nan_probe) {
   typedef typename MaskOf<V>::type M;
-  M need = mnot(mand(x.ok, in_domain<V>(in, nan_probe)));
+  const V tc_d = celsius<V>(in.t_d), tc_n = celsius<V>(in.t_n);
+  M need = mnot(mand(x.ok, in_domain<V>(in, tc_d, tc_n, nan_probe)));
   const V oma = 1.0f - in.alb;
   const V a_d = vfma(in.sw_d, oma, in.lw_d);            // :225
   const V a_n = in.lw_n;                                 // :226
   const V a_nc = vfma(in.sw_n, oma, in.lw_n);            // :272 (night: sw_rad_night)
   // soil heat flux (:229-241)
   const M cond = mand(x.window, vge(in.t_d - in.t_n, splat<V>(5.0f)));
-  V g_d = vsel(cond, vfma(celsius<V>(in.t_d), 4.73f, -20.87f), splat<V>(0.0f));
-  V g_n = vsel(cond, vfma(celsius<V>(in.t_n), 4.73f, -20.87f), splat<V>(0.0f));
+  V g_d = vsel(cond, vfma(tc_d, 4.73f, -20.87f), splat<V>(0.0f));
+  V g_n = vsel(cond, vfma(tc_n, 4.73f, -20.87f), splat<V>(0.0f));
   const V lim_d = 0.39f * a_d, lim_n = 0.39f * a_n;
-  // |G| > 0.39 |A| switches G to 0.39 A (:239); within rounding of equality the decision
-  // is the double code's.  A_day > 0 gates both limits below (:245-252).
-  need = mor(need, mor(mor(vle(vabs(vabs(g_d) - vabs(lim_d)), splat<V>(1.0e-4f)),
-                           vle(vabs(vabs(g_n) - vabs(lim_n)), splat<V>(1.0e-4f))),
-                       vlt(vabs(a_d), splat<V>(1.0e-4f))));
-  g_d = vsel(vgt(vabs(g_d), vabs(lim_d)), lim_d, g_d);
-  g_n = vsel(vgt(vabs(g_n), vabs(lim_n)), lim_n, g_n);
+  // |G| > 0.39 |A| switches G to 0.39 A (:239); within kGuard of equality the decision is
+  // the double code's.  A_day > 0 gates both limits below (:245-252).
+  const V gd_d = vabs(g_d) - vabs(lim_d), gd_n = vabs(g_n) - vabs(lim_n);
+  g_d = vsel(vgt(gd_d, splat<V>(0.0f)), lim_d, g_d);
+  g_n = vsel(vgt(gd_n, splat<V>(0.0f)), lim_n, g_n);
   const M a_pos = vgt(a_d, splat<V>(0.0f));
   V r_d = a_d - g_d;                                     // A - G, day
   V r_n = a_n - g_n;
@@ -476,13 +503,16 @@ M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<
   r_n = vsel(mand(a_pos, vlt(r_n, floor_n)), floor_n, r_n);  // :248-252 (G := A_n + A_d / 2)
   const V omf = 1.0f - in.fpar;
   M unused = mask_splat<V>(false);
-  V gs_unused;
-  o.day = half_fast<V, SEM, true, HAS_RC>(in.t_d, in.vpd_d, in.fpar * a_d, omf * r_d, in.rc_d,
-                                          in.tmin, in.fpar, omf, in.lai, c, x, gate, g_pos,
-                                          need, gs_day);
-  o.night = half_fast<V, SEM, false, HAS_RC>(in.t_n, in.vpd_n, in.fpar * a_nc, omf * r_n,
+  V gs_unused, ga_d, gb_d, ga_n, gb_n;
+  o.day = half_fast<V, SEM, true, HAS_RC>(in.t_d, tc_d, in.vpd_d, in.fpar * a_d, omf * r_d,
+                                          in.rc_d, in.tmin, in.fpar, omf, in.lai, c, x, gate,
+                                          g_pos, need, gs_day, ga_d, gb_d);
+  o.night = half_fast<V, SEM, false, HAS_RC>(in.t_n, tc_n, in.vpd_n, in.fpar * a_nc, omf * r_n,
                                              in.rc_n, in.tmin, in.fpar, omf, in.lai, c, x, gate,
-                                             unused, need, gs_unused);
+                                             unused, need, gs_unused, ga_n, gb_n);
+  // every discontinuity guard in one compare: the smallest scaled distance to a switch
+  const V dist = vminabs3(vminabs3(gd_d, gd_n, a_d), vminabs3(ga_d, gb_d, ga_n), gb_n);
+  need = mor(need, vlt(dist, splat<V>(kGuard)));
   if (SEM == SEM_STATIC) {  // :380
     o.tot_day = (o.day.trans + o.day.canopy) + o.day.soil;
     o.tot_night = (o.night.trans + o.night.canopy) + o.night.soil;
@@ -568,6 +598,9 @@ M16_HD StepInV<float> to_v(const StepIn& in) {
 //                   :1258: finite result); night: lw_net_night, temp_night, vpd_night,
 //                   pressure, fpar
 // (sw_rad_night, tmin and temp_annual are not in the lists: their NaN can be masked away.)
+// A NEGATIVE temperature (the -9999 / -32768 fill values of real tiles) acts like a NaN one:
+// r_corr = (101300 / P) (T / 293.15)^1.75 is NaN for T < 0 (:292, :771) and poisons the soil
+// term of its half-day (:363, :533) and g_surf (:328).
 // nan_halves() returns bit 0 / bit 1 when the day / night total is NaN by this rule (the other
 // drivers then do not matter for that half: NaN + x = NaN).  `g_pos` is the element's gate
 // predicate g_surf > 0 (:343), which a NaN total does not prevent; it is formed from Tmin,
@@ -578,22 +611,22 @@ template <int SEM>
 M16_HD int nan_halves(const StepIn& in, const PftConstV<float>& c, bool has_rc, bool& g_pos) {
   g_pos = false;
   if (has_rc) return 0;
-  const bool n_t_d = in.t_d != in.t_d, n_vpd_d = in.vpd_d != in.vpd_d, n_p = in.p != in.p,
-             n_fpar = in.fpar != in.fpar;
+  const bool n_t_d = !(in.t_d >= 0.0f), n_t_n = !(in.t_n >= 0.0f);  // NaN or negative
+  const bool n_vpd_d = in.vpd_d != in.vpd_d, n_p = in.p != in.p, n_fpar = in.fpar != in.fpar;
   const bool n_lai = SEM == SEM_STATIC && in.lai != in.lai;
   const bool day = in.lw_d != in.lw_d || in.sw_d != in.sw_d || in.alb != in.alb || n_t_d ||
                    n_vpd_d || n_p || n_fpar || n_lai;
-  const bool night = in.lw_n != in.lw_n || in.t_n != in.t_n || in.vpd_n != in.vpd_n || n_p ||
+  const bool night = in.lw_n != in.lw_n || n_t_n || in.vpd_n != in.vpd_n || n_p ||
                      n_fpar || n_lai;
   if (!(day || night)) return 0;
   if (SEM == SEM_STATIC && !(n_t_d || n_p || n_vpd_d || in.tmin != in.tmin)) {
     if (c.ok == 0.0f) return 0;
-    const bool sane = in.t_d > 200.0f && in.t_d < 340.0f && in.p >= 3.0e4f && in.p <= 1.2e5f &&
-                      in.vpd_d >= 0.0f && in.vpd_d < 1.0e5f && fabsf(in.tmin) < 9000.0f;
+    const bool sane = in.t_d > 206.3f && in.t_d < 340.0f && in.p >= 3.0e4f && in.p <= 1.2e5f &&
+                      in.vpd_d > -1000.0f && in.vpd_d < 1.0e5f && fabsf(in.tmin) < 9000.0f;
     if (!sane) return 0;
     // g_surf = csl m_tmin m_vpd / r_corr, r_corr > 0 here (:325-328)
-    const float m_t = vsat((celsius<float>(in.tmin) - c.tmin_close) * c.inv_dtmin);
-    const float m_v = vsat((c.vpd_close - in.vpd_d) * c.inv_dvpd);
+    const float m_t = vsat(fmaf(in.tmin, c.inv_dtmin, c.tmin_bias));
+    const float m_v = vsat(fmaf(-in.vpd_d, c.inv_dvpd, c.vpd_off));
     g_pos = (c.csl * m_t) * m_v > 0.0f;
   }
   return (day ? 1 : 0) | (night ? 2 : 0);

@@ -1,486 +1,22 @@
-// K1, float32 fast path.
+// K1, float32 fast path: host-side dispatch and the small kernels around the headline one.
 //
-// forward_pipe_kernel -- the headline kernel.  Layout: (T, N) row-major structure-of-arrays.
-//   One block per SM-resident tile of 480 pixels walks a chunk of time steps two at a time.
-//   A producer warp streams the eleven per-step driver rows of the next steps into a
-//   five-stage shared-memory ring with bulk asynchronous copies (cp.async.bulk, completion
-//   on an mbarrier); fifteen consumer warps evaluate the model with the packed-FP32
-//   (FFMA2) math of mod16_fast.cuh -- the two lanes of every packed instruction are the
-//   same pixel at two consecutive time steps, so all BPLUT-derived and per-pixel constants
-//   are scalar registers -- and write ET exactly once.  Algorithmic traffic: 11 x 4 B in +
-//   4 B out = 48 B per pixel-timestep (OUT_SUM).
+// forward_pipe_kernel (mod16_forward_pipe.cuh, instantiated in mod16_forward_pipe_{static,
+//   instance}.cu) -- the headline kernel: dense (T, N) structure-of-arrays drivers streamed
+//   through a shared-memory ring by bulk asynchronous copies, packed-FP32 math.
 //
 // forward_strided_fast_kernel -- same math, one pixel-timestep at a time, for layouts the
-//   bulk copies cannot express (broadcast strides, per-pixel parameter arrays, N % 4 != 0,
-//   unaligned bases, r_corr_list).
-#include <type_traits>
-
-#include "mod16_common.cuh"
-#include "mod16_fast.cuh"
-#include "mod16_pipe.cuh"
+//   bulk copies cannot express (broadcast strides, N % 4 != 0, unaligned bases, r_corr_list).
+//
+// redo_queue_kernel / redo_sweep_kernel -- the double-precision evaluation of the elements
+//   the fast math flagged.
+#include "mod16_forward_pipe.cuh"
 
 namespace mod16 {
 
-using fast::PftConst;
-using fast::PixConst;
-using fast::StepIn;
-
-// Shared-memory copy of the BPLUT: derived float constants for the fast math and the raw
-// double table for the op-for-op fallback.
-// Column MOD16_N_PFT is an all-NaN column for land-cover codes outside 0..12.
-struct SharedLut {
-  PftConst pc[MOD16_N_PFT + 1];
-  double tab[MOD16_N_PARAMS][MOD16_N_PFT + 1];
-};
-
-template <int SEM>
-__device__ __forceinline__ void stage_lut(const ForwardArgs<float>& a, SharedLut& s) {
-  for (int i = threadIdx.x; i < MOD16_N_PARAMS * (MOD16_N_PFT + 1); i += blockDim.x) {
-    const int k = i / (MOD16_N_PFT + 1), c = i % (MOD16_N_PFT + 1);
-    s.tab[k][c] = c < MOD16_N_PFT ? a.table[k][c] : __longlong_as_double(0x7ff8000000000000LL);
-  }
-  __syncthreads();
-  if (threadIdx.x < MOD16_N_PFT + 1) {
-    double col[MOD16_N_PARAMS];
-#pragma unroll
-    for (int k = 0; k < MOD16_N_PARAMS; ++k) col[k] = s.tab[k][threadIdx.x];
-    s.pc[threadIdx.x] = fast::make_pft_const(col, SEM);
-  }
-  __syncthreads();
-}
-
-// Exact re-evaluation of ONE element that step_fast() flagged (pixel n, time step t).  Out
-// of line and self-contained (re-reads its inputs from global memory, which the fast pass
-// has just pulled through L2), so that the double-precision code costs the hot loop no
-// registers.  Returns the gate predicate of the element.
-template <int SEM, int OUT>
-__device__ __noinline__ bool fix_exact_one(const ForwardArgs<float>& a, const SharedLut& lut,
-                                           int64_t t, int64_t n) {
-  int code = 0;
-  if (a.par_mode == 1) {
-    code = (int)__ldg(a.pft + n);
-    code = code < MOD16_N_PFT ? code : MOD16_N_PFT;
-  }
-  double col[MOD16_N_PARAMS];
-  for (int k = 0; k < MOD16_N_PARAMS; ++k) col[k] = lut.tab[k][code];
-  StepIn in;
-  in.lw_d = a.drv[MOD16_D_LW_NET_DAY].at(t, n);
-  in.lw_n = a.drv[MOD16_D_LW_NET_NIGHT].at(t, n);
-  in.sw_d = a.drv[MOD16_D_SW_RAD_DAY].at(t, n);
-  in.sw_n = a.drv[MOD16_D_SW_RAD_NIGHT].at(t, n);
-  in.alb = a.drv[MOD16_D_SW_ALBEDO].at(t, n);
-  in.t_d = a.drv[MOD16_D_TEMP_DAY].at(t, n);
-  in.t_n = a.drv[MOD16_D_TEMP_NIGHT].at(t, n);
-  in.t_ann = a.drv[MOD16_D_TEMP_ANNUAL].at(t, n);
-  in.tmin = a.drv[MOD16_D_TMIN].at(t, n);
-  in.vpd_d = a.drv[MOD16_D_VPD_DAY].at(t, n);
-  in.vpd_n = a.drv[MOD16_D_VPD_NIGHT].at(t, n);
-  in.p = a.drv[MOD16_D_PRESSURE].at(t, n);
-  in.fpar = a.drv[MOD16_D_FPAR].at(t, n);
-  in.lai = a.drv[MOD16_D_LAI].at(t, n);
-  in.rc_d = 0.0f; in.rc_n = 0.0f;
-  fast::StepOut r;
-  bool g_pos;
-  fast::pixel_step_exact<SEM>(in, col, false, a.gate, r, g_pos);
-  const int64_t o = t * a.N + n;
-  if (OUT == 0) {
-    a.out[0][o] = r.tot;
-  } else if (OUT == 1) {
-    a.out[0][o] = r.tot_day;
-    a.out[1][o] = r.tot_night;
-  } else {
-    a.out[0][o] = r.day.canopy;   a.out[1][o] = r.day.soil;   a.out[2][o] = r.day.trans;
-    a.out[3][o] = r.night.canopy; a.out[4][o] = r.night.soil; a.out[5][o] = r.night.trans;
-  }
-  return g_pos;
-}
-
-// fast::nan_halves() for ONE flagged element, out of line and self-contained like
-// fix_exact_one (the hot loop keeps no inputs alive for it).
-template <int SEM>
-__device__ __noinline__ int nan_halves_one(const ForwardArgs<float>& a, const SharedLut& lut,
-                                           int64_t t, int64_t n, bool& g_pos) {
-  int code = 0;
-  if (a.par_mode == 1) {
-    code = (int)__ldg(a.pft + n);
-    code = code < MOD16_N_PFT ? code : MOD16_N_PFT;
-  }
-  StepIn in;
-  in.lw_d = a.drv[MOD16_D_LW_NET_DAY].at(t, n);
-  in.lw_n = a.drv[MOD16_D_LW_NET_NIGHT].at(t, n);
-  in.sw_d = a.drv[MOD16_D_SW_RAD_DAY].at(t, n);
-  in.sw_n = a.drv[MOD16_D_SW_RAD_NIGHT].at(t, n);
-  in.alb = a.drv[MOD16_D_SW_ALBEDO].at(t, n);
-  in.t_d = a.drv[MOD16_D_TEMP_DAY].at(t, n);
-  in.t_n = a.drv[MOD16_D_TEMP_NIGHT].at(t, n);
-  in.t_ann = 0.0f;
-  in.tmin = a.drv[MOD16_D_TMIN].at(t, n);
-  in.vpd_d = a.drv[MOD16_D_VPD_DAY].at(t, n);
-  in.vpd_n = a.drv[MOD16_D_VPD_NIGHT].at(t, n);
-  in.p = a.drv[MOD16_D_PRESSURE].at(t, n);
-  in.fpar = a.drv[MOD16_D_FPAR].at(t, n);
-  in.lai = a.drv[MOD16_D_LAI].at(t, n);
-  in.rc_d = in.rc_n = 0.0f;
-  return fast::nan_halves<SEM>(in, lut.pc[code], a.has_rc != 0, g_pos);
-}
-
-// ---- forward_pipe_kernel ------------------------------------------------------------------
-// Warp specialisation: warp 15 is the PRODUCER; for every pair of time steps its elected
-// lane waits until a stage is free, arms the stage's `full` mbarrier with the byte count
-// and issues 22 (24 with a sw_rad_night array) `cp.async.bulk` copies of 1920 B, one per
-// driver row and step.  The fifteen CONSUMER warps wait on the barrier's phase, pull their
-// inputs out of shared memory (conflict-free 32-bit LDS, the rows of step t and t + 1
-// landing in the two halves of an FFMA2 operand pair), release the stage at once (`empty`
-// mbarrier) and then evaluate and store.  The copies of the next 2 x PIPE_STAGES steps are
-// in flight while a pair of steps is evaluated: HBM latency is hidden by the copy engine
-// instead of by registers, there is no block-wide barrier, no table gather and no address
-// arithmetic in the time loop, and issuing the copies costs the consumers nothing
-// (measured alternatives: profiles/r01_pipebench.txt and DESIGN.md).
-// Elements that need the double-precision code are not evaluated in the loop -- one such
-// element would hold its warp for ~20 us and, through the ring, the whole block -- but
-// queued and evaluated afterwards, one element per thread: by redo_queue_kernel when the
-// caller supplied a workspace, else by this block after its loop.
-#ifndef M16_PIPE_WARPS
-#define M16_PIPE_WARPS 15
-#endif
-#ifndef M16_PIPE_STAGES
-#define M16_PIPE_STAGES 5
-#endif
-constexpr int PIPE_CONSUMER_WARPS = M16_PIPE_WARPS;
-constexpr int PIPE_CONSUMERS = PIPE_CONSUMER_WARPS * 32;
-constexpr int PIPE_THREADS = PIPE_CONSUMERS + 32;
-constexpr int PIPE_TILE = PIPE_CONSUMERS;  // pixels per block
-constexpr int PIPE_SUB = 2;                // time steps per stage (the two FFMA2 lanes)
-constexpr int PIPE_STAGES = M16_PIPE_STAGES;
-constexpr int PIPE_MAX_ARR = 12;
-constexpr int REDO_MARK = 0x7fc0dead;  // a NaN no arithmetic produces: "evaluate me exactly"
-constexpr int PIPE_QCAP = 512;             // deferred exact re-evaluations per block
-
-struct PipeSrc {  // per-step arrays in stage order
-  const float* ptr[PIPE_MAX_ARR];
-  int n_arr;
-  int n_stages;  // PIPE_STAGES, one fewer when a twelfth array must fit in shared memory
-};
-
-// Producer step, executed by the WHOLE producer warp so that addresses stay in uniform
-// registers and the base pointers come straight from the constant bank; one elected lane
-// arms the barrier and starts the row copies of `n_sub` time steps.  (Measured: this form
-// issues > 50 copies/us, an elected thread inside a divergent branch only 18 --
-// profiles/r01_issuebench.txt.)
-__device__ __forceinline__ void pipe_issue(const PipeSrc& src, int n_arr, int n_sub,
-                                           uint32_t dst, uint32_t bar, int64_t off,
-                                           int64_t t_stride, uint32_t row_bytes) {
-  if (elect_one()) {
-    mbar_expect_tx(bar, row_bytes * (uint32_t)(n_arr * n_sub));
-#pragma unroll
-    for (int u = 0; u < PIPE_SUB; ++u) {
-      if (u < n_sub) {
-#pragma unroll
-        for (int k = 0; k < PIPE_MAX_ARR; ++k)
-          if (k < n_arr)
-            bulk_g2s(dst + (uint32_t)(u * n_arr + k) * PIPE_TILE * (uint32_t)sizeof(float),
-                     src.ptr[k] + off + u * t_stride, row_bytes, bar);
-      }
-    }
-  }
-  __syncwarp();
-}
-
-template <int SEM, int OUT, bool SWN>
-__global__ void __launch_bounds__(PIPE_THREADS, 1)
-forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
-                    const __grid_constant__ PipeSrc src) {
-  using fast::F2;
-  using fast::M2;
-  // [stage][sub-step][array][PIPE_TILE]
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
-  __shared__ SharedLut lut;
-  __shared__ __align__(8) uint64_t full[PIPE_STAGES], empty[PIPE_STAGES];
-  __shared__ uint32_t redo_q[PIPE_QCAP];  // (step within the chunk) << 10 | consumer thread
-  __shared__ int redo_n;
-  if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
-  const int tid = threadIdx.x;
-  const int n_arr = src.n_arr;
-  const int64_t tile0 = (int64_t)blockIdx.x * PIPE_TILE;
-  const int64_t t0 = (int64_t)blockIdx.y * a.t_chunk;
-  int64_t t1 = t0 + a.t_chunk;
-  if (t1 > a.T) t1 = a.T;
-  const int nsteps = (int)(t1 - t0);
-  const int niter = (nsteps + PIPE_SUB - 1) / PIPE_SUB;  // stage uses; the last may hold 1 step
-  const int64_t left = a.N - tile0;
-  const uint32_t row_bytes = (uint32_t)((left < PIPE_TILE ? left : PIPE_TILE) * sizeof(float));
-  constexpr uint32_t ROWB = PIPE_TILE * sizeof(float);         // bytes per array row
-  const uint32_t SUBB = (uint32_t)n_arr * ROWB;                // bytes per sub-step
-  const uint32_t STAGEB = PIPE_SUB * SUBB;                     // bytes per stage
-  const int n_stages = src.n_stages;
-  const uint32_t full0 = smem_u32(&full[0]), empty0 = smem_u32(&empty[0]);
-  const uint32_t data0 = smem_u32(dyn_smem);
-  const bool producer = tid >= PIPE_CONSUMERS;
-
-  if (producer) {  // barriers, first fills (before the table staging: latency overlaps)
-    if (tid == PIPE_CONSUMERS) {
-      for (int s = 0; s < PIPE_STAGES; ++s) {
-        mbar_init(full0 + 8 * s, 1);
-        mbar_init(empty0 + 8 * s, PIPE_CONSUMER_WARPS);
-      }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      redo_n = 0;
-    }
-    __syncwarp();
-    for (int s = 0; s < n_stages && s < niter; ++s)
-      pipe_issue(src, n_arr, nsteps - s * PIPE_SUB >= PIPE_SUB ? PIPE_SUB : 1,
-                 data0 + s * STAGEB, full0 + 8 * s, (t0 + s * PIPE_SUB) * a.N + tile0, a.N,
-                 row_bytes);
-  }
-  stage_lut<SEM>(a, lut);  // (contains __syncthreads: the barriers are visible to everyone)
-
-  if (producer) {
-    int stage = 0;
-    uint32_t phase = 0;  // parity of the stage's previous use
-#pragma unroll 1
-    for (int i = n_stages; i < niter; ++i) {
-      mbar_wait(empty0 + 8 * stage, phase);  // all fifteen warps have read the stage
-      pipe_issue(src, n_arr, nsteps - i * PIPE_SUB >= PIPE_SUB ? PIPE_SUB : 1,
-                 data0 + (uint32_t)stage * STAGEB, full0 + 8 * stage,
-                 (t0 + (int64_t)i * PIPE_SUB) * a.N + tile0, a.N, row_bytes);
-      if (++stage == n_stages) { stage = 0; phase ^= 1u; }
-    }
-    return;
-  }
-
-  const int64_t n = tile0 + tid;
-  const bool live = n < a.N;
-  bool any_pos = false;
-  float gs_max = 0.0f;  // max of the gate quantity g_surf over this thread's elements (:343)
-  // per-pixel state, all scalar: BPLUT column constants, pressure terms, annual window
-  fast::PftConstV<F2> pc;
-  fast::PixConstV<F2> px;
-  {
-    int code = 0;
-    float p = 1e5f, ta = 0.f;
-    if (live) {
-      if (a.par_mode == 1) {
-        code = (int)__ldg(a.pft + n);
-        code = code < MOD16_N_PFT ? code : MOD16_N_PFT;  // out of range: the all-NaN column
-      }
-      p = a.drv[MOD16_D_PRESSURE].at(0, n);   // per pixel or scalar (checked on the host)
-      ta = a.drv[MOD16_D_TEMP_ANNUAL].at(0, n);
-    }
-    PftConst c1 = lut.pc[code];
-    // threads past the last pixel run the loop on whatever the stage holds (they take part
-    // in the barriers); csl = 0 keeps them out of the gate, `live` out of stores and queue
-    if (!live) c1.csl = 0.0f;
-    const PixConst x1 = fast::make_pix_const(p, ta, c1, SEM);
-    pc = fast::pair_pft(c1, c1);
-    px = fast::pair_pix(x1, x1);
-  }
-  const float swn_scalar = a.drv[MOD16_D_SW_RAD_NIGHT].scalar;
-  const int gate = a.gate;
-  constexpr int n_out = OUT == 0 ? 1 : (OUT == 1 ? 2 : 6);
-  const uint32_t my0 = data0 + (uint32_t)tid * 4u;  // this thread's pixel within a row
-  const int64_t t_stride = a.N;
-  int64_t off = t0 * t_stride + n;                  // running output offset
-  const bool warp_lead = (tid & 31) == 0;
-  int stage = 0;
-  uint32_t phase = 0;
-
-  // One use of a stage.  TWO: both time steps of the pair exist (always, except for the last
-  // use of an odd chunk, which is peeled off the loop below so that the loop carries no
-  // tail handling).  Stage order == PipeSrc order (see launch_pipe).  The inputs are pulled
-  // into registers at once so that the stage can be re-filled while the steps are
-  // evaluated.  Lane x of every pair is step t, lane y is step t + 1 (step t again when the
-  // chunk is odd).
-  auto consume = [&](auto two_tag, const int i) {
-    constexpr bool TWO = decltype(two_tag)::value;
-    mbar_wait(full0 + 8 * stage, phase);
-    fast::StepInV<F2> in;
-    {
-      const uint32_t s0 = my0 + (uint32_t)stage * STAGEB;
-      const uint32_t s1 = TWO ? s0 + SUBB : s0;
-#define M16_IN(k) F2{lds1(s0 + (k) * ROWB), lds1(s1 + (k) * ROWB)}
-      in.lw_d = M16_IN(0);  in.lw_n = M16_IN(1);  in.sw_d = M16_IN(2);  in.alb = M16_IN(3);
-      in.t_d = M16_IN(4);   in.t_n = M16_IN(5);   in.tmin = M16_IN(6);  in.vpd_d = M16_IN(7);
-      in.vpd_n = M16_IN(8); in.fpar = M16_IN(9);  in.lai = M16_IN(10);
-      if (SWN) in.sw_n = M16_IN(11);
-      else in.sw_n = F2{swn_scalar, swn_scalar};
-#undef M16_IN
-      in.rc_d = F2{0.f, 0.f}; in.rc_n = F2{0.f, 0.f};
-    }
-    __syncwarp();
-    if (warp_lead) mbar_arrive(empty0 + 8 * stage);  // this warp has read the stage
-    fast::StepOutV<F2> r;
-    M2 g_pos;
-    F2 gs, nan_probe;
-    M2 need = fast::step_fast<F2, SEM, false>(in, pc, px, gate, r, g_pos, gs, nan_probe);
-    need.x = need.x && live;
-    need.y = need.y && live && TWO;
-    F2 res[6];
-    if (OUT == 0) {
-      res[0] = r.tot;
-    } else if (OUT == 1) {
-      res[0] = r.tot_day; res[1] = r.tot_night;
-    } else {
-      res[0] = r.day.canopy;   res[1] = r.day.soil;   res[2] = r.day.trans;
-      res[3] = r.night.canopy; res[4] = r.night.soil; res[5] = r.night.trans;
-    }
-    if (!(need.x || need.y)) {
-      // (a NaN gate quantity -- garbage read by a thread past the last pixel -- is dropped)
-      gs_max = fmaxf(gs_max, fmaxf(gs.x, gs.y));
-      if (live) {
-#pragma unroll
-        for (int k = 0; k < n_out; ++k) {
-          st_stream1(a.out[k] + off, res[k].x);
-          if (TWO) st_stream1(a.out[k] + off + t_stride, res[k].y);
-        }
-      }
-    } else {  // rare: queue for the double-precision pass after the loop
-      any_pos |= (g_pos.x && !need.x) || (g_pos.y && !need.y);
-#pragma unroll
-      for (int k = 0; k < n_out; ++k) {
-        if (!need.x) st_stream1(a.out[k] + off, res[k].x);
-        if (TWO && !need.y) st_stream1(a.out[k] + off + t_stride, res[k].y);
-      }
-#pragma unroll
-      for (int j = 0; j < PIPE_SUB; ++j) {
-        if (j == 0 ? need.x : need.y) {
-          const int64_t t = t0 + i * PIPE_SUB + j;
-          if (OUT != 2) {  // masked (NaN) drivers: the total is NaN without the double code
-            // The probe of step_fast (or the pixel's pressure) is NaN exactly when a driver of
-            // the masked-driver rule is.  Static `_et` total: NaN follows at once, decided
-            // from registers -- a masked pixel is masked at every step, its warp must not
-            // stall on re-reads -- with the hot path's own gate predicate (g_surf > 0 from
-            // Tmin, VPD, T, P).  Other modes: the out-of-line rule says which halves.
-            const float probe = j == 0 ? nan_probe.x : nan_probe.y;
-            if (probe != probe || px.pa.x != px.pa.x) {
-              bool gp = j == 0 ? g_pos.x : g_pos.y;
-              int h = 3;
-              if (!(OUT == 0 && SEM == SEM_STATIC && pc.ok.x != 0.0f))
-                h = nan_halves_one<SEM>(a, lut, t, n, gp);
-              if (OUT == 0 ? h != 0 : h == 3) {
-                const float qnan = __int_as_float(0x7fc00000);
-                st_stream1(a.out[0] + off + j * t_stride, qnan);
-                if (OUT == 1) st_stream1(a.out[1] + off + j * t_stride, qnan);
-                any_pos |= gp;
-                continue;
-              }
-            }
-          }
-          bool queued = false;
-          if (a.redo_cap > 0) {  // global queue, evaluated by redo_queue_kernel
-            const unsigned long long slot = atomicAdd(a.redo_ws, 1ULL);
-            queued = slot < (unsigned long long)a.redo_cap;
-            if (queued) a.redo_ws[1 + slot] = (unsigned long long)(t * a.N + n);
-          } else {               // no workspace: block-local queue, evaluated after the loop
-            const int slot = atomicAdd(&redo_n, 1);
-            queued = slot < PIPE_QCAP;
-            if (queued) redo_q[slot] = (uint32_t)(i * PIPE_SUB + j) << 10 | (uint32_t)tid;
-          }
-          if (!queued) {
-            if (a.redo_cap > 0) {
-              // global queue full (fill-heavy data): leave a marker in the first output; the
-              // sweep kernel finds and evaluates it (the counter past the capacity tells it
-              // to run).  One in-place double evaluation here would hold the whole block.
-              st_stream1(a.out[0] + off + j * t_stride, __int_as_float(REDO_MARK));
-            } else {
-              any_pos |= fix_exact_one<SEM, OUT>(a, lut, t, n);  // no workspace at all
-            }
-          }
-        }
-      }
-    }
-    off += PIPE_SUB * t_stride;
-    if (++stage == n_stages) { stage = 0; phase ^= 1u; }
-  };
-  const int nfull = nsteps / PIPE_SUB;
-#pragma unroll 1
-  for (int i = 0; i < nfull; ++i) consume(std::true_type(), i);
-  if (nsteps & 1) consume(std::false_type(), nfull);
-  any_pos |= gs_max > 0.0f;
-  // the block-local deferred pass: consumers only (named barrier 1), one element each
-  if (a.redo_cap == 0) {
-    asm volatile("bar.sync 1, %0;" ::"n"(PIPE_CONSUMERS) : "memory");
-    const int total = redo_n < PIPE_QCAP ? redo_n : PIPE_QCAP;
-    for (int e = tid; e < total; e += PIPE_CONSUMERS) {
-      const uint32_t q = redo_q[e];
-      any_pos |= fix_exact_one<SEM, OUT>(a, lut, t0 + (int64_t)(q >> 10), tile0 + (q & 1023u));
-    }
-  }
-  if (a.track_gate) {
-    if (__any_sync(0xffffffffu, any_pos) && (threadIdx.x & 31) == 0) *a.gate_flag = 1;
-  }
-}
-
-// The BPLUT column of pixel n in double, for any parameter source.
-__device__ __forceinline__ void load_column(const ForwardArgs<float>& a, int64_t n,
-                                            double col[MOD16_N_PARAMS]) {
-  if (a.par_mode == 2) {
-#pragma unroll
-    for (int k = 0; k < MOD16_N_PARAMS; ++k)
-      col[k] = (double)__ldg(a.par_arr[k] + n * a.par_stride[k]);
-  } else {
-    int code = 0;
-    if (a.par_mode == 1) code = (int)__ldg(a.pft + n);
-    // numpy fancy indexing would raise on a code > 12; the kernels yield NaN parameters
-#pragma unroll
-    for (int k = 0; k < MOD16_N_PARAMS; ++k)
-      col[k] = code < MOD16_N_PFT ? a.table[k][code] : __longlong_as_double(0x7ff8000000000000LL);
-  }
-}
-
-__device__ __forceinline__ StepIn load_step(const ForwardArgs<float>& a, int64_t t, int64_t n) {
-  StepIn in;
-  in.lw_d = a.drv[MOD16_D_LW_NET_DAY].at(t, n);
-  in.lw_n = a.drv[MOD16_D_LW_NET_NIGHT].at(t, n);
-  in.sw_d = a.drv[MOD16_D_SW_RAD_DAY].at(t, n);
-  in.sw_n = a.drv[MOD16_D_SW_RAD_NIGHT].at(t, n);
-  in.alb = a.drv[MOD16_D_SW_ALBEDO].at(t, n);
-  in.t_d = a.drv[MOD16_D_TEMP_DAY].at(t, n);
-  in.t_n = a.drv[MOD16_D_TEMP_NIGHT].at(t, n);
-  in.t_ann = a.drv[MOD16_D_TEMP_ANNUAL].at(t, n);
-  in.tmin = a.drv[MOD16_D_TMIN].at(t, n);
-  in.vpd_d = a.drv[MOD16_D_VPD_DAY].at(t, n);
-  in.vpd_n = a.drv[MOD16_D_VPD_NIGHT].at(t, n);
-  in.p = a.drv[MOD16_D_PRESSURE].at(t, n);
-  in.fpar = a.drv[MOD16_D_FPAR].at(t, n);
-  in.lai = a.drv[MOD16_D_LAI].at(t, n);
-  in.rc_d = a.has_rc ? a.rc[0].at(t, n) : 0.0f;
-  in.rc_n = a.has_rc ? a.rc[1].at(t, n) : 0.0f;
-  return in;
-}
-
-// The rare element of the strided kernel that step_fast() flagged: masked-driver rule first,
-// else the op-for-op double code.  Out of line and self-contained (re-reads its inputs), so
-// that the double code costs the loop no registers.  Writes the outputs; returns g_surf > 0.
-template <int SEM, int OUT>
-__device__ __noinline__ bool strided_rare_one(const ForwardArgs<float>& a, int64_t t, int64_t n) {
-  double col[MOD16_N_PARAMS];
-  load_column(a, n, col);
-  const StepIn in = load_step(a, t, n);
-  const int64_t o = t * a.N + n;
-  bool g_pos = false;
-  if (OUT != 2) {
-    const PftConst pc = fast::make_pft_const(col, SEM);
-    const int h = fast::nan_halves<SEM>(in, pc, a.has_rc != 0, g_pos);
-    if (OUT == 0 ? h != 0 : h == 3) {
-      const float qnan = __int_as_float(0x7fc00000);
-      a.out[0][o] = qnan;
-      if (OUT == 1) a.out[1][o] = qnan;
-      return g_pos;
-    }
-  }
-  fast::StepOut r;
-  fast::pixel_step_exact<SEM>(in, col, a.has_rc != 0, a.gate, r, g_pos);
-  if (OUT == 0) {
-    a.out[0][o] = r.tot;
-  } else if (OUT == 1) {
-    a.out[0][o] = r.tot_day;
-    a.out[1][o] = r.tot_night;
-  } else {
-    a.out[0][o] = r.day.canopy;   a.out[1][o] = r.day.soil;   a.out[2][o] = r.day.trans;
-    a.out[3][o] = r.night.canopy; a.out[4][o] = r.night.soil; a.out[5][o] = r.night.trans;
-  }
-  return g_pos;
-}
+int launch_pipe_static(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode, int extra,
+                       dim3 grid, cudaStream_t st);
+int launch_pipe_instance(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode,
+                         int extra, dim3 grid, cudaStream_t st);
 
 template <int SEM, int OUT>
 __global__ void __launch_bounds__(256, 4)
@@ -512,7 +48,7 @@ forward_strided_fast_kernel(const __grid_constant__ ForwardArgs<float> a) {
       const bool need = has_rc ? fast::step_fast<float, SEM, true>(v, pc, px, a.gate, r, g_pos)
                                : fast::step_fast<float, SEM, false>(v, pc, px, a.gate, r, g_pos);
       if (need) {
-        any_pos |= strided_rare_one<SEM, OUT>(a, t, n);
+        any_pos |= rare_one<SEM, OUT>(a, t, n, false) > 0;
       } else {
         any_pos |= g_pos;
         const int64_t o = t * a.N + n;
@@ -537,17 +73,15 @@ forward_strided_fast_kernel(const __grid_constant__ ForwardArgs<float> a) {
 template <int SEM, int OUT>
 __global__ void __launch_bounds__(128)
 redo_queue_kernel(const __grid_constant__ ForwardArgs<float> a) {
-  __shared__ SharedLut lut;
   if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
   unsigned long long cnt = a.redo_ws[0];
   if (cnt == 0) return;
   if (cnt > (unsigned long long)a.redo_cap) cnt = (unsigned long long)a.redo_cap;
-  stage_lut<SEM>(a, lut);
   bool any_pos = false;
   for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt;
        e += (unsigned long long)gridDim.x * blockDim.x) {
     const long long idx = (long long)a.redo_ws[1 + e];
-    any_pos |= fix_exact_one<SEM, OUT>(a, lut, idx / a.N, idx % a.N);
+    any_pos |= fix_exact_one<SEM, OUT>(a, idx / a.N, idx % a.N);
   }
   if (a.track_gate) {
     if (__any_sync(0xffffffffu, any_pos) && (threadIdx.x & 31) == 0) *a.gate_flag = 1;
@@ -565,12 +99,10 @@ constexpr int SWEEP_CHUNK = SWEEP_THREADS * 16;
 template <int SEM, int OUT>
 __global__ void __launch_bounds__(SWEEP_THREADS)
 redo_sweep_kernel(const __grid_constant__ ForwardArgs<float> a) {
-  __shared__ SharedLut lut;
   __shared__ long long found[SWEEP_CHUNK];
   __shared__ int n_found;
   if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
   if (a.redo_ws[0] <= (unsigned long long)a.redo_cap) return;
-  stage_lut<SEM>(a, lut);
   bool any_pos = false;
   const long long total = (long long)a.T * a.N;
   for (long long base = (long long)blockIdx.x * SWEEP_CHUNK; base < total;
@@ -586,7 +118,7 @@ redo_sweep_kernel(const __grid_constant__ ForwardArgs<float> a) {
     __syncthreads();
     for (int k = threadIdx.x; k < n_found; k += SWEEP_THREADS) {
       const long long e = found[k];
-      any_pos |= fix_exact_one<SEM, OUT>(a, lut, e / a.N, e % a.N);
+      any_pos |= fix_exact_one<SEM, OUT>(a, e / a.N, e % a.N);
     }
     __syncthreads();
   }
@@ -597,68 +129,64 @@ redo_sweep_kernel(const __grid_constant__ ForwardArgs<float> a) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static bool dense_tn(const Arr<float>& d, int64_t T, int64_t N) {
+  return d.ptr && d.ns == 1 && aligned16(d.ptr) && (T == 1 || d.ts == N);
+}
+
 // The pipelined kernel needs: N % 4 == 0 and 16-byte aligned bases (every bulk copy is a
 // multiple of 16 bytes at a 16-byte aligned address); the eleven per-step drivers dense
-// (T, N); sw_rad_night a scalar or dense; pressure / temp_annual per pixel (or scalar);
-// parameters from the table (uniform or gathered by land cover); no r_corr_list.
-static bool pipe_ok(const ForwardArgs<float>& a) {
-  if (a.N % 4 != 0 || a.has_rc || a.par_mode == 2) return false;
+// (T, N); sw_rad_night a scalar or dense; pressure and temp_annual both per pixel / scalar,
+// or both dense (T, N) (the calibration's annual means, mod16/calibration.py:556-560);
+// parameters from the table (uniform or gathered by land cover) or per-pixel arrays (the
+// reference callers' `params[pft_map].reshape((1, N))`); no r_corr_list.
+// Returns the EXTRA variant (mod16_forward_pipe.cuh), or -1.
+static int pipe_variant(const ForwardArgs<float>& a, uint32_t flags) {
+  if (a.N % 4 != 0 || a.has_rc) return -1;
   static const int per_step[] = {
       MOD16_D_LW_NET_DAY, MOD16_D_LW_NET_NIGHT, MOD16_D_SW_RAD_DAY, MOD16_D_SW_ALBEDO,
       MOD16_D_TEMP_DAY,   MOD16_D_TEMP_NIGHT,   MOD16_D_TMIN,       MOD16_D_VPD_DAY,
       MOD16_D_VPD_NIGHT,  MOD16_D_FPAR,         MOD16_D_LAI};
-  for (int k : per_step) {
-    const Arr<float>& d = a.drv[k];
-    if (!d.ptr || d.ns != 1 || !aligned16(d.ptr)) return false;
-    if (a.T > 1 && d.ts != a.N) return false;
-  }
+  for (int k : per_step)
+    if (!dense_tn(a.drv[k], a.T, a.N)) return -1;
+  int extra = 0;
   const Arr<float>& sn = a.drv[MOD16_D_SW_RAD_NIGHT];
-  if (sn.ptr && (sn.ns != 1 || !aligned16(sn.ptr) || (a.T > 1 && sn.ts != a.N))) return false;
-  for (int k : {MOD16_D_PRESSURE, MOD16_D_TEMP_ANNUAL}) {
-    const Arr<float>& d = a.drv[k];
-    if (d.ptr && (d.ts != 0 || d.ns != 1)) return false;
+  if (sn.ptr) {
+    if (!dense_tn(sn, a.T, a.N)) return -1;
+    extra |= 1;
   }
-  return true;
-}
-
-template <int SEM, int OUT, bool SWN>
-static int launch_pipe_swn(const ForwardArgs<float>& a, const PipeSrc& src, dim3 grid,
-                           size_t smem, cudaStream_t st) {
-  // (the attribute is per function AND per device: set before every launch, it is cheap)
-  M16_CUDA_CHECK(cudaFuncSetAttribute(
-      forward_pipe_kernel<SEM, OUT, SWN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-      PIPE_STAGES * PIPE_SUB * (PIPE_MAX_ARR - 1) * PIPE_TILE * (int)sizeof(float)));
-  if (a.redo_cap > 0) M16_CUDA_CHECK(cudaMemsetAsync(a.redo_ws, 0, 8, st));
-  forward_pipe_kernel<SEM, OUT, SWN><<<grid, PIPE_THREADS, smem, st>>>(a, src);
-  M16_CUDA_CHECK(cudaGetLastError());
-  if (a.redo_cap > 0) {
-    redo_queue_kernel<SEM, OUT><<<148 * 4, 128, 0, st>>>(a);  // 126 registers: 4 blocks per SM
-    M16_CUDA_CHECK(cudaGetLastError());
-    redo_sweep_kernel<SEM, OUT><<<148 * 4, SWEEP_THREADS, 0, st>>>(a);
-    M16_CUDA_CHECK(cudaGetLastError());
+  const Arr<float>& pr = a.drv[MOD16_D_PRESSURE];
+  const Arr<float>& ta = a.drv[MOD16_D_TEMP_ANNUAL];
+  const bool pr_pix = !pr.ptr || (pr.ts == 0 && pr.ns == 1) || (pr.ts == 0 && pr.ns == 0);
+  const bool ta_pix = !ta.ptr || (ta.ts == 0 && ta.ns == 1) || (ta.ts == 0 && ta.ns == 0);
+  if (!(pr_pix && ta_pix)) {
+    // time-varying: both streamed (T > 1 here: a T == 1 array counts as per pixel)
+    if (a.T == 1 || !dense_tn(pr, a.T, a.N) || !dense_tn(ta, a.T, a.N)) return -1;
+    extra |= 2;
   }
-  return MOD16_OK;
-}
-
-template <int SEM, int OUT>
-static int launch_pipe_one(const ForwardArgs<float>& a, const PipeSrc& src, dim3 grid,
-                           size_t smem, cudaStream_t st) {
-  // (a dense sw_rad_night array is a twelfth stream; every reference caller passes 0)
-  if (src.n_arr == PIPE_MAX_ARR) return launch_pipe_swn<SEM, OUT, true>(a, src, grid, smem, st);
-  return launch_pipe_swn<SEM, OUT, false>(a, src, grid, smem, st);
+  const uint32_t om = flags & MOD16_OUT_MASK;
+  const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1 : 2);
+  if (!pipe_has_variant(out_mode, extra)) return -1;
+  return extra;
 }
 
 // Grid of the pipelined kernel: one block per 480-pixel tile and time chunk; the chunk is
 // as long as possible (the per-block set-up is amortised over it) while the grid still
 // holds several waves of 148 SMs x 1 resident block.
-static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
+static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStream_t st) {
   static const int order[] = {
       MOD16_D_LW_NET_DAY, MOD16_D_LW_NET_NIGHT, MOD16_D_SW_RAD_DAY, MOD16_D_SW_ALBEDO,
       MOD16_D_TEMP_DAY,   MOD16_D_TEMP_NIGHT,   MOD16_D_TMIN,       MOD16_D_VPD_DAY,
-      MOD16_D_VPD_NIGHT,  MOD16_D_FPAR,         MOD16_D_LAI,        MOD16_D_SW_RAD_NIGHT};
+      MOD16_D_VPD_NIGHT,  MOD16_D_FPAR,         MOD16_D_LAI};
   PipeSrc src;
-  src.n_arr = a.drv[MOD16_D_SW_RAD_NIGHT].ptr ? PIPE_MAX_ARR : PIPE_MAX_ARR - 1;
-  for (int k = 0; k < PIPE_MAX_ARR; ++k) src.ptr[k] = k < src.n_arr ? a.drv[order[k]].ptr : nullptr;
+  for (int k = 0; k < PIPE_MAX_ARR; ++k) { src.ptr[k] = nullptr; src.ts[k] = 0; }
+  int n_arr = 0;
+  for (int k = 0; k < 11; ++k) src.ptr[n_arr++] = a.drv[order[k]].ptr;
+  if (extra & 1) src.ptr[n_arr++] = a.drv[MOD16_D_SW_RAD_NIGHT].ptr;
+  if (extra & 2) {
+    src.ptr[n_arr++] = a.drv[MOD16_D_TEMP_ANNUAL].ptr;
+    src.ptr[n_arr++] = a.drv[MOD16_D_PRESSURE].ptr;
+  }
+  for (int k = 0; k < n_arr; ++k) src.ts[k] = a.N;
   const int64_t bx = (a.N + PIPE_TILE - 1) / PIPE_TILE;
   if (bx > 2147483647LL) return MOD16_ERR_SHAPE;
   int64_t want_rows = (148 * 6 + bx - 1) / bx;
@@ -670,20 +198,33 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
   while (by > 65535) { chunk *= 2; by = (a.T + chunk - 1) / chunk; }
   a.t_chunk = (int)chunk;
   dim3 grid((unsigned)bx, (unsigned)by);
-  src.n_stages = src.n_arr == PIPE_MAX_ARR ? PIPE_STAGES - 1 : PIPE_STAGES;
-  const size_t smem = (size_t)src.n_stages * PIPE_SUB * src.n_arr * PIPE_TILE * sizeof(float);
   const uint32_t om = flags & MOD16_OUT_MASK;
+  const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1 : 2);
   const bool is_static = (flags & MOD16_SEM_MASK) == MOD16_SEM_STATIC;
-#define M16_PIPE(S, O) return launch_pipe_one<S, O>(a, src, grid, smem, st)
-  if (is_static) {
-    if (om == MOD16_OUT_SUM) M16_PIPE(SEM_STATIC, 0);
-    if (om == MOD16_OUT_DAY_NIGHT) M16_PIPE(SEM_STATIC, 1);
-    M16_PIPE(SEM_STATIC, 2);
+  if (a.redo_cap > 0) M16_CUDA_CHECK(cudaMemsetAsync(a.redo_ws, 0, 8, st));
+  const int rc = is_static ? launch_pipe_static(a, src, out_mode, extra, grid, st)
+                           : launch_pipe_instance(a, src, out_mode, extra, grid, st);
+  if (rc != MOD16_OK) return rc;
+  if (a.redo_cap > 0) {
+#define M16_REDO(S, O)                                                                  \
+  do {                                                                                  \
+    redo_queue_kernel<S, O><<<148 * 4, 128, 0, st>>>(a);                                \
+    M16_CUDA_CHECK(cudaGetLastError());                                                 \
+    redo_sweep_kernel<S, O><<<148 * 4, SWEEP_THREADS, 0, st>>>(a);                      \
+    M16_CUDA_CHECK(cudaGetLastError());                                                 \
+  } while (0)
+    if (is_static) {
+      if (out_mode == 0) M16_REDO(SEM_STATIC, 0);
+      else if (out_mode == 1) M16_REDO(SEM_STATIC, 1);
+      else M16_REDO(SEM_STATIC, 2);
+    } else {
+      if (out_mode == 0) M16_REDO(SEM_INSTANCE, 0);
+      else if (out_mode == 1) M16_REDO(SEM_INSTANCE, 1);
+      else M16_REDO(SEM_INSTANCE, 2);
+    }
+#undef M16_REDO
   }
-  if (om == MOD16_OUT_SUM) M16_PIPE(SEM_INSTANCE, 0);
-  if (om == MOD16_OUT_DAY_NIGHT) M16_PIPE(SEM_INSTANCE, 1);
-  M16_PIPE(SEM_INSTANCE, 2);
-#undef M16_PIPE
+  return MOD16_OK;
 }
 
 template <int SEM>
@@ -698,7 +239,10 @@ static int launch_strided_sem(const ForwardArgs<float>& a, uint32_t om, dim3 gri
 
 int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
   if (a.T == 0 || a.N == 0) return MOD16_OK;
-  if (!(flags & MOD16_FORCE_GENERIC) && pipe_ok(a)) return launch_pipe(a, flags, st);
+  if (!(flags & MOD16_FORCE_GENERIC)) {
+    const int extra = pipe_variant(a, flags);
+    if (extra >= 0) return launch_pipe(a, flags, extra, st);
+  }
   const int threads = 256;
   const int64_t bx = (a.N + threads - 1) / threads;
   if (bx > 2147483647LL) return MOD16_ERR_SHAPE;

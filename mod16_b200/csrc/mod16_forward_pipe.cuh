@@ -1,0 +1,390 @@
+// K1, float32 fast path: forward_pipe_kernel -- the headline kernel.
+//
+// Layout: (T, N) row-major structure-of-arrays.  One block per SM-resident tile of 480
+// pixels walks a chunk of time steps two at a time.  A producer warp streams the per-step
+// driver rows of the next steps into a shared-memory ring with bulk asynchronous copies
+// (cp.async.bulk, completion on an mbarrier; SASS UBLKCP); fifteen consumer warps evaluate
+// the model with the packed-FP32 (FFMA2) math of mod16_fast.cuh -- the two lanes of every
+// packed instruction are the same pixel at two consecutive time steps, so all
+// BPLUT-derived and per-pixel constants are scalar registers -- and write ET exactly once.
+// Algorithmic traffic: 11 x 4 B in + 4 B out = 48 B per pixel-timestep (OUT_SUM).
+//
+// Warp specialisation: warp 15 is the PRODUCER; for every pair of time steps it waits until
+// a stage is free, arms the stage's `full` mbarrier with the byte count and issues one
+// `cp.async.bulk` of 1920 B per driver row and step.  The fifteen CONSUMER warps wait on
+// the barrier's phase, pull their inputs out of shared memory (conflict-free 32-bit LDS,
+// the rows of step t and t + 1 landing in the two halves of an FFMA2 operand pair), release
+// the stage at once (`empty` mbarrier) and then evaluate and store.  The copies of the next
+// 2 x stages steps are in flight while a pair of steps is evaluated: HBM latency is hidden
+// by the copy engine instead of by registers, there is no block-wide barrier, no table
+// gather and no address arithmetic in the time loop.
+//
+// The set of streamed arrays is a template parameter (EXTRA), so every shared-memory offset
+// of the loop is an immediate:
+//   EXTRA 0: the eleven per-step drivers                                     (5 stages)
+//   EXTRA 1: + sw_rad_night as a dense array (every reference caller passes 0) (4 stages)
+//   EXTRA 2: + temp_annual and pressure varying in time -- the (T x N) annual means of
+//            mod16/calibration.py:556-560; the per-pixel terms are then rebuilt per step
+//   EXTRA 3: all fourteen
+// Parameters come from the BPLUT (one column, or gathered by land cover) or from per-pixel
+// arrays -- the `params_dict[key][pft_map].reshape((1, N))` form of the reference's own
+// callers (notebooks/MOD16_Forward_Run_example.ipynb) --: they are time-invariant, so the
+// block prologue turns either into the same scalar registers.
+//
+// Elements that need the double-precision code are not evaluated in the loop -- one such
+// element would hold its warp for ~20 us and, through the ring, the whole block -- but
+// queued and evaluated afterwards, one element per thread: by redo_queue_kernel when the
+// caller supplied a workspace, else by this block after its loop.
+#pragma once
+#include <type_traits>
+
+#include "mod16_pipe.cuh"
+#include "mod16_rare.cuh"
+
+namespace mod16 {
+
+#ifndef M16_PIPE_WARPS
+#define M16_PIPE_WARPS 15
+#endif
+constexpr int PIPE_CONSUMER_WARPS = M16_PIPE_WARPS;
+constexpr int PIPE_CONSUMERS = PIPE_CONSUMER_WARPS * 32;
+constexpr int PIPE_THREADS = PIPE_CONSUMERS + 32;
+constexpr int PIPE_TILE = PIPE_CONSUMERS;  // pixels per block
+constexpr int PIPE_SUB = 2;                // time steps per stage (the two FFMA2 lanes)
+constexpr int PIPE_MAX_ARR = 14;
+constexpr int PIPE_MAX_STAGES = 5;
+constexpr int REDO_MARK = 0x7fc0dead;  // a NaN no arithmetic produces: "evaluate me exactly"
+constexpr int PIPE_QCAP = 512;             // deferred exact re-evaluations per block
+constexpr uint32_t PIPE_ROWB = PIPE_TILE * sizeof(float);  // bytes per array row
+
+__host__ __device__ constexpr int pipe_n_arr(int extra) {
+  return 11 + ((extra & 1) ? 1 : 0) + ((extra & 2) ? 2 : 0);
+}
+// as many stages as fit into 227 KB of shared memory next to ~6 KB of static data
+__host__ __device__ constexpr int pipe_n_stages(int extra) {
+  return pipe_n_arr(extra) == 11 ? 5 : 4;
+}
+// stage slot of an optional array (the first eleven are fixed, see launch_pipe)
+__host__ __device__ constexpr int pipe_slot_swn(int extra) { return 11; }
+__host__ __device__ constexpr int pipe_slot_tann(int extra) { return (extra & 1) ? 12 : 11; }
+__host__ __device__ constexpr int pipe_slot_p(int extra) { return pipe_slot_tann(extra) + 1; }
+
+struct PipeSrc {  // streamed arrays in stage order: base pointer and elements per time step
+  const float* ptr[PIPE_MAX_ARR];
+  int64_t ts[PIPE_MAX_ARR];
+};
+
+// Producer step, executed by the WHOLE producer warp so that addresses stay in uniform
+// registers and the base pointers come straight from the constant bank; one elected lane
+// arms the barrier and starts the row copies of `n_sub` time steps.  (Measured: this form
+// issues > 50 copies/us, an elected thread inside a divergent branch only 18 --
+// profiles/r01_issuebench.txt.)
+template <int NARR>
+__device__ __forceinline__ void pipe_issue(const PipeSrc& src, int n_sub, uint32_t dst,
+                                           uint32_t bar, int64_t t, int64_t tile0,
+                                           uint32_t row_bytes) {
+  if (elect_one()) {
+    mbar_expect_tx(bar, row_bytes * (uint32_t)(NARR * n_sub));
+#pragma unroll
+    for (int u = 0; u < PIPE_SUB; ++u) {
+      if (u < n_sub) {
+#pragma unroll
+        for (int k = 0; k < NARR; ++k)
+          bulk_g2s(dst + (uint32_t)(u * NARR + k) * PIPE_ROWB,
+                   src.ptr[k] + (t + u) * src.ts[k] + tile0, row_bytes, bar);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// fast::nan_halves() for ONE flagged element of the pipelined kernel, out of line and
+// self-contained (the hot loop keeps no inputs alive for it); the six BPLUT-derived
+// constants the rule reads are the thread's own registers.
+template <int SEM>
+__device__ __noinline__ int nan_halves_one(const ForwardArgs<float>& a, int64_t t, int64_t n,
+                                           float ok, float csl, float inv_dtmin,
+                                           float tmin_bias, float vpd_off, float inv_dvpd,
+                                           bool& g_pos) {
+  StepIn in = load_step(a, t, n);
+  in.t_ann = 0.0f;
+  fast::PftConstV<float> c;
+  c.ok = ok; c.csl = csl; c.inv_dtmin = inv_dtmin; c.tmin_bias = tmin_bias;
+  c.vpd_off = vpd_off; c.inv_dvpd = inv_dvpd;
+  return fast::nan_halves<SEM>(in, c, a.has_rc != 0, g_pos);
+}
+
+template <int SEM, int OUT, int EXTRA>
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
+                    const __grid_constant__ PipeSrc src) {
+  using fast::F2;
+  using fast::M2;
+  constexpr int NARR = pipe_n_arr(EXTRA);
+  constexpr int NST = pipe_n_stages(EXTRA);
+  constexpr bool SWN = (EXTRA & 1) != 0;   // sw_rad_night streamed
+  constexpr bool PXT = (EXTRA & 2) != 0;   // temp_annual / pressure streamed
+  constexpr uint32_t SUBB = NARR * PIPE_ROWB;    // bytes per sub-step
+  constexpr uint32_t STAGEB = PIPE_SUB * SUBB;   // bytes per stage
+  // [stage][sub-step][array][PIPE_TILE]
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ SharedLut lut;
+  __shared__ __align__(8) uint64_t full[PIPE_MAX_STAGES], empty[PIPE_MAX_STAGES];
+  __shared__ uint32_t redo_q[PIPE_QCAP];  // (step within the chunk) << 10 | consumer thread
+  __shared__ int redo_n;
+  if (a.skip_if_flag && *((volatile int*)a.gate_flag) != 0) return;
+  const int tid = threadIdx.x;
+  const int64_t tile0 = (int64_t)blockIdx.x * PIPE_TILE;
+  const int64_t t0 = (int64_t)blockIdx.y * a.t_chunk;
+  int64_t t1 = t0 + a.t_chunk;
+  if (t1 > a.T) t1 = a.T;
+  const int nsteps = (int)(t1 - t0);
+  const int niter = (nsteps + PIPE_SUB - 1) / PIPE_SUB;  // stage uses; the last may hold 1 step
+  const int64_t left = a.N - tile0;
+  const uint32_t row_bytes = (uint32_t)((left < PIPE_TILE ? left : PIPE_TILE) * sizeof(float));
+  const uint32_t full0 = smem_u32(&full[0]), empty0 = smem_u32(&empty[0]);
+  const uint32_t data0 = smem_u32(dyn_smem);
+  const bool producer = tid >= PIPE_CONSUMERS;
+
+  if (producer) {  // barriers, first fills (before the table staging: latency overlaps)
+    if (tid == PIPE_CONSUMERS) {
+      for (int s = 0; s < NST; ++s) {
+        mbar_init(full0 + 8 * s, 1);
+        mbar_init(empty0 + 8 * s, PIPE_CONSUMER_WARPS);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      redo_n = 0;
+    }
+    __syncwarp();
+    for (int s = 0; s < NST && s < niter; ++s)
+      pipe_issue<NARR>(src, nsteps - s * PIPE_SUB >= PIPE_SUB ? PIPE_SUB : 1,
+                       data0 + s * STAGEB, full0 + 8 * s, t0 + s * PIPE_SUB, tile0, row_bytes);
+  }
+  if (a.par_mode != 2) stage_lut<SEM>(a, lut);  // (contains __syncthreads)
+  else __syncthreads();                         // (the barriers are visible to everyone)
+
+  if (producer) {
+    int stage = 0;
+    uint32_t phase = 0;  // parity of the stage's previous use
+#pragma unroll 1
+    for (int i = NST; i < niter; ++i) {
+      mbar_wait(empty0 + 8 * stage, phase);  // all fifteen warps have read the stage
+      pipe_issue<NARR>(src, nsteps - i * PIPE_SUB >= PIPE_SUB ? PIPE_SUB : 1,
+                       data0 + (uint32_t)stage * STAGEB, full0 + 8 * stage,
+                       t0 + (int64_t)i * PIPE_SUB, tile0, row_bytes);
+      if (++stage == NST) { stage = 0; phase ^= 1u; }
+    }
+    return;
+  }
+
+  const int64_t n = tile0 + tid;
+  const bool live = n < a.N;
+  bool any_pos = false;
+  float gs_max = 0.0f;  // max of the gate quantity g_surf over this thread's elements (:343)
+  // per-pixel state, all scalar: BPLUT column constants, pressure terms, annual window
+  fast::PftConstV<F2> pc;
+  fast::PixConstV<F2> px;
+  PftConst c1;
+  {
+    if (a.par_mode == 2) {  // per-pixel parameter arrays: same constants, built per thread
+      double col[MOD16_N_PARAMS];
+      load_column(a, live ? n : 0, col);
+      c1 = fast::make_pft_const(col, SEM);
+    } else {
+      int code = 0;
+      if (live && a.par_mode == 1) {
+        code = (int)__ldg(a.pft + n);
+        code = code < MOD16_N_PFT ? code : MOD16_N_PFT;  // out of range: the all-NaN column
+      }
+      c1 = lut.pc[code];
+    }
+    // threads past the last pixel run the loop on whatever the stage holds (they take part
+    // in the barriers); csl = 0 keeps them out of the gate, `live` out of stores and queue
+    if (!live) c1.csl = 0.0f;
+    pc = fast::pair_pft(c1, c1);
+    if (!PXT) {
+      float p = 1e5f, ta = 0.f;
+      if (live) {
+        p = a.drv[MOD16_D_PRESSURE].at(0, n);   // per pixel or scalar (checked on the host)
+        ta = a.drv[MOD16_D_TEMP_ANNUAL].at(0, n);
+      }
+      const PixConst x1 = fast::make_pix_const(p, ta, c1, SEM);
+      px = fast::pair_pix(x1, x1);
+    }
+  }
+  const float swn_scalar = a.drv[MOD16_D_SW_RAD_NIGHT].scalar;
+  const int gate = a.gate;
+  constexpr int n_out = OUT == 0 ? 1 : (OUT == 1 ? 2 : 6);
+  const uint32_t my0 = data0 + (uint32_t)tid * 4u;  // this thread's pixel within a row
+  const int64_t t_stride = a.N;
+  int64_t off = t0 * t_stride + n;                  // running output offset
+  const bool warp_lead = (tid & 31) == 0;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  // One use of a stage.  TWO: both time steps of the pair exist (always, except for the last
+  // use of an odd chunk, which is peeled off the loop below so that the loop carries no
+  // tail handling).  Stage order == PipeSrc order (see launch_pipe).  The inputs are pulled
+  // into registers at once so that the stage can be re-filled while the steps are
+  // evaluated.  Lane x of every pair is step t, lane y is step t + 1 (step t again when the
+  // chunk is odd).
+  auto consume = [&](auto two_tag, const int i) {
+    constexpr bool TWO = decltype(two_tag)::value;
+    mbar_wait(full0 + 8 * stage, phase);
+    fast::StepInV<F2> in;
+    {
+      const uint32_t s0 = my0 + (uint32_t)stage * STAGEB;
+      const uint32_t s1 = TWO ? s0 + SUBB : s0;
+#define M16_IN(k) F2{lds1(s0 + (k) * PIPE_ROWB), lds1(s1 + (k) * PIPE_ROWB)}
+      in.lw_d = M16_IN(0);  in.lw_n = M16_IN(1);  in.sw_d = M16_IN(2);  in.alb = M16_IN(3);
+      in.t_d = M16_IN(4);   in.t_n = M16_IN(5);   in.tmin = M16_IN(6);  in.vpd_d = M16_IN(7);
+      in.vpd_n = M16_IN(8); in.fpar = M16_IN(9);  in.lai = M16_IN(10);
+      if (SWN) in.sw_n = M16_IN(pipe_slot_swn(EXTRA));
+      else in.sw_n = F2{swn_scalar, swn_scalar};
+      if (PXT) {  // per-step annual mean temperature and pressure: rebuild the pixel terms
+        const F2 ta = M16_IN(pipe_slot_tann(EXTRA)), p = M16_IN(pipe_slot_p(EXTRA));
+        px = fast::pair_pix(fast::make_pix_const(p.x, ta.x, c1, SEM),
+                            fast::make_pix_const(p.y, ta.y, c1, SEM));
+      }
+#undef M16_IN
+      in.rc_d = F2{0.f, 0.f}; in.rc_n = F2{0.f, 0.f};
+    }
+    __syncwarp();
+    if (warp_lead) mbar_arrive(empty0 + 8 * stage);  // this warp has read the stage
+    fast::StepOutV<F2> r;
+    M2 g_pos;
+    F2 gs, nan_probe;
+    M2 need = fast::step_fast<F2, SEM, false>(in, pc, px, gate, r, g_pos, gs, nan_probe);
+    need.x = need.x && live;
+    need.y = need.y && live && TWO;
+    F2 res[6];
+    if (OUT == 0) {
+      res[0] = r.tot;
+    } else if (OUT == 1) {
+      res[0] = r.tot_day; res[1] = r.tot_night;
+    } else {
+      res[0] = r.day.canopy;   res[1] = r.day.soil;   res[2] = r.day.trans;
+      res[3] = r.night.canopy; res[4] = r.night.soil; res[5] = r.night.trans;
+    }
+    if (!(need.x || need.y)) {
+      // (a NaN gate quantity -- garbage read by a thread past the last pixel -- is dropped)
+      gs_max = fmaxf(gs_max, fmaxf(gs.x, gs.y));
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < n_out; ++k) {
+          st_stream1(a.out[k] + off, res[k].x);
+          if (TWO) st_stream1(a.out[k] + off + t_stride, res[k].y);
+        }
+      }
+    } else {  // rare: queue for the double-precision pass after the loop
+      any_pos |= (g_pos.x && !need.x) || (g_pos.y && !need.y);
+#pragma unroll
+      for (int k = 0; k < n_out; ++k) {
+        if (!need.x) st_stream1(a.out[k] + off, res[k].x);
+        if (TWO && !need.y) st_stream1(a.out[k] + off + t_stride, res[k].y);
+      }
+#pragma unroll
+      for (int j = 0; j < PIPE_SUB; ++j) {
+        if (j == 0 ? need.x : need.y) {
+          const int64_t t = t0 + i * PIPE_SUB + j;
+          if (OUT != 2) {  // masked drivers: the total is NaN without the double code
+            // The probe of step_fast (or the pixel's pressure) is NaN exactly when a driver of
+            // the masked-driver rule is; a negative (fill) temperature acts the same (its
+            // r_corr is NaN).  Static `_et` total: NaN follows at once, decided from
+            // registers -- a masked pixel is masked at every step, its warp must not stall
+            // on re-reads -- with the hot path's own gate predicate (g_surf > 0 from Tmin,
+            // VPD, T, P; NaN > 0 is false).  Other modes: the out-of-line rule says which
+            // halves.
+            const float probe = j == 0 ? nan_probe.x : nan_probe.y;
+            const float td = j == 0 ? in.t_d.x : in.t_d.y, tn = j == 0 ? in.t_n.x : in.t_n.y;
+            const float pa = j == 0 ? px.pa.x : px.pa.y;
+            if (probe != probe || pa != pa || td < 0.0f || tn < 0.0f) {
+              bool gp = j == 0 ? g_pos.x : g_pos.y;
+              int h = 3;
+              if (!(OUT == 0 && SEM == SEM_STATIC && c1.ok != 0.0f))
+                h = nan_halves_one<SEM>(a, t, n, c1.ok, c1.csl, c1.inv_dtmin, c1.tmin_bias,
+                                        c1.vpd_off, c1.inv_dvpd, gp);
+              if (OUT == 0 ? h != 0 : h == 3) {
+                const float qnan = __int_as_float(0x7fc00000);
+                st_stream1(a.out[0] + off + j * t_stride, qnan);
+                if (OUT == 1) st_stream1(a.out[1] + off + j * t_stride, qnan);
+                any_pos |= gp;
+                continue;
+              }
+            }
+          }
+          bool queued = false;
+          if (a.redo_cap > 0) {  // global queue, evaluated by redo_queue_kernel
+            const unsigned long long slot = atomicAdd(a.redo_ws, 1ULL);
+            queued = slot < (unsigned long long)a.redo_cap;
+            if (queued) a.redo_ws[1 + slot] = (unsigned long long)(t * a.N + n);
+          } else {               // no workspace: block-local queue, evaluated after the loop
+            const int slot = atomicAdd(&redo_n, 1);
+            queued = slot < PIPE_QCAP;
+            if (queued) redo_q[slot] = (uint32_t)(i * PIPE_SUB + j) << 10 | (uint32_t)tid;
+          }
+          if (!queued) {
+            if (a.redo_cap > 0) {
+              // global queue full (fill-heavy data): leave a marker in the first output; the
+              // sweep kernel finds and evaluates it (the counter past the capacity tells it
+              // to run).  One in-place double evaluation here would hold the whole block.
+              st_stream1(a.out[0] + off + j * t_stride, __int_as_float(REDO_MARK));
+            } else {
+              any_pos |= fix_exact_one<SEM, OUT>(a, t, n);  // no workspace at all
+            }
+          }
+        }
+      }
+    }
+    off += PIPE_SUB * t_stride;
+    if (++stage == NST) { stage = 0; phase ^= 1u; }
+  };
+  const int nfull = nsteps / PIPE_SUB;
+#pragma unroll 1
+  for (int i = 0; i < nfull; ++i) consume(std::true_type(), i);
+  if (nsteps & 1) consume(std::false_type(), nfull);
+  any_pos |= gs_max > 0.0f;
+  // the block-local deferred pass: consumers only (named barrier 1), one element each
+  if (a.redo_cap == 0) {
+    asm volatile("bar.sync 1, %0;" ::"n"(PIPE_CONSUMERS) : "memory");
+    const int total = redo_n < PIPE_QCAP ? redo_n : PIPE_QCAP;
+    for (int e = tid; e < total; e += PIPE_CONSUMERS) {
+      const uint32_t q = redo_q[e];
+      any_pos |= fix_exact_one<SEM, OUT>(a, t0 + (int64_t)(q >> 10), tile0 + (q & 1023u));
+    }
+  }
+  if (a.track_gate) {
+    if (__any_sync(0xffffffffu, any_pos) && (threadIdx.x & 31) == 0) *a.gate_flag = 1;
+  }
+}
+
+template <int SEM, int OUT, int EXTRA>
+static int launch_pipe_inst(const ForwardArgs<float>& a, const PipeSrc& src, dim3 grid,
+                            cudaStream_t st) {
+  constexpr size_t smem = (size_t)pipe_n_stages(EXTRA) * PIPE_SUB * pipe_n_arr(EXTRA) * PIPE_ROWB;
+  // (the attribute is per function AND per device: set before every launch, it is cheap)
+  M16_CUDA_CHECK(cudaFuncSetAttribute(forward_pipe_kernel<SEM, OUT, EXTRA>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  forward_pipe_kernel<SEM, OUT, EXTRA><<<grid, PIPE_THREADS, smem, st>>>(a, src);
+  M16_CUDA_CHECK(cudaGetLastError());
+  return MOD16_OK;
+}
+
+// Instantiated per semantics in mod16_forward_pipe_{static,instance}.cu (parallel builds).
+// EXTRA 2 / 3 (time-varying annual temperature / pressure) exist for the summed and the
+// day / night outputs; `separate=True` with such drivers takes the strided kernel.
+template <int SEM>
+int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode, int extra,
+                    dim3 grid, cudaStream_t st) {
+#define M16_PIPE(O, E) \
+  if (out_mode == O && extra == E) return launch_pipe_inst<SEM, O, E>(a, src, grid, st)
+  M16_PIPE(0, 0); M16_PIPE(0, 1); M16_PIPE(0, 2); M16_PIPE(0, 3);
+  M16_PIPE(1, 0); M16_PIPE(1, 1); M16_PIPE(1, 2); M16_PIPE(1, 3);
+  M16_PIPE(2, 0); M16_PIPE(2, 1);
+#undef M16_PIPE
+  return MOD16_ERR_FLAGS;
+}
+
+inline bool pipe_has_variant(int out_mode, int extra) { return out_mode < 2 || extra < 2; }
+
+}  // namespace mod16

@@ -1,0 +1,9 @@
+// forward_pipe_kernel, instance semantics (`evapotranspiration()`): instantiations.
+#include "mod16_forward_pipe.cuh"
+
+namespace mod16 {
+int launch_pipe_instance(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode,
+                         int extra, dim3 grid, cudaStream_t st) {
+  return launch_pipe_sem<SEM_INSTANCE>(a, src, out_mode, extra, grid, st);
+}
+}  // namespace mod16

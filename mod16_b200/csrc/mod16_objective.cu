@@ -120,7 +120,7 @@ obj_classify_kernel(const __grid_constant__ ObjArgs<float> a) {
         // masked (NaN) drivers: the prediction is NaN for every draw, so the pair is not
         // valid for any of them -- same as a missing observation
         fast::PftConstV<float> sane;
-        sane.tmin_close = -8.0f; sane.inv_dtmin = 0.1f; sane.vpd_close = 3000.0f;
+        sane.tmin_bias = -26.5f; sane.inv_dtmin = 0.1f; sane.vpd_off = 3.0f;
         sane.inv_dvpd = 1e-3f; sane.csl = 0.0f; sane.ok = 1.0f;
         bool gp;
         if (fast::nan_halves<SEM_STATIC>(in, sane, false, gp) != 0) c = 0;

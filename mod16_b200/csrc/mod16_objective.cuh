@@ -168,8 +168,8 @@ M16_HD float float_round_down(double x) {
 // then evaluate the whole draw with the op-for-op double code): same test as make_pft_const.
 M16_HD bool make_draw_const(const double v[11], DrawConstV<float>& c) {
   const fast::PftConst p = fast::make_pft_const(v, SEM_STATIC);
-  c.tmin_close = p.tmin_close; c.inv_dtmin = p.inv_dtmin;
-  c.vpd_close = p.vpd_close;   c.inv_dvpd = p.inv_dvpd;
+  c.tmin_close = (float)v[0]; c.inv_dtmin = p.inv_dtmin;
+  c.vpd_close = (float)v[3];  c.inv_dvpd = p.inv_dvpd;
   c.gl_sh = p.gl_sh; c.gl_wv = p.gl_wv; c.g_cut = p.g_cut; c.csl = p.csl;
   c.rbl_max = p.rbl_max; c.rbl_delta = p.rbl_delta; c.inv_beta = p.inv_beta;
   c.tann_lo = float_round_down(273.15 + v[1]);

@@ -57,9 +57,7 @@ class ObjectiveBackend(object):
         reference callers drop the elements without an observation BEFORE the model sees
         them (mod16/calibration.py:895-900 ``d.copy()[~np.isnan(tower_obs)]``,
         mod16/sensitivity.py:179-186 ``drivers = [d[mask] for d in drivers]``), so their
-        ``np.any(g_surf > 0)`` never covers such elements either.  A caller that wants the
-        gate over ALL elements passes observations without NaN and a weight of 0 where the
-        observation is missing.
+        ``np.any(g_surf > 0)`` never covers such elements either.
     dtype : np.float32 (fast path) or np.float64; default follows numpy promotion
     '''
 

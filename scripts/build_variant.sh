@@ -6,4 +6,4 @@ mkdir -p mod16_b200/lib/variants
 cd mod16_b200/csrc
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --expt-relaxed-constexpr \
   -Xcompiler -fPIC --fmad=true -shared "$@" -o ../lib/variants/lib$name.so \
-  mod16_forward.cu mod16_forward_fast.cu mod16_aggregate.cu mod16_objective.cu mod16_elementwise.cu
+  *.cu

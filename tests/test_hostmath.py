@@ -221,7 +221,8 @@ def test_masked_driver_rule_is_sound(semantics):
     masked = rng.random(N) < 0.2            # whole masked pixels, as on a real tile
     for k in ('fpar', 'lai', 'sw_albedo'):
         d[k][:, masked] = np.nan
-    d['temp_day'][rng.random((T, N)) < 0.002] = -9999.0   # fills must NOT be decided here
+    fill_td = rng.random((T, N)) < 0.002
+    d['temp_day'][fill_td] = -9999.0     # a negative temperature: r_corr is NaN (:292)
     drv = [d[k] for k in NAMES]
     d64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
     table = _table()
@@ -233,10 +234,8 @@ def test_masked_driver_rule_is_sound(semantics):
         else:
             day, night = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, col))).evapotranspiration(*d64)
     assert np.isnan(day[(h & 1) > 0]).all() and np.isnan(night[(h & 2) > 0]).all()
-    # a fill value in a driver the gate predicate reads is left to the double code
-    if semantics == 'static':
-        assert not (h[(d['temp_day'] == -9999.0) & ~np.isnan(d['vpd_day']) &
-                      ~np.isnan(np.broadcast_to(d['pressure'], (T, N)))] > 0).any()
+    # a negative (fill) temperature makes its half-day NaN like a NaN one does
+    assert ((h[fill_td] & 1) > 0).all() and np.isnan(day[fill_td]).all()
     only_masked = np.broadcast_to(masked, (T, N)).copy()
     for k in names2d:
         if k not in ('fpar', 'lai', 'sw_albedo'):
