@@ -378,9 +378,10 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
     const V den = vfma((S + G) * prod, X, (G * Yd) * tot);
     V tr = (num * ((omfw * prod) * X)) * vrcp(den);
     if (SEM == SEM_STATIC) {
-      if (gate == GATE_CLOSED) tr = splat<V>(0.0f);
-      else if (gate == GATE_ELEMENT) tr = vsel(g_pos, tr, splat<V>(0.0f));
-      o.trans = tr;
+      // the gate without a branch: open -> keep; closed -> drop; per element -> g_surf > 0
+      const float g_el = gate == GATE_ELEMENT ? 1.0f : 0.0f;
+      const float g_op = (gate == GATE_CLOSED || gate == GATE_ELEMENT) ? 0.0f : 1.0f;
+      o.trans = vsel(vgt(vfma(gs, g_el, g_op), splat<V>(0.0f)), tr, splat<V>(0.0f));
     } else {
       const M dead = mor(mnot(ok), vle(prod, 1e-7f * tot));                     // :1258
       o.trans = vsel(dead, splat<V>(0.0f), tr * il);
@@ -429,11 +430,12 @@ M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in, V tc_d, V tc_n, 
   const V lo = vmin3(in.lai, in.fpar, in.alb);
   const V vlo = vmin(in.vpd_d, in.vpd_n);
   const V tmag = vmax(vabs(tc_d), vabs(tc_n));
-  // (nan_probe bounds s2 and is the one sum that sees the temperatures: fmax below would
-  // drop a NaN temperature)
-  return mand(mand(mand(vlt(sa + sb, splat<V>(9000.0f)), vlt(nan_probe, splat<V>(1.1e5f))),
-                   mand(vge(lo, splat<V>(0.0f)), vgt(vlo, splat<V>(-1000.0f)))),
-              vlt(tmag, splat<V>(66.85f)));
+  // ONE magnitude test: radiation terms and Tmin weigh twelve times (|.| < 9000 each: a fill
+  // value fails), everything else once (< 1.1e5); the sum sees every driver, so a NaN or an
+  // infinity anywhere fails it (fmin / fmax below would drop a NaN operand)
+  const V mag = vfma(sa + sb, 11.0f, nan_probe + sb);
+  return mand(mand(vlt(mag, splat<V>(1.1e5f)), vge(lo, splat<V>(0.0f))),
+              mand(vgt(vlo, splat<V>(-1000.0f)), vlt(tmag, splat<V>(66.85f))));
 }
 template <class V>
 M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in) {
@@ -473,14 +475,16 @@ M16_HD bool element_needs_exact(const StepInV<float>& in, float p) {
 // discontinuity); their entries of `o` are unspecified.
 // `gs_day` receives the day's gate quantity g_surf (> 0 <=> g_pos), so that a caller can
 // track `any(g_surf > 0)` with one max instead of predicate logic.
+// step_core(): everything but the domain test (the pipelined kernel tests the domain FIRST
+// and deals with the elements outside it while all their inputs are still in registers);
+// returns the mask of elements within rounding of a discontinuity.
 template <class V, int SEM, bool HAS_RC>
-M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,
-                                          const PixConstV<V>& x, int gate, StepOutV<V>& o,
-                                          typename MaskOf<V>::type& g_pos, V& gs_day,
-                                          V& nan_probe) {
+M16_HD typename MaskOf<V>::type step_core(const StepInV<V>& in, V tc_d, V tc_n,
+                                          const PftConstV<V>& c, const PixConstV<V>& x,
+                                          int gate, StepOutV<V>& o,
+                                          typename MaskOf<V>::type& g_pos, V& gs_day) {
   typedef typename MaskOf<V>::type M;
-  const V tc_d = celsius<V>(in.t_d), tc_n = celsius<V>(in.t_n);
-  M need = mnot(mand(x.ok, in_domain<V>(in, tc_d, tc_n, nan_probe)));
+  M need = mask_splat<V>(false);
   const V oma = 1.0f - in.alb;
   const V a_d = vfma(in.sw_d, oma, in.lw_d);            // :225
   const V a_n = in.lw_n;                                 // :226
@@ -522,6 +526,15 @@ M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<
   }
   o.tot = o.tot_day + o.tot_night;
   return need;
+}
+template <class V, int SEM, bool HAS_RC>
+M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,
+                                          const PixConstV<V>& x, int gate, StepOutV<V>& o,
+                                          typename MaskOf<V>::type& g_pos, V& gs_day,
+                                          V& nan_probe) {
+  const V tc_d = celsius<V>(in.t_d), tc_n = celsius<V>(in.t_n);
+  const typename MaskOf<V>::type bad = mnot(mand(x.ok, in_domain<V>(in, tc_d, tc_n, nan_probe)));
+  return mor(bad, step_core<V, SEM, HAS_RC>(in, tc_d, tc_n, c, x, gate, o, g_pos, gs_day));
 }
 template <class V, int SEM, bool HAS_RC>
 M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,

@@ -98,20 +98,63 @@ __device__ __forceinline__ void pipe_issue(const PipeSrc& src, int n_sub, uint32
   __syncwarp();
 }
 
-// fast::nan_halves() for ONE flagged element of the pipelined kernel, out of line and
-// self-contained (the hot loop keeps no inputs alive for it); the six BPLUT-derived
-// constants the rule reads are the thread's own registers.
-template <int SEM>
-__device__ __noinline__ int nan_halves_one(const ForwardArgs<float>& a, int64_t t, int64_t n,
-                                           float ok, float csl, float inv_dtmin,
-                                           float tmin_bias, float vpd_off, float inv_dvpd,
-                                           bool& g_pos) {
+// ---- rare-path helpers ---------------------------------------------------------------------
+// Out of line, and they work out the element's indices themselves (block and thread index,
+// `ts` = time step within the block's chunk): the hot loop keeps nothing alive for them.
+
+// Defers ONE element to the double-precision pass: the caller's queue (redo_queue_kernel)
+// or -- no workspace -- this block's own queue (evaluated after its loop); a full queue
+// leaves a marker in the output instead, which redo_sweep_kernel / the block's own sweep
+// finds (the counter past the capacity tells them to run).  One in-place double evaluation
+// here would hold the whole block.  Inlined on purpose: a CALL inside the time loop keeps
+// the loop's uniform values out of the uniform registers.
+__device__ __forceinline__ void pipe_defer(const ForwardArgs<float>& a, int ts, uint32_t* redo_q,
+                                           int* redo_n) {
+  const int tid = (int)threadIdx.x;
+  const int64_t n = (int64_t)blockIdx.x * PIPE_TILE + tid;
+  const int64_t t = (int64_t)blockIdx.y * a.t_chunk + ts;
+  bool queued;
+  if (a.redo_cap > 0) {
+    const unsigned long long slot = atomicAdd(a.redo_ws, 1ULL);
+    queued = slot < (unsigned long long)a.redo_cap;
+    if (queued) a.redo_ws[1 + slot] = (unsigned long long)(t * a.N + n);
+  } else {
+    const int slot = atomicAdd(redo_n, 1);
+    queued = slot < PIPE_QCAP;
+    if (queued) redo_q[slot] = (uint32_t)ts << 10 | (uint32_t)tid;
+  }
+  if (!queued) st_stream1(a.out[0] + t * a.N + n, __int_as_float(REDO_MARK));
+}
+
+// The masked-driver rule (fast::nan_halves) for ONE element of the modes that cannot decide
+// it from registers: re-reads the element's inputs.  Writes the NaN outputs and returns the
+// gate predicate (0 / 1) when the rule decides the element, else -1.
+template <int SEM, int OUT>
+__device__ __forceinline__ int pipe_rule(const ForwardArgs<float>& a, int ts, float ok, float csl,
+                                      float inv_dtmin, float tmin_bias, float vpd_off,
+                                      float inv_dvpd) {
+  const int64_t n = (int64_t)blockIdx.x * PIPE_TILE + (int)threadIdx.x;
+  const int64_t t = (int64_t)blockIdx.y * a.t_chunk + ts;
   StepIn in = load_step(a, t, n);
   in.t_ann = 0.0f;
   fast::PftConstV<float> c;
   c.ok = ok; c.csl = csl; c.inv_dtmin = inv_dtmin; c.tmin_bias = tmin_bias;
   c.vpd_off = vpd_off; c.inv_dvpd = inv_dvpd;
-  return fast::nan_halves<SEM>(in, c, a.has_rc != 0, g_pos);
+  bool g_pos;
+  const int h = fast::nan_halves<SEM>(in, c, a.has_rc != 0, g_pos);
+  if (OUT == 2 || !(OUT == 0 ? h != 0 : h == 3)) return -1;
+  const float qnan = __int_as_float(0x7fc00000);
+  st_stream1(a.out[0] + t * a.N + n, qnan);
+  if (OUT == 1) st_stream1(a.out[1] + t * a.N + n, qnan);
+  return g_pos ? 1 : 0;
+}
+
+// (a value the compiler must compute once and keep: shared-window addresses would otherwise
+// be re-derived from special registers in every iteration)
+__device__ __forceinline__ uint32_t keep_u32(uint32_t x) {
+  uint32_t y;
+  asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
 }
 
 template <int SEM, int OUT, int EXTRA>
@@ -141,7 +184,8 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   const int nsteps = (int)(t1 - t0);
   const int niter = (nsteps + PIPE_SUB - 1) / PIPE_SUB;  // stage uses; the last may hold 1 step
   const int64_t left = a.N - tile0;
-  const uint32_t row_bytes = (uint32_t)((left < PIPE_TILE ? left : PIPE_TILE) * sizeof(float));
+  const int n_live = (int)(left < PIPE_TILE ? left : PIPE_TILE);
+  const uint32_t row_bytes = (uint32_t)n_live * (uint32_t)sizeof(float);
   const uint32_t full0 = smem_u32(&full[0]), empty0 = smem_u32(&empty[0]);
   const uint32_t data0 = smem_u32(dyn_smem);
   const bool producer = tid >= PIPE_CONSUMERS;
@@ -177,8 +221,15 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     return;
   }
 
-  const int64_t n = tile0 + tid;
-  const bool live = n < a.N;
+  // ---- consumers ---------------------------------------------------------------------------
+  // Per-thread element state of an iteration, one bit per lane (x: step t, y: step t + 1):
+  //   DONE    the element needs nothing more from this thread (a pixel past the end of the
+  //           tile, the missing second step of an odd chunk, an element already deferred)
+  //   MASKED  static `_et` total of an element with a masked (NaN) driver: NaN goes out
+  //           after the math, with the hot path's own gate predicate
+  constexpr uint32_t DONE_X = 1u, DONE_Y = 2u, MASKED_X = 4u, MASKED_Y = 8u;
+  const bool live = tid < n_live;
+  const uint32_t flags0 = live ? 0u : (DONE_X | DONE_Y);
   bool any_pos = false;
   float gs_max = 0.0f;  // max of the gate quantity g_surf over this thread's elements (:343)
   // per-pixel state, all scalar: BPLUT column constants, pressure terms, annual window
@@ -186,6 +237,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   fast::PixConstV<F2> px;
   PftConst c1;
   {
+    const int64_t n = tile0 + tid;
     if (a.par_mode == 2) {  // per-pixel parameter arrays: same constants, built per thread
       double col[MOD16_N_PARAMS];
       load_column(a, live ? n : 0, col);
@@ -198,9 +250,6 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       }
       c1 = lut.pc[code];
     }
-    // threads past the last pixel run the loop on whatever the stage holds (they take part
-    // in the barriers); csl = 0 keeps them out of the gate, `live` out of stores and queue
-    if (!live) c1.csl = 0.0f;
     pc = fast::pair_pft(c1, c1);
     if (!PXT) {
       float p = 1e5f, ta = 0.f;
@@ -212,15 +261,15 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       px = fast::pair_pix(x1, x1);
     }
   }
+  // the masked-driver rule is decided from registers for the static total of a sane column
+  const bool rule_in_regs = OUT == 0 && SEM == SEM_STATIC && c1.ok != 0.0f;
   const float swn_scalar = a.drv[MOD16_D_SW_RAD_NIGHT].scalar;
   const int gate = a.gate;
   constexpr int n_out = OUT == 0 ? 1 : (OUT == 1 ? 2 : 6);
-  const uint32_t my0 = data0 + (uint32_t)tid * 4u;  // this thread's pixel within a row
+  const uint32_t my0 = keep_u32(data0 + (uint32_t)tid * 4u);  // this thread's pixel in a row
+  const uint32_t full_k = keep_u32(full0), empty_k = keep_u32(empty0);
   const int64_t t_stride = a.N;
-  int64_t off = t0 * t_stride + n;                  // running output offset
-  const bool warp_lead = (tid & 31) == 0;
-  int stage = 0;
-  uint32_t phase = 0;
+  int64_t off = t0 * t_stride + tile0 + tid;        // running output offset
 
   // One use of a stage.  TWO: both time steps of the pair exist (always, except for the last
   // use of an odd chunk, which is peeled off the loop below so that the loop carries no
@@ -230,10 +279,12 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   // chunk is odd).
   auto consume = [&](auto two_tag, const int i) {
     constexpr bool TWO = decltype(two_tag)::value;
-    mbar_wait(full0 + 8 * stage, phase);
+    const uint32_t stage = (uint32_t)i % (uint32_t)NST;
+    const uint32_t phase = ((uint32_t)i / (uint32_t)NST) & 1u;
+    mbar_wait(full_k + 8 * stage, phase);
     fast::StepInV<F2> in;
     {
-      const uint32_t s0 = my0 + (uint32_t)stage * STAGEB;
+      const uint32_t s0 = my0 + stage * STAGEB;
       const uint32_t s1 = TWO ? s0 + SUBB : s0;
 #define M16_IN(k) F2{lds1(s0 + (k) * PIPE_ROWB), lds1(s1 + (k) * PIPE_ROWB)}
       in.lw_d = M16_IN(0);  in.lw_n = M16_IN(1);  in.sw_d = M16_IN(2);  in.alb = M16_IN(3);
@@ -250,13 +301,46 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       in.rc_d = F2{0.f, 0.f}; in.rc_n = F2{0.f, 0.f};
     }
     __syncwarp();
-    if (warp_lead) mbar_arrive(empty0 + 8 * stage);  // this warp has read the stage
+    if (elect_one()) mbar_arrive(empty_k + 8 * stage);  // this warp has read the stage
+    uint32_t flags = TWO ? flags0 : (flags0 | DONE_Y);
+
+    // -- the domain of the fast formulas, tested while every input is still in a register
+    const F2 tc_d = fast::celsius<F2>(in.t_d), tc_n = fast::celsius<F2>(in.t_n);
+    F2 nan_probe;
+    const M2 dom = fast::mand(px.ok, fast::in_domain<F2>(in, tc_d, tc_n, nan_probe));
+    if (!(dom.x && dom.y)) {  // rare
+#pragma unroll
+      for (int j = 0; j < PIPE_SUB; ++j) {
+        const uint32_t done_j = j == 0 ? DONE_X : DONE_Y;
+        if ((j == 0 ? dom.x : dom.y) || (flags & done_j)) continue;
+        // A NaN probe (or pressure) means a NaN driver of the masked-driver rule; a negative
+        // (fill) temperature acts the same (its r_corr is NaN).  A masked pixel is masked at
+        // every step: its warp must not stall on re-reads or on the double code.
+        const float probe = j == 0 ? nan_probe.x : nan_probe.y;
+        const float td = j == 0 ? in.t_d.x : in.t_d.y, tn = j == 0 ? in.t_n.x : in.t_n.y;
+        const float pa = j == 0 ? px.pa.x : px.pa.y;
+        if (OUT != 2 && (probe != probe || pa != pa || td < 0.0f || tn < 0.0f)) {
+          if (rule_in_regs) {
+            flags |= j == 0 ? MASKED_X : MASKED_Y;
+            continue;
+          }
+          const int r = pipe_rule<SEM, OUT>(a, i * PIPE_SUB + j, c1.ok, c1.csl, c1.inv_dtmin,
+                                            c1.tmin_bias, c1.vpd_off, c1.inv_dvpd);
+          flags |= done_j;
+          if (r >= 0) {
+            any_pos |= r > 0;
+            continue;
+          }
+        }
+        flags |= done_j;
+        pipe_defer(a, i * PIPE_SUB + j, redo_q, &redo_n);
+      }
+    }
+
     fast::StepOutV<F2> r;
     M2 g_pos;
-    F2 gs, nan_probe;
-    M2 need = fast::step_fast<F2, SEM, false>(in, pc, px, gate, r, g_pos, gs, nan_probe);
-    need.x = need.x && live;
-    need.y = need.y && live && TWO;
+    F2 gs;
+    const M2 late = fast::step_core<F2, SEM, false>(in, tc_d, tc_n, pc, px, gate, r, g_pos, gs);
     F2 res[6];
     if (OUT == 0) {
       res[0] = r.tot;
@@ -266,91 +350,53 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       res[0] = r.day.canopy;   res[1] = r.day.soil;   res[2] = r.day.trans;
       res[3] = r.night.canopy; res[4] = r.night.soil; res[5] = r.night.trans;
     }
-    if (!(need.x || need.y)) {
-      // (a NaN gate quantity -- garbage read by a thread past the last pixel -- is dropped)
+    if (flags == 0u && !(late.x || late.y)) {
       gs_max = fmaxf(gs_max, fmaxf(gs.x, gs.y));
-      if (live) {
-#pragma unroll
-        for (int k = 0; k < n_out; ++k) {
-          st_stream1(a.out[k] + off, res[k].x);
-          if (TWO) st_stream1(a.out[k] + off + t_stride, res[k].y);
-        }
-      }
-    } else {  // rare: queue for the double-precision pass after the loop
-      any_pos |= (g_pos.x && !need.x) || (g_pos.y && !need.y);
 #pragma unroll
       for (int k = 0; k < n_out; ++k) {
-        if (!need.x) st_stream1(a.out[k] + off, res[k].x);
-        if (TWO && !need.y) st_stream1(a.out[k] + off + t_stride, res[k].y);
+        st_stream1(a.out[k] + off, res[k].x);
+        if (TWO) st_stream1(a.out[k] + off + t_stride, res[k].y);
       }
+    } else {  // rare
 #pragma unroll
       for (int j = 0; j < PIPE_SUB; ++j) {
-        if (j == 0 ? need.x : need.y) {
-          const int64_t t = t0 + i * PIPE_SUB + j;
-          if (OUT != 2) {  // masked drivers: the total is NaN without the double code
-            // The probe of step_fast (or the pixel's pressure) is NaN exactly when a driver of
-            // the masked-driver rule is; a negative (fill) temperature acts the same (its
-            // r_corr is NaN).  Static `_et` total: NaN follows at once, decided from
-            // registers -- a masked pixel is masked at every step, its warp must not stall
-            // on re-reads -- with the hot path's own gate predicate (g_surf > 0 from Tmin,
-            // VPD, T, P; NaN > 0 is false).  Other modes: the out-of-line rule says which
-            // halves.
-            const float probe = j == 0 ? nan_probe.x : nan_probe.y;
-            const float td = j == 0 ? in.t_d.x : in.t_d.y, tn = j == 0 ? in.t_n.x : in.t_n.y;
-            const float pa = j == 0 ? px.pa.x : px.pa.y;
-            if (probe != probe || pa != pa || td < 0.0f || tn < 0.0f) {
-              bool gp = j == 0 ? g_pos.x : g_pos.y;
-              int h = 3;
-              if (!(OUT == 0 && SEM == SEM_STATIC && c1.ok != 0.0f))
-                h = nan_halves_one<SEM>(a, t, n, c1.ok, c1.csl, c1.inv_dtmin, c1.tmin_bias,
-                                        c1.vpd_off, c1.inv_dvpd, gp);
-              if (OUT == 0 ? h != 0 : h == 3) {
-                const float qnan = __int_as_float(0x7fc00000);
-                st_stream1(a.out[0] + off + j * t_stride, qnan);
-                if (OUT == 1) st_stream1(a.out[1] + off + j * t_stride, qnan);
-                any_pos |= gp;
-                continue;
-              }
-            }
-          }
-          bool queued = false;
-          if (a.redo_cap > 0) {  // global queue, evaluated by redo_queue_kernel
-            const unsigned long long slot = atomicAdd(a.redo_ws, 1ULL);
-            queued = slot < (unsigned long long)a.redo_cap;
-            if (queued) a.redo_ws[1 + slot] = (unsigned long long)(t * a.N + n);
-          } else {               // no workspace: block-local queue, evaluated after the loop
-            const int slot = atomicAdd(&redo_n, 1);
-            queued = slot < PIPE_QCAP;
-            if (queued) redo_q[slot] = (uint32_t)(i * PIPE_SUB + j) << 10 | (uint32_t)tid;
-          }
-          if (!queued) {
-            if (a.redo_cap > 0) {
-              // global queue full (fill-heavy data): leave a marker in the first output; the
-              // sweep kernel finds and evaluates it (the counter past the capacity tells it
-              // to run).  One in-place double evaluation here would hold the whole block.
-              st_stream1(a.out[0] + off + j * t_stride, __int_as_float(REDO_MARK));
-            } else {
-              any_pos |= fix_exact_one<SEM, OUT>(a, t, n);  // no workspace at all
-            }
-          }
+        if (flags & (j == 0 ? DONE_X : DONE_Y)) continue;
+        if (flags & (j == 0 ? MASKED_X : MASKED_Y)) {
+          // (g_surf > 0 from Tmin, VPD, T, P of the hot path; NaN > 0 is false)
+          st_stream1(a.out[0] + off + j * t_stride, __int_as_float(0x7fc00000));
+          any_pos |= j == 0 ? g_pos.x : g_pos.y;
+        } else if (j == 0 ? late.x : late.y) {
+          pipe_defer(a, i * PIPE_SUB + j, redo_q, &redo_n);
+        } else {
+          any_pos |= j == 0 ? g_pos.x : g_pos.y;
+#pragma unroll
+          for (int k = 0; k < n_out; ++k)
+            st_stream1(a.out[k] + off + j * t_stride, j == 0 ? res[k].x : res[k].y);
         }
       }
     }
     off += PIPE_SUB * t_stride;
-    if (++stage == NST) { stage = 0; phase ^= 1u; }
   };
   const int nfull = nsteps / PIPE_SUB;
 #pragma unroll 1
   for (int i = 0; i < nfull; ++i) consume(std::true_type(), i);
   if (nsteps & 1) consume(std::false_type(), nfull);
   any_pos |= gs_max > 0.0f;
-  // the block-local deferred pass: consumers only (named barrier 1), one element each
+  // the block-local deferred pass: consumers only (named barrier 1), one element each; when
+  // the block's queue overflowed, every thread also looks for markers in its own column
   if (a.redo_cap == 0) {
     asm volatile("bar.sync 1, %0;" ::"n"(PIPE_CONSUMERS) : "memory");
     const int total = redo_n < PIPE_QCAP ? redo_n : PIPE_QCAP;
     for (int e = tid; e < total; e += PIPE_CONSUMERS) {
       const uint32_t q = redo_q[e];
       any_pos |= fix_exact_one<SEM, OUT>(a, t0 + (int64_t)(q >> 10), tile0 + (q & 1023u));
+    }
+    if (redo_n > PIPE_QCAP && live) {
+      for (int ts = 0; ts < nsteps; ++ts) {
+        const int64_t o = (t0 + ts) * a.N + tile0 + tid;
+        if (__float_as_int(((volatile float*)a.out[0])[o]) == REDO_MARK)
+          any_pos |= fix_exact_one<SEM, OUT>(a, t0 + ts, tile0 + tid);
+      }
     }
   }
   if (a.track_gate) {
