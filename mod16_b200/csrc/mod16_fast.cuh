@@ -151,6 +151,14 @@ M16_HD F2 vsel(M2 m, F2 a, F2 b) { return F2{m.x ? a.x : b.x, m.y ? a.y : b.y}; 
 M16_HD F2 vsel(M2 m, F2 a, float b) { return F2{m.x ? a.x : b, m.y ? a.y : b}; }
 M16_HD F2 vsel(M2 m, float a, F2 b) { return F2{m.x ? a : b.x, m.y ? a : b.y}; }
 M16_HD bool many(M2 m) { return m.x || m.y; }
+// comparison results as 1.0f / 0.0f (device: FSET.BF, one instruction instead of a compare
+// and a select); a NaN compares false
+M16_HD float vstep_ge(float a, float b) { return a >= b ? 1.0f : 0.0f; }
+M16_HD F2 vstep_ge(F2 a, float b) { return F2{a.x >= b ? 1.0f : 0.0f, a.y >= b ? 1.0f : 0.0f}; }
+M16_HD float vstep_ge_and(float a, float b, bool m) { return (a >= b && m) ? 1.0f : 0.0f; }
+M16_HD F2 vstep_ge_and(F2 a, float b, M2 m) {
+  return F2{(a.x >= b && m.x) ? 1.0f : 0.0f, (a.y >= b && m.y) ? 1.0f : 0.0f};
+}
 
 template <class V> struct MaskOf;
 template <> struct MaskOf<float> { typedef bool type; };
@@ -163,6 +171,21 @@ template <> M16_HD M2 mask_splat<F2>(bool b) { return M2{b, b}; }
 constexpr double kLam0 = 2.45e6;          // lambda / kLam0 ~ 1
 constexpr double kT0 = 293.15;            // T / kT0 = q ~ 1            (:292)
 constexpr double kDD0 = 264.0 * 264.0;    // (239 + Tc)^2 / kDD0 ~ 1    (:1397)
+
+// Every Penman-Monteith ratio below is homogeneous of degree one in (S, G, K) -- the scaled
+// slope, psychrometric constant and vapour-pressure term --, so a common factor cancels.  It
+// is chosen such that S = e lam q and K = lam dd VPD carry no constant of their own and
+// B = 4 sigma T^4 / Cp is (q^2)^2: q = kKappa T / kT0, dd = (kR (239 + Tc))^2.
+constexpr double csqrt(double x) {
+  double g = x > 1.0 ? x : 1.0;
+  for (int i = 0; i < 100; ++i) g = 0.5 * (g + x / g);
+  return g;
+}
+constexpr double kCB = 4.0 * kSigma * kT0 * kT0 * kT0 * kT0 / kCp;   // B = kCB (T / kT0)^4
+constexpr double kKappa = csqrt(csqrt(kCB));
+constexpr double kKappa175 = kKappa * csqrt(kKappa) * csqrt(csqrt(kKappa));   // kKappa^1.75
+constexpr double kC1 = 17.38 * 239.0 * 610.8;      // slope: kC1 e / (239 + Tc)^2   (:1397)
+constexpr double kR = csqrt(kKappa * kCp / (kT0 * kC1));
 
 // ======================= per-PFT and per-pixel constants ==================================
 // constants derived from one BPLUT column (computed in double, stored as float)
@@ -207,8 +230,8 @@ M16_HD PftConst make_pft_const(const double v[11], int sem) {
 template <class V>
 struct PixConstV {
   V pa;        // 0.348444 * (P / 100)                          (:410)
-  V inv_p101;  // P / 101300 = 1 / (101300 / P)                 (:292)
-  V cpp_n;     // Cp P / eps / (kLam0 kDD0): scaled gamma numerator (:1289)
+  V ip;        // (P / 101300) kKappa^1.75: 1 / r_corr = ip q^-1.75     (:292)
+  V gp;        // scaled psychrometric term: G = gp q dd                (:1289)
   typename MaskOf<V>::type window;  // annual-temperature window (:230-233)
   typename MaskOf<V>::type ok;      // pressure and BPLUT column inside the fast domain
 };
@@ -217,8 +240,8 @@ typedef PixConstV<float> PixConst;
 M16_HD PixConst make_pix_const(float p, float t_ann, const PftConst& c, int sem) {
   PixConst x;
   x.pa = 0.348444f * (p * 0.01f);
-  x.inv_p101 = p * (float)(1.0 / 101300.0);
-  x.cpp_n = p * (float)(kCp / kEps / (kLam0 * kDD0));
+  x.ip = p * (float)(kKappa175 / 101300.0);
+  x.gp = p * (float)(kT0 / (kEps * kLam0 * kKappa));
   // the window is decided in double: a float32 T_ann must fall on the same side of
   // 298.15 and of 273.15 + tmin as it does in the float64 reference
   const double ta = (double)t_ann;
@@ -230,8 +253,8 @@ M16_HD PixConst make_pix_const(float p, float t_ann, const PftConst& c, int sem)
 
 M16_HD PixConstV<F2> pair_pix(const PixConst& a, const PixConst& b) {
   PixConstV<F2> r;
-  r.pa = F2{a.pa, b.pa}; r.inv_p101 = F2{a.inv_p101, b.inv_p101};
-  r.cpp_n = F2{a.cpp_n, b.cpp_n};
+  r.pa = F2{a.pa, b.pa}; r.ip = F2{a.ip, b.ip};
+  r.gp = F2{a.gp, b.gp};
   r.window = M2{a.window, b.window}; r.ok = M2{a.ok, b.ok};
   return r;
 }
@@ -293,7 +316,8 @@ constexpr float kGuard = 1.0e-4f;
 // compare.  `need` is only touched for a supplied r_corr outside its sane range.
 template <class V, int SEM, bool DAY, bool HAS_RC>
 M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V fpar, V omf,
-                          V lai, const PftConstV<V>& c, const PixConstV<V>& x, int gate,
+                          V lai, V gl, V gw, const PftConstV<V>& c, const PixConstV<V>& x,
+                          int gate,
                           typename MaskOf<V>::type& g_pos, typename MaskOf<V>::type& need,
                           V& gs_out, V& guard_a, V& guard_b) {
   typedef typename MaskOf<V>::type M;
@@ -310,27 +334,27 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
   guard_a = vfma(rh, 25.0f, -17.5f);       // (rh - 0.7) * 25      : 4e-6 -> kGuard
   guard_b = vfma(rh, 0.1f, -kGuard);       // (rh - 1e-3) * 0.1    : 1e-3 -> kGuard
   const V rh2 = rh * rh;
-  const V fw = vsel(vge(rh, splat<V>(0.7f)), rh2 * rh2, splat<V>(0.0f));  // :282
+  const V fw = vstep_ge(rh, 0.7f) * (rh2 * rh2);                          // :282
   const V omfw = 1.0f - fw;
-  // scaled slope S = s m, psychrometric constant G = gamma m and K = rho Cp VPD m / X
-  const V q = t * (float)(1.0 / kT0);
-  const V d2 = tc + 239.0f;
+  // scaled slope S, psychrometric constant G and vapour-pressure term K (see kKappa)
+  const V q = t * (float)(kKappa / kT0);
+  const V d2 = vfma(tc, (float)kR, (float)(239.0 * kR));
   const V dd = d2 * d2;
   const V lam_n = vfma(tc, (float)(-2361.0 / kLam0), (float)(2.501e6 / kLam0));    // :121
-  const V S = (((float)(17.38 * 239.0 * 610.8 / kDD0) * e) * lam_n) * q;            // :1397
-  const V G = (x.cpp_n * q) * dd;                                                    // :1289
-  const V Kv = (((float)(kCp / (kT0 * kDD0)) * lam_n) * dd) * vpd;
+  const V S = (e * lam_n) * q;                                                       // :1397
+  const V G = (x.gp * q) * dd;                                                       // :1289
+  const V Kv = (lam_n * dd) * vpd;
   // X = rho T (:409-412); B = X / r_r = 4 sigma T^4 / Cp (:298-299)
   const V X = vfma(rh, vfma(tc, -0.252f, 2.0582f), x.pa);
   const V q2 = q * q;
-  const V B = (float)(4.0 * kSigma * kT0 * kT0 * kT0 * kT0 / kCp) * (q2 * q2);
+  const V B = q2 * q2;
   // 1 / r_corr = (P / 101300) (T / 293.15)^-1.75 (:292), or the supplied r_corr_list entry
   V inv_rc;
   if (HAS_RC) {
     inv_rc = vrcp(rc);
     need = mor(need, mnot(mand(vgt(rc, splat<V>(1e-6f)), vlt(rc, splat<V>(1e6f)))));
   } else {
-    inv_rc = x.inv_p101 * vex2(-1.75f * vlg2(q));
+    inv_rc = x.ip * vex2(-1.75f * vlg2(q));
   }
   const V m_v = vsat(vfma(-vpd, c.inv_dvpd, c.vpd_off));  // reversed ramp on VPD (:326)
   const V Kf = Kv * fpar;
@@ -341,12 +365,11 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
   HalfV<V> o;
   // -- wet canopy (:305-320): e = fw ce X (S Ac + Kf Y) / (S ce X + G Y), Y = X / r_aw
   {
-    const V lf = lai * fw;
-    const V ce = c.gl_wv * lf;
-    const V Y = vfma(c.gl_sh * lf, X, B);
+    const V ceX = (gw * fw) * X;
+    const V Y = vfma(gl * fw, X, B);
     const V num = vfma(Kf, Y, SA);
-    const V den = vfma(S * ce, X, G * Y);
-    const V r = ((fw * ce) * X) * vrcp(den);
+    const V den = vfma(S, ceX, G * Y);
+    const V r = (fw * ceX) * vrcp(den);
     if (SEM == SEM_STATIC) {
       o.canopy = num * r;  // the (lai f_wet <= 1e-7) mask changes less than 1e-6 W m-2
     } else {
@@ -366,7 +389,7 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
     g_pos = vgt(gs, splat<V>(0.0f));
     gs_out = gs;
     const V sc = vfma(c.g_cut, inv_rc, gs);                                     // :329
-    const V gbl = (c.gl_sh * lai) * omfw;                                       // :333
+    const V gbl = gl * omfw;                                                    // :333
     // lai > 0 and 1 - f_wet > 0 (:336): with gl_sh > 0 (PftConst::ok) and lai >= 0 (domain)
     // that is gbl > 0 -- rh > 1 (negative VPD, static) makes 1 - f_wet and gbl negative
     const M ok = vgt(gbl, splat<V>(0.0f));
@@ -490,9 +513,9 @@ M16_HD typename MaskOf<V>::type step_core(const StepInV<V>& in, V tc_d, V tc_n,
   const V a_n = in.lw_n;                                 // :226
   const V a_nc = vfma(in.sw_n, oma, in.lw_n);            // :272 (night: sw_rad_night)
   // soil heat flux (:229-241)
-  const M cond = mand(x.window, vge(in.t_d - in.t_n, splat<V>(5.0f)));
-  V g_d = vsel(cond, vfma(tc_d, 4.73f, -20.87f), splat<V>(0.0f));
-  V g_n = vsel(cond, vfma(tc_n, 4.73f, -20.87f), splat<V>(0.0f));
+  const V cond = vstep_ge_and(in.t_d - in.t_n, 5.0f, x.window);  // 1 inside the window, else 0
+  V g_d = cond * vfma(tc_d, 4.73f, -20.87f);
+  V g_n = cond * vfma(tc_n, 4.73f, -20.87f);
   const V lim_d = 0.39f * a_d, lim_n = 0.39f * a_n;
   // |G| > 0.39 |A| switches G to 0.39 A (:239); within kGuard of equality the decision is
   // the double code's.  A_day > 0 gates both limits below (:245-252).
@@ -506,14 +529,15 @@ M16_HD typename MaskOf<V>::type step_core(const StepInV<V>& in, V tc_d, V tc_n,
   const V floor_n = -0.5f * a_d;
   r_n = vsel(mand(a_pos, vlt(r_n, floor_n)), floor_n, r_n);  // :248-252 (G := A_n + A_d / 2)
   const V omf = 1.0f - in.fpar;
+  const V gl = c.gl_sh * in.lai, gw = c.gl_wv * in.lai;  // shared by the two half-days
   M unused = mask_splat<V>(false);
   V gs_unused, ga_d, gb_d, ga_n, gb_n;
   o.day = half_fast<V, SEM, true, HAS_RC>(in.t_d, tc_d, in.vpd_d, in.fpar * a_d, omf * r_d,
-                                          in.rc_d, in.tmin, in.fpar, omf, in.lai, c, x, gate,
-                                          g_pos, need, gs_day, ga_d, gb_d);
+                                          in.rc_d, in.tmin, in.fpar, omf, in.lai, gl, gw, c, x,
+                                          gate, g_pos, need, gs_day, ga_d, gb_d);
   o.night = half_fast<V, SEM, false, HAS_RC>(in.t_n, tc_n, in.vpd_n, in.fpar * a_nc, omf * r_n,
-                                             in.rc_n, in.tmin, in.fpar, omf, in.lai, c, x, gate,
-                                             unused, need, gs_unused, ga_n, gb_n);
+                                             in.rc_n, in.tmin, in.fpar, omf, in.lai, gl, gw, c, x,
+                                             gate, unused, need, gs_unused, ga_n, gb_n);
   // every discontinuity guard in one compare: the smallest scaled distance to a switch
   const V dist = vminabs3(vminabs3(gd_d, gd_n, a_d), vminabs3(ga_d, gb_d, ga_n), gb_n);
   need = mor(need, vlt(dist, splat<V>(kGuard)));

@@ -52,7 +52,10 @@ constexpr int PIPE_THREADS = PIPE_CONSUMERS + 32;
 constexpr int PIPE_TILE = PIPE_CONSUMERS;  // pixels per block
 constexpr int PIPE_SUB = 2;                // time steps per stage (the two FFMA2 lanes)
 constexpr int PIPE_MAX_ARR = 14;
-constexpr int PIPE_MAX_STAGES = 5;
+#ifndef M16_PIPE_MAX_STAGES
+#define M16_PIPE_MAX_STAGES 5
+#endif
+constexpr int PIPE_MAX_STAGES = M16_PIPE_MAX_STAGES;
 constexpr int REDO_MARK = 0x7fc0dead;  // a NaN no arithmetic produces: "evaluate me exactly"
 constexpr int PIPE_QCAP = 512;             // deferred exact re-evaluations per block
 constexpr uint32_t PIPE_ROWB = PIPE_TILE * sizeof(float);  // bytes per array row
@@ -60,9 +63,11 @@ constexpr uint32_t PIPE_ROWB = PIPE_TILE * sizeof(float);  // bytes per array ro
 __host__ __device__ constexpr int pipe_n_arr(int extra) {
   return 11 + ((extra & 1) ? 1 : 0) + ((extra & 2) ? 2 : 0);
 }
-// as many stages as fit into 227 KB of shared memory next to ~6 KB of static data
+// as many stages as fit into 227 KB of shared memory next to ~8 KB of static data, at most
+// PIPE_MAX_STAGES (more copies in flight than that buy nothing)
 __host__ __device__ constexpr int pipe_n_stages(int extra) {
-  return pipe_n_arr(extra) == 11 ? 5 : 4;
+  const int fit = (int)((232448u - 8192u) / ((uint32_t)(PIPE_SUB * pipe_n_arr(extra)) * PIPE_ROWB));
+  return fit < PIPE_MAX_STAGES ? fit : PIPE_MAX_STAGES;
 }
 // stage slot of an optional array (the first eleven are fixed, see launch_pipe)
 __host__ __device__ constexpr int pipe_slot_swn(int extra) { return 11; }
