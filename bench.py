@@ -15,8 +15,18 @@ Printed by rank 0 as ONE JSON line: whole-job throughput with inputs resident in
 (`e2e`), the HBM roofline of the fused kernel (`roofline`), the numpy port of the reference
 timed on this box's host cores (`cpu_baseline`), SM clocks under load (`clocks`).
 
-`--impl reference` times the CPU implementation of the path (the numpy restatement of the
-reference in oracle/, all host cores) on a bounded sample of the same workload.
+The same line carries `secondary`: bounded runs of the other BASELINE.json configurations on
+the same box and ranks -- the reference's own call form (per-pixel parameter arrays), the
+float64 entry, the global 0.05 degree year pixel-tiled across the ranks with the
+transpiration gate all-reduced inside the timed region (T-chunked where it does not fit),
+and the objective batches K2 of the calibration and Sobol configurations (sharded by draw
+and by site under torchrun).
+
+`--impl reference` times the CPU implementation of the path -- the UNMODIFIED reference
+`MOD16._et` from oracle/_ref when it has been materialised (oracle/make_ref.py), else the
+numpy restatement in oracle/ -- on all host cores, on a bounded sample of the same workload,
+in the reference's stock precision (float32 drivers + float64 BPLUT: numpy promotes to
+float64) and with float32 parameters (float32 throughout); `value` is the faster leg.
 '''
 import argparse
 import json
@@ -58,10 +68,13 @@ def parse():
     ap.add_argument('--T', type=int, default=YEAR_T, help='time steps resident per GPU')
     ap.add_argument('--dtype', default='float32', choices=['float32', 'float64'])
     ap.add_argument('--kind', default='physical', choices=['physical', 'stress'])
-    ap.add_argument('--e2e-T', type=int, default=16, help='time steps of the end-to-end leg')
+    ap.add_argument('--e2e-T', type=int, default=YEAR_T,
+                    help='time steps of the end-to-end leg (bounded by free host memory)')
     ap.add_argument('--cpu-pixels', type=int, default=20000)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true',
+                    help='skip the bounded runs of the other configurations')
     ap.add_argument('--gate', default='global')
     ap.add_argument('--kernel', default='pipe', choices=['pipe', 'generic', 'mirror'],
                     help='f32 kernel variant (profiling): bulk-copy pipeline (default), strided '
@@ -124,48 +137,80 @@ class ClockSampler(threading.Thread):
 _CPU_DATA = {}
 
 
-def _cpu_prepare(key, seed, T, n, kind):
-    'Builds (once per process) the inputs of the numpy port for one pixel chunk.'
+def _cpu_model():
+    '''
+    The CPU implementation that is timed: the unmodified reference (oracle/_ref, made by
+    oracle/make_ref.py in the build container) or, when that is absent, the numpy port.
+    Returns (callable `_et(params, *drivers)`, kind).
+    '''
+    from oracle import make_ref
+    mod = make_ref.load()
+    if mod is not None:
+        return mod.MOD16._et, 'reference'
+    from oracle import mod16_oracle as orc
+    return orc.static_et, 'port'
+
+
+def _cpu_prepare(key, seed, T, n, kind, par_dtype):
+    'Builds (once per process) the inputs of the CPU model for one pixel chunk.'
     if key not in _CPU_DATA:
         from mod16_b200 import synthetic
         d = synthetic.host_drivers(T, n, seed, kind=kind, dtype=np.float32)
         table = bplut_table()
         pft = synthetic.host_pft_map(n, seed + 1)
-        vec = [table[i][pft].reshape(1, n) for i in range(11)]
+        # the reference callers' form: params[key][pft_map].reshape((1, N))
+        vec = [table[i][pft].reshape(1, n).astype(par_dtype) for i in range(11)]
         _CPU_DATA[key] = (vec, [d[k] for k in synthetic.DRIVER_NAMES])
     return _CPU_DATA[key]
 
 
 def _cpu_chunk(args):
     """
-    One worker: the numpy port of the reference `_et` on its pixel chunk.  With run=False
-    only the inputs are built, so that the timed region holds the model evaluation alone.
+    One worker: `_et` on its pixel chunk.  With run=False only the inputs are built, so that
+    the timed region holds the model evaluation alone.  par_dtype float64 is the reference's
+    stock path (numpy promotes the float32 drivers), float32 computes in float32 throughout.
     """
-    seed, T, n, kind, run = args
-    from oracle import mod16_oracle as orc
-    vec, drv = _cpu_prepare((os.getpid(), T, n, kind), seed + os.getpid() % 9973, T, n, kind)
+    seed, T, n, kind, run, par_dtype = args
+    fn, _ = _cpu_model()
+    vec, drv = _cpu_prepare((os.getpid(), T, n, kind, par_dtype), seed + os.getpid() % 9973, T, n,
+                            kind, np.dtype(par_dtype))
     if not run:
         return 0.0, 0.0
     t0 = time.perf_counter()
     with np.errstate(all='ignore'):
-        out = orc.static_et(vec, *drv)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            out = fn(vec, *drv)
     dt = time.perf_counter() - t0
     return dt, float(np.nansum(out))
 
 
 def cpu_single(T, n, kind):
-    _cpu_chunk((16002, T, n, kind, False))
-    dt, _ = _cpu_chunk((16002, T, n, kind, True))
-    return {'value': T * n / dt, 'unit': 'pixel-timesteps/s', 'cores': 1, 'kind': 'port',
-            'sample': 'numpy port of MOD16._et (oracle/mod16_oracle.py), float32 drivers + '
-                      'float64 per-pixel BPLUT parameters, %d pixels x %d steps of the '
-                      'workload, 1 process, numpy %s' % (n, T, np.__version__)}
+    _, impl = _cpu_model()
+    legs = {}
+    for par_dtype in ('float64', 'float32'):
+        _cpu_chunk((16002, T, n, kind, False, par_dtype))
+        dt, _ = _cpu_chunk((16002, T, n, kind, True, par_dtype))
+        legs[par_dtype] = T * n / dt
+    best = max(legs, key=legs.get)
+    return {'value': legs[best], 'unit': 'pixel-timesteps/s', 'cores': 1, 'kind': impl,
+            'legs': {'f64_stock_promotion': legs['float64'], 'f32_throughout': legs['float32']},
+            'sample': '%s MOD16._et, per-pixel BPLUT parameters (1, N), %d pixels x %d steps of '
+                      'the workload, 1 process, numpy %s; value = the faster of the two legs '
+                      '(%s parameters)' % (
+                          'unmodified reference (oracle/_ref)' if impl == 'reference' else
+                          'numpy port (oracle/mod16_oracle.py) of', n, T, np.__version__, best)}
 
 
 def run_reference(args):
     'The reference arm: the CPU implementation of the path on all host cores.'
     import multiprocessing as mp
     cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
     T, n = args.T, args.cpu_pixels
     try:  # the numpy path holds ~42 full-size temporaries: bound the sample by free memory
         import psutil
@@ -173,34 +218,54 @@ def run_reference(args):
         n = int(max(256, min(n, budget / (400.0 * T))))
     except Exception:
         pass
+    _, impl = _cpu_model()
     ctx = mp.get_context('spawn')
+    legs = {}
     with ctx.Pool(cores) as pool:
-        jobs = lambda run: [(16002, T, n, args.kind, run)] * cores
-        pool.map(_cpu_chunk, jobs(False), chunksize=1)      # imports, inputs, page-in
-        for _ in range(args.warmup):
-            pool.map(_cpu_chunk, jobs(True), chunksize=1)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pool.map(_cpu_chunk, jobs(True), chunksize=1)
-        wall = time.perf_counter() - t0
+        for par_dtype in ('float64', 'float32'):
+            jobs = lambda run: [(16002, T, n, args.kind, run, par_dtype)] * cores
+            pool.map(_cpu_chunk, jobs(False), chunksize=1)      # imports, inputs, page-in
+            for _ in range(args.warmup):
+                pool.map(_cpu_chunk, jobs(True), chunksize=1)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                pool.map(_cpu_chunk, jobs(True), chunksize=1)
+            legs[par_dtype] = time.perf_counter() - t0
     units = args.steps * cores * T * n
+    best = min(legs, key=legs.get)
+    wall = legs[best]
     value = units / wall
-    sample = ('numpy port of MOD16._et (oracle/mod16_oracle.py; the Python reference itself '
-              'cannot travel to the GPU box), %d processes x %d pixels x %d steps per bench '
-              'step, float32 drivers + float64 per-pixel parameters, numpy %s' % (
-                  cores, n, T, np.__version__))
+    sample = ('%s MOD16._et through its public call form (per-pixel parameter arrays (1, N)), '
+              '%d processes x %d pixels x %d steps per bench step; float32 drivers; value = the '
+              'faster leg (%s parameters); numpy %s' % (
+                  'unmodified reference (oracle/_ref/mod16)' if impl == 'reference' else
+                  'numpy port (oracle/mod16_oracle.py; oracle/_ref absent) of', cores, n, T,
+                  best, np.__version__))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'pixel-timesteps/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * wall / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': workload_name(args), 'sample_units_per_step': cores * T * n},
+        'vs_baseline': None, 'dtype': 'f32' if best == 'float32' else 'f64', 'data': 'synthetic',
+        'config': bench_config(args, args.gpus, args.pixels, args.T),
         'cpu_baseline': {'value': value, 'unit': 'pixel-timesteps/s', 'cores': cores,
-                         'kind': 'port', 'sample': sample},
+                         'kind': impl, 'sample': sample,
+                         'sample_units_per_step': cores * T * n,
+                         'legs': {'f64_stock_promotion': units / legs['float64'],
+                                  'f32_throughout': units / legs['float32']}},
         'e2e': {'value': value, 'unit': 'pixel-timesteps/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
     emit(json.dumps(line))
+
+
+def bench_config(args, world, N, T):
+    'The `config` object of the headline line -- the same for both arms.'
+    bpu = BYTES_PER_UNIT_F32 * (2 if args.dtype == 'float64' else 1)
+    return {'workload': workload_name(args), 'pixels_per_gpu': N, 'steps_per_gpu': T,
+            'units_per_step': float(T) * N * (world if args.workload != 'global' else 1),
+            'gate': args.gate,
+            'l2': 'inputs (%.1f GB per GPU) exceed L2 (126 MB); no flush needed' % (
+                bpu * T * N / 1e9)}
 
 
 def workload_name(args):
@@ -214,44 +279,41 @@ def workload_name(args):
 
 
 # ---- K2: objective batch (BASELINE configs 4 and 5) ---------------------------------------
-def run_objective_bench(args):
-    '''
-    `--workload calibration`: D = 10^5 draws x 300 sites x 3652 days (30 % of the observations
-    missing and removed by the compaction), tmin_close / tmin_open / vpd_open fixed;
-    `--workload sobol`: D = 2^16 rows x 1000 pixels x 365 days, all eleven parameters free.
+def objective_bench(workload, *, dev, world, rank, shard='draw', draws=None, dtype='float32',
+                    steps=3, warm=1, cpu_draws=2):
+    """
+    `calibration`: D = 10^5 draws x 300 sites x 3652 days (30 % of the observations missing
+    and removed by the compaction), tmin_close / tmin_open / vpd_open fixed;
+    `sobol`: D = 2^16 rows x 1000 pixels x 365 days, all eleven parameters free.
     One step = one `mod16_objective_batch_f32` call (all its launches) with drivers,
     observations and draws resident in HBM; the unit is draw-elements/s over the VALID
-    elements.  Under torchrun `--shard draw` gives every rank all sites and D / world draws
-    (all-gather of the results, no data-path collective), `--shard site` gives every rank
+    elements.  With world > 1 `shard='draw'` gives every rank all sites and D / world draws
+    (all-gather of the results, no data-path collective), `shard='site'` gives every rank
     N / world sites and all draws (ONE all-reduce of the (D, 5) un-gated statistics, then each
     draw's gate over all shards); the job is the same at every world size (strong scaling).
-    The bound is FP32 issue, not HBM: no `roofline` object is claimed for this line.
-    '''
+    The bound is the FP32 pipe (packed instructions) together with the special-function
+    unit, not HBM: `pipe` reports the fraction of the packed-FP32 issue rate the kernel's
+    51 packed instructions per pair of draws and element amount to.
+    Returns the result dict on rank 0, None elsewhere.
+    """
     import torch
+    import torch.distributed as dist
     from mod16_b200 import synthetic, utils, MOD16
     from mod16_b200.objective import ObjectiveBackend
     from mod16_b200.forward import run_forward
-    import torch.distributed as dist
     from mod16_b200 import distributed as mdist
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    if args.workload == 'calibration':
+    if workload == 'calibration':
         T, N, D, seed, fixed = 3652, 300, 100000, 16004, ('tmin_close', 'tmin_open', 'vpd_open')
     else:
         T, N, D, seed, fixed = 365, 1000, 65536, 16005, ()
-    D = args.draws or D
-    t_dtype = torch.float32 if args.dtype == 'float32' else torch.float64
-    steps, warm = min(args.steps, 5), min(max(args.warmup, 1), 3)
+    D = draws or D
+    t_dtype = torch.float32 if dtype == 'float32' else torch.float64
     table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51), MOD16.required_parameters,
                               default_beta=250.0)
     col = np.array(table[:, 7])
     d = synthetic.device_drivers(T, N, seed, dev, dtype=t_dtype)
     drv = [d[k] for k in synthetic.DRIVER_NAMES]
-    truth = run_forward(drv, params=list(col), dtype=np.dtype(args.dtype), device=dev,
+    truth = run_forward(drv, params=list(col), dtype=np.dtype(dtype), device=dev,
                         as_torch=True)[0]
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -259,36 +321,41 @@ def run_objective_bench(args):
     obs[obs < 0] = float('nan')
     obs[torch.rand(truth.shape, generator=g, device=dev) < 0.3] = float('nan')
     w = 0.2 + 0.8 * torch.rand(truth.shape, generator=g, device=dev, dtype=t_dtype)
-    draws = torch.from_numpy(synthetic.host_param_draws(D, seed, bplut_column=col,
-                                                        fixed=fixed)).to(dev)
+    pdraws = torch.from_numpy(synthetic.host_param_draws(D, seed, bplut_column=col,
+                                                         fixed=fixed)).to(dev)
     # (every rank generated the same data: same seeds)
-    if world > 1 and args.shard == 'site':
+    if world > 1 and shard == 'site':
         lo, hi = mdist.pixel_range(N, rank, world, align=1)
         local = mdist.shard_pixels(drv, lo, hi)
-        backend = ObjectiveBackend(local, obs[:, lo:hi], w[:, lo:hi], dtype=np.dtype(args.dtype),
+        backend = ObjectiveBackend(local, obs[:, lo:hi], w[:, lo:hi], dtype=np.dtype(dtype),
                                    device=dev)
-        run = lambda: mdist.objective_site_sharded(backend, draws)
+        run = lambda: mdist.objective_site_sharded(backend, pdraws)
     elif world > 1:
-        backend = ObjectiveBackend(drv, obs, w, dtype=np.dtype(args.dtype), device=dev)
-        run = lambda: mdist.objective_draw_sharded(backend, draws)
+        backend = ObjectiveBackend(drv, obs, w, dtype=np.dtype(dtype), device=dev)
+        run = lambda: mdist.objective_draw_sharded(backend, pdraws)
     else:
-        backend = ObjectiveBackend(drv, obs, w, dtype=np.dtype(args.dtype), device=dev)
-        run = lambda: backend(draws, as_torch=True)
+        backend = ObjectiveBackend(drv, obs, w, dtype=np.dtype(dtype), device=dev)
+        run = lambda: backend(pdraws, as_torch=True)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
     for _ in range(warm):
         sse, cnt = run()
     barrier()
+    sampler.active.set()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         sse, cnt = run()
     e1.record()
     barrier()
+    sampler.active.clear()
+    sampler.stop()
     tm = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -296,39 +363,64 @@ def run_objective_bench(args):
     valid = float(cnt.max().item())
     units = valid * D
     rm = torch.sqrt(sse / cnt)
-
+    if rank != 0:
+        return None
     # the reference loop on the host: one numpy `_et` + nanmean per draw
     cpu = None
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    if args.cpu_draws > 0:
+    if cpu_draws > 0:
         from oracle import mod16_oracle as orc
+        fn, impl = _cpu_model()
         h = [v.cpu().numpy().astype(np.float64) if isinstance(v, torch.Tensor) else v for v in drv]
         ho, hw = obs.cpu().numpy().astype(np.float64), w.cpu().numpy().astype(np.float64)
-        hd = draws[:args.cpu_draws].cpu().numpy()
+        hd = pdraws[:cpu_draws].cpu().numpy()
         t0 = time.perf_counter()
         ref = []
         with np.errstate(all='ignore'):
             for x in hd:
-                s, c = orc.objective_stats(orc.static_et(list(x), *h), ho, hw)
-                ref.append(np.sqrt(s / c))
+                sr, cr = orc.objective_stats(fn(list(x), *h), ho, hw)
+                ref.append(np.sqrt(sr / cr))
         dt = time.perf_counter() - t0
-        got = rm[:args.cpu_draws].cpu().numpy()
-        cpu = {'value': args.cpu_draws * T * N / dt, 'unit': 'draw-elements/s (all elements)',
-               'cores': 1, 'kind': 'port', 'sample': '%d draws' % args.cpu_draws,
+        got = rm[:cpu_draws].cpu().numpy()
+        cpu = {'value': cpu_draws * T * N / dt, 'unit': 'draw-elements/s (all elements)',
+               'cores': 1, 'kind': impl, 'sample': '%d draws' % cpu_draws,
                'rmsd_max_abs_diff': float(np.max(np.abs(got - np.array(ref))))}
-    emit(json.dumps({
-        'metric': 'draw-elements/s (objective batch)', 'value': units / (ms * 1e-3),
-        'unit': 'draw-elements/s', 'n_gpus': world, 'shard': args.shard if world > 1 else None,
+    clocks = sampler.summary()
+    # packed-FP32 pipe: one FFMA2-class warp instruction per two clocks per SM sub-partition
+    # = 32 lanes x 2 draws... per pair of draws and element the fast kernel issues 51 packed
+    # instructions: rate bound = 148 SMs x 4 x clk / 2 x 32 pairs x 2 draws / 51
+    clk = (clocks['sm_mhz'] or 1965.0) * 1e6
+    pipe_peak = 148 * 4 * clk / 2.0 * 64.0 / 51.0 * world
+    value = units / (ms * 1e-3)
+    return {
+        'metric': 'draw-elements/s (objective batch)', 'value': value,
+        'unit': 'draw-elements/s', 'n_gpus': world, 'shard': shard if world > 1 else None,
         'scaling': 'strong', 'steps': steps, 'warmup': warm, 'ms_per_step': ms,
         'higher_is_better': True, 'vs_baseline': None, 'data': 'synthetic',
-        'dtype': 'f32' if args.dtype == 'float32' else 'f64',
-        'config': {'workload': args.workload, 'draws': D, 'T': T, 'N': N,
+        'dtype': 'f32' if dtype == 'float32' else 'f64',
+        'config': {'workload': workload, 'draws': D, 'T': T, 'N': N,
                    'valid_elements': valid, 'all_elements': T * N},
         'rmsd_range': [float(rm.min().item()), float(rm.max().item())],
-        'cpu_baseline': cpu}))
+        'pipe': {'bound': 'fp32 packed issue (FFMA2 class, 1 per 2 clk per SM sub-partition)',
+                 'achieved': value, 'peak': pipe_peak, 'unit': 'draw-elements/s',
+                 'frac': value / pipe_peak, 'packed_instructions_per_pair_element': 51},
+        'clocks': clocks, 'cpu_baseline': cpu}
+
+
+def run_objective_bench(args):
+    'Stand-alone `--workload calibration|sobol` line.'
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    res = objective_bench(args.workload, dev=dev, world=world, rank=rank, shard=args.shard,
+                          draws=args.draws, dtype=args.dtype, steps=min(args.steps, 5),
+                          warm=min(max(args.warmup, 1), 3), cpu_draws=args.cpu_draws)
+    if res is not None:
+        emit(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 
@@ -384,6 +476,238 @@ def emit(line):
         print(line, flush=True)
 
 
+def fill_synthetic(bufs, rows, N, seed, device, torch_dtype, kind):
+    'Writes `rows` time steps of synthetic per-step drivers into the buffers, slab by slab.'
+    from mod16_b200 import synthetic
+    slab = max(1, min(rows, (1 << 27) // max(N, 1)))
+    for t0 in range(0, rows, slab):
+        t1 = min(rows, t0 + slab)
+        d = synthetic.device_drivers(t1 - t0, N, seed + t0, device, kind=kind, dtype=torch_dtype)
+        for k, v in bufs.items():
+            v[t0:t1].copy_(d[k])
+        del d
+
+
+def all_ok(ok, world, device):
+    'True when every rank says so (one int all-reduce): ranks skip a leg together or not at all.'
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return bool(ok)
+    t = torch.tensor([1 if ok else 0], device=device, dtype=torch.int32)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        return json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def global_year(args, device, world, rank, steps, warm):
+    """
+    BASELINE configs[2]: the global 0.05 degree CMG grid (7200 x 3600 pixels) x 365 daily
+    steps as ONE `_et` call, pixel-tiled across the ranks (strong scaling).  A rank's shard
+    that does not fit in HBM (one or two GPUs) is walked in T-chunks through two alternating
+    buffer sets (mod16_b200/chunked.py); the transpiration gate is evaluated
+    over all chunks and ranks -- its all-reduce is inside the timed region.  Throughput is
+    over the device time of the kernels and the gate exchange; refilling a buffer set with
+    the next chunk's synthetic drivers is not in it ("kernel time over
+    resident chunks").
+    """
+    import torch
+    import torch.distributed as dist
+    from mod16_b200 import synthetic
+    from mod16_b200.chunked import ChunkedForward, PER_STEP
+    from mod16_b200.distributed import pixel_range
+    np_dtype = np.dtype(args.dtype)
+    t_dtype = torch.float32 if np_dtype == np.float32 else torch.float64
+    T = args.T
+    lo, hi = pixel_range(7200 * 3600, rank, world)
+    N = hi - lo
+    free, total = torch.cuda.mem_get_info(device)
+    out_bytes = T * N * np_dtype.itemsize
+    budget = int(min(free, 170e9) - out_bytes - 6e9)
+    resident = len(PER_STEP) * T * N * np_dtype.itemsize <= budget
+    err = None
+    cf = out = None
+    try:
+        table = bplut_table()
+        pft = torch.from_numpy(synthetic.host_pft_map(N, 16002 + rank)).to(device)
+        g = torch.Generator(device=device)
+        g.manual_seed(16002 + rank)
+        lo_b, hi_b = synthetic.BOUNDS['temp_annual']
+        t_ann = torch.empty(N, device=device, dtype=t_dtype).uniform_(lo_b, hi_b, generator=g)
+        lo_b, hi_b = synthetic.BOUNDS['pressure']
+        prs = torch.empty(N, device=device, dtype=t_dtype).uniform_(lo_b, hi_b, generator=g)
+        cf = ChunkedForward(T, N, table, pft, t_ann, prs, device=device, dtype=np_dtype,
+                            budget_bytes=budget, n_buffers=1 if resident else 2)
+        out = torch.empty((T, N), device=device, dtype=t_dtype)
+    except Exception as exc:  # (out of memory on a small GPU ...)
+        err = '%s: %s' % (type(exc).__name__, exc)
+    if not all_ok(err is None, world, device):
+        return {'name': 'global', 'error': err or 'another rank failed to set up'}
+    filled = set()
+
+    def fill(k, t0, t1, bufs):
+        if resident and k in filled:
+            return          # the whole shard stays resident between steps
+        fill_synthetic(bufs, t1 - t0, N, 16002 + 1000 * rank + 7 * t0, device, t_dtype, args.kind)
+        filled.add(k)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(device.index)
+    sampler.start()
+    for _ in range(warm):
+        cf.run(fill, out)
+    barrier()
+    sampler.active.set()
+    ms = 0.0
+    for _ in range(steps):
+        cf.run(fill, out)
+        ms += cf.kernel_ms
+    barrier()
+    sampler.active.clear()
+    sampler.stop()
+    tm = torch.tensor([ms / steps], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item())
+    probe = out[:1, :4096].float().cpu().numpy()
+    assert np.isfinite(probe).all() and 0 < np.abs(probe).mean() < 1e3, 'implausible ET'
+    units = float(T) * 7200 * 3600
+    bpu = BYTES_PER_UNIT_F32 * (2 if np_dtype == np.float64 else 1)
+    peak, peak_src = hbm_peak()
+    achieved = bpu * units / (ms * 1e-3) / 1e9
+    res = {
+        'name': 'global', 'metric': METRIC, 'value': units / (ms * 1e-3),
+        'unit': 'pixel-timesteps/s', 'n_gpus': world, 'scaling': 'strong', 'steps': steps,
+        'warmup': warm, 'ms_per_step': ms, 'dtype': 'f32' if np_dtype == np.float32 else 'f64',
+        'config': {'workload': 'global 0.05 deg CMG grid 7200x3600 x %d daily steps, one `_et` '
+                               'call pixel-tiled across %d rank(s), synthetic %s drivers' % (
+                                   T, world, args.kind),
+                   'pixels_per_gpu': N, 'units_per_step': units,
+                   'time_chunks_per_rank': [list(c) for c in cf.chunks],
+                   'resident': resident,
+                   'timed': 'device time of the chunk kernels + the cross-rank gate all-reduce '
+                            '(max over ranks)%s' % ('' if resident else
+                                                     '; refills between chunks not included'),
+                   'gate': 'global (open pass per chunk, all-reduce(max) of one int over %d '
+                           'rank(s), closed pass only if nobody transpired)' % world},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak * world, 'unit': 'GB/s',
+                     'frac': achieved / (peak * world), 'peak_source': peak_src,
+                     'frac_of_spec_8tbs': achieved / (8000.0 * world),
+                     'kernel': 'forward_pipe_kernel', 'bytes_per_unit': bpu},
+        'gpu_launches': cf.launches * steps, 'comm': {'collective': 'all_reduce(max) int32[1]',
+                                                       'per_step': 1, 'nranks': world},
+        'clocks': sampler.summary()}
+    del cf, out
+    torch.cuda.empty_cache()
+    return res if rank == 0 else None
+
+
+def secondary_lines(args, device, world, rank, drv_list, drv, pft, table, out):
+    """
+    Bounded runs of the other BASELINE.json configurations (and of the other entry points of
+    the headline one) on the same box and ranks; each entry carries its own timing, roofline
+    or pipe fraction and clocks.  `drv_list` is the resident float32 tile-year of the
+    headline; it is released before the legs that need the memory.
+    """
+    import torch
+    import torch.distributed as dist
+    from mod16_b200 import synthetic
+    from mod16_b200.forward import run_forward
+    lines = []
+    T, N = out.shape
+    peak, peak_src = hbm_peak()
+
+    def timed(fn, steps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tm = torch.tensor([e0.elapsed_time(e1) / steps], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm.item())
+
+    # (1) the reference's own call form: MOD16._et(params, *drivers) with per-pixel parameter
+    #     arrays params[k] = table[k][pft_map].reshape(1, N) (Forward_Run_example.ipynb cell 32)
+    err = None
+    try:
+        tab_t = torch.from_numpy(np.asarray(table, np.float32)).to(device)
+        vec = [tab_t[k][pft.long()].reshape(1, N).contiguous() for k in range(11)]
+        flag = torch.zeros(1, device=device, dtype=torch.int32)
+        ref_out = out[:2].clone()
+        fn = lambda: run_forward(drv_list, params=vec, semantics='static', out_mode='sum',
+                                 gate='global', dtype=np.float32, device=device,
+                                 gate_flag=flag, out=[out])
+    except Exception as exc:
+        err = '%s: %s' % (type(exc).__name__, exc)
+    if all_ok(err is None, world, device):
+        ms = timed(fn, 5)
+        diff = float((torch.nan_to_num(out[:2]) - torch.nan_to_num(ref_out)).abs().max().item())
+        ach = BYTES_PER_UNIT_F32 * T * N / (ms * 1e-3) / 1e9
+        if rank == 0:
+            lines.append({
+                'name': 'tile-year, reference call form (per-pixel parameter arrays)',
+                'metric': METRIC, 'value': world * T * N / (ms * 1e-3),
+                'unit': 'pixel-timesteps/s', 'n_gpus': world, 'ms_per_step': ms, 'steps': 5,
+                'dtype': 'f32', 'max_abs_diff_vs_pft_gather_w_m2': diff,
+                'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                             'frac': ach / peak, 'kernel': 'forward_pipe_kernel',
+                             'peak_source': peak_src}})
+        del vec
+    else:
+        lines.append({'name': 'tile-year, reference call form', 'error': err})
+
+    # (2) the float64 entry (1e-10 path) on a slab of the same tile
+    err = None
+    try:
+        Ts = 16
+        d64 = [v[:Ts].double() if isinstance(v, torch.Tensor) and v.ndim == 2 else
+               (v.double() if isinstance(v, torch.Tensor) else v) for v in drv_list]
+        out64 = torch.empty((Ts, N), device=device, dtype=torch.float64)
+        flag = torch.zeros(1, device=device, dtype=torch.int32)
+        fn = lambda: run_forward(d64, pft=pft, table=table, semantics='static', out_mode='sum',
+                                 gate='global', dtype=np.float64, device=device,
+                                 gate_flag=flag, out=[out64])
+    except Exception as exc:
+        err = '%s: %s' % (type(exc).__name__, exc)
+    if all_ok(err is None, world, device):
+        ms = timed(fn, 3, warm=1)
+        ach = 2 * BYTES_PER_UNIT_F32 * Ts * N / (ms * 1e-3) / 1e9
+        if rank == 0:
+            lines.append({
+                'name': 'float64 entry, %d-step slab of the tile' % Ts, 'metric': METRIC,
+                'value': world * Ts * N / (ms * 1e-3), 'unit': 'pixel-timesteps/s',
+                'n_gpus': world, 'ms_per_step': ms, 'steps': 3, 'dtype': 'f64',
+                'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                             'frac': ach / peak, 'kernel': f64_kernel_name(),
+                             'peak_source': peak_src, 'bytes_per_unit': 96}})
+        del d64, out64
+    else:
+        lines.append({'name': 'float64 entry', 'error': err})
+    return lines
+
+
+def f64_kernel_name():
+    return 'forward_strided_kernel<double>'
+
+
 def main():
     global _OUT
     args = parse()
@@ -416,17 +740,18 @@ def main():
         dist.init_process_group('nccl', device_id=device)
     _abi.load()
 
+    if args.workload == 'global':
+        res = global_year(args, device, world, rank, args.steps, max(args.warmup, 3))
+        if rank == 0:
+            res.update({'higher_is_better': True, 'vs_baseline': None, 'data': 'synthetic'})
+            emit(json.dumps(res))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     np_dtype = np.dtype(args.dtype)
     t_dtype = torch.float32 if np_dtype == np.float32 else torch.float64
     T, N = args.T, args.pixels
-    if args.workload == 'global':
-        from mod16_b200.distributed import pixel_range
-        lo, hi = pixel_range(7200 * 3600, rank, world)
-        N = hi - lo
-        need = 48.0 * T * N / 1e9
-        if need > 170.0:
-            raise SystemExit('global workload: %.0f GB per GPU do not fit; use more GPUs or '
-                             'a smaller --T' % need)
     table = bplut_table()
     pft = torch.from_numpy(synthetic.host_pft_map(N, 16002 + rank)).to(device)
     drv = resident_drivers(T, N, 16002 + 1000 * rank, device, t_dtype, args.kind)
@@ -442,18 +767,6 @@ def main():
              'mirror': _abi.FORCE_MIRROR}[args.kernel]
 
     def step():
-        if args.workload == 'global' and args.gate == 'global' and world > 1:
-            # one reference call over the WHOLE grid: the transpiration gate is evaluated
-            # across the ranks (open pass, all-reduce(max) of one int, fix-up pass)
-            run_forward(drv_list, pft=pft, table=table, semantics='static', out_mode='sum',
-                        gate='open_track', dtype=np_dtype, device=device, gate_flag=flag,
-                        out=[out], force=force)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-            run_forward(drv_list, pft=pft, table=table, semantics='static', out_mode='sum',
-                        gate='fixup', dtype=np_dtype, device=device, gate_flag=flag,
-                        out=[out], force=force)
-            flag.zero_()
-            return
         run_forward(drv_list, pft=pft, table=table, semantics='static', out_mode='sum',
                     gate=args.gate, dtype=np_dtype, device=device, gate_flag=flag, out=[out],
                     force=force)
@@ -487,30 +800,26 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     total_ms = float(tm.item())
     units_per_rank = T * N
-    tu = torch.tensor([units_per_rank], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tu, op=dist.ReduceOp.SUM)
-    units_total = float(tu.item())
+    units_total = float(units_per_rank) * world
     value = units_total * args.steps / (total_ms * 1e-3)
     bytes_per_unit = BYTES_PER_UNIT_F32 * (2 if np_dtype == np.float64 else 1)
     kernel_ms = float(np.mean(step_ms))
     achieved = bytes_per_unit * units_per_rank / (kernel_ms * 1e-3) / 1e9
 
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
-    # (bytes per pixel-timestep x the units of one launch), see profiles/traffic.json
-    traffic = None
+    # (bytes per pixel-timestep x the units of one launch), see profiles/traffic.json; the
+    # entry names the commit of the kernel source it was captured from
+    traffic = traffic_src = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
     kname = ('forward_pipe_kernel' if args.kernel == 'pipe' else args.kernel) \
-        if np_dtype == np.float32 else 'forward_strided_kernel<double>'
+        if np_dtype == np.float32 else f64_kernel_name()
     if os.path.exists(tpath):
         rec = json.load(open(tpath)).get(kname)
         if rec:
             traffic = rec['dram_bytes_per_unit'] * units_per_rank
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json)'
-    else:
-        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+            traffic_src = '%s; kernel source at commit %s' % (
+                rec.get('source', ''), rec.get('kernel_source_commit', '?'))
+    peak, peak_src = hbm_peak()
 
     # a cheap sanity check that real work happened: ET of the resident block is finite
     # and of plausible size (the parity tests are the real check)
@@ -519,21 +828,36 @@ def main():
 
     e2e = None
     if not args.no_e2e:
+        # the whole resident block goes through the host: as many of its time steps as a
+        # third of the free host memory holds (pinned), all 365 on a box with >= 300 GB free
         Te = min(args.e2e_T, T)
+        try:
+            import psutil
+            room = psutil.virtual_memory().available / 3.0 / max(world, 1)
+            Te = max(4, min(Te, int(room // (12 * N * np_dtype.itemsize))))
+        except Exception:
+            Te = min(Te, 16)
+        tq = torch.tensor([Te], device=device, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(tq, op=dist.ReduceOp.MIN)
+        Te = int(tq.item())
         names = [k for k in synthetic.DRIVER_NAMES
                  if k not in synthetic.PER_PIXEL and k != 'sw_rad_night']
-        host = dict((k, drv[k][:Te].cpu().pin_memory()) for k in names)
+        host = {}
+        for k in names:
+            host[k] = torch.empty((Te, N), dtype=t_dtype, pin_memory=True)
+            host[k].copy_(drv[k][:Te])
         for k in synthetic.PER_PIXEL:
             host[k] = drv[k].cpu().pin_memory()
         host['sw_rad_night'] = 0
-        out_host = torch.empty((Te, N), dtype=t_dtype).pin_memory()
-        runner = StreamedForward(N, max(1, Te // 4), table, pft.cpu().numpy(), device=device,
+        out_host = torch.empty((Te, N), dtype=t_dtype, pin_memory=True)
+        slab = max(1, min(8, Te // 4))
+        runner = StreamedForward(N, slab, table, pft.cpu().numpy(), device=device,
                                  dtype=np_dtype, gate=args.gate)
-        for _ in range(2):
-            runner.run(host, out_host)
+        runner.run(host, out_host)
         barrier()
         runner.h2d_bytes = runner.d2h_bytes = runner.launches = 0
-        reps = max(3, min(args.steps, 10))
+        reps = 3 if Te > 64 else max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(reps):
             runner.run(host, out_host)
@@ -546,11 +870,13 @@ def main():
         e2e = {'value': world * reps * Te * N / dt, 'unit': 'pixel-timesteps/s',
                'h2d_bytes_per_step': runner.h2d_bytes // reps,
                'd2h_bytes_per_step': runner.d2h_bytes // reps,
-               'sample': '%d steps x %d pixels per GPU from pinned host memory through '
-                         'mod16_b200.streaming.StreamedForward (4 slabs, copies overlapped '
-                         'with the kernel)%s' % (Te, N, '' if numa is None else
-                                                 '; rank bound to NUMA node %d' % numa)}
+               'sample': '%d of the %d steps x %d pixels per GPU from pinned host memory through '
+                         'mod16_b200.streaming.StreamedForward (slabs of %d steps, copies '
+                         'overlapped with the kernel)%s' % (Te, T, N, slab, '' if numa is None
+                                                            else '; rank bound to NUMA node %d'
+                                                            % numa)}
         assert np.isfinite(out_host[:1, :4096].numpy()).all()
+        del host, out_host, runner
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:   # (reported at N = 1 only)
@@ -558,28 +884,46 @@ def main():
     sampler.stop()
     clocks = sampler.summary()
 
+    secondary = None
+    if not args.no_secondary and args.kernel == 'pipe' and np_dtype == np.float32:
+        secondary = secondary_lines(args, device, world, rank, drv_list, drv, pft, table, out)
+        del drv, drv_list, out
+        torch.cuda.empty_cache()
+        g_args = argparse.Namespace(**vars(args))
+        g_args.T = YEAR_T
+        legs = [lambda: global_year(g_args, device, world, rank, 2, 1)]
+        for wl in ('calibration', 'sobol'):
+            for shard in (('draw', 'site') if (world > 1 and wl == 'calibration') else ('draw',)):
+                legs.append(lambda wl=wl, shard=shard: objective_bench(
+                    wl, dev=device, world=world, rank=rank, shard=shard, steps=3, warm=1,
+                    cpu_draws=1 if world == 1 else 0))
+        for leg in legs:
+            res = leg()
+            torch.cuda.empty_cache()
+            if rank == 0 and res is not None:
+                secondary.append(res)
+
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'pixel-timesteps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'strong' if args.workload == 'global' else 'weak', 'vs_baseline': None,
+            'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32' if np_dtype == np.float32 else 'f64', 'data': 'synthetic',
-            'config': {'workload': workload_name(args), 'pixels_per_gpu': N, 'steps_per_gpu': T,
-                       'units_per_step': units_total, 'gate': args.gate,
-                       'l2': 'inputs (%.1f GB per GPU) exceed L2 (126 MB); no flush needed' % (
-                           bytes_per_unit * units_per_rank / 1e9)},
+            'config': bench_config(args, world, N, T),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                         'frac': achieved / peak, 'traffic': traffic,
+                         'traffic_source': traffic_src, 'peak_source': peak_src,
                          'frac_of_spec_8tbs': achieved / 8000.0,
                          'kernel': {'pipe': 'forward_pipe_kernel',
                                     'generic': 'forward_strided_fast_kernel',
                                     'mirror': 'forward_strided_kernel<float>'}[args.kernel]
-                                   if np_dtype == np.float32 else 'forward_strided_kernel<double>',
+                                   if np_dtype == np.float32 else f64_kernel_name(),
                          'kernel_ms': kernel_ms, 'bytes_per_unit': bytes_per_unit},
             'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
             'clocks': clocks, 'cpu_baseline': cpu,
             'wall_s_timed_region': t_wall,
+            'secondary': secondary,
         }
         emit(json.dumps(line))
     if world > 1:

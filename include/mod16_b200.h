@@ -139,6 +139,15 @@ typedef struct mod16_out {
 int mod16_abi_version(void);
 int64_t mod16_workspace_bytes(void); /* recommended size of mod16_out_t.workspace */
 int mod16_last_cuda_error(void);
+/* Which kernel the last mod16_forward_* call of this thread launched (for tests and
+   profiling): 0 none yet; MOD16_KERNEL_PIPE | (variant << 8) the bulk-copy pipeline
+   (variant bit 0: sw_rad_night streamed, bit 1: temp_annual / pressure streamed);
+   MOD16_KERNEL_STRIDED the float32 strided kernel; MOD16_KERNEL_EXACT the op-for-op kernel
+   (float64 entry, MOD16_FORCE_MIRROR). */
+#define MOD16_KERNEL_PIPE 1
+#define MOD16_KERNEL_STRIDED 2
+#define MOD16_KERNEL_EXACT 3
+int mod16_last_forward_kernel(void);
 const char* mod16_error_string(int code);
 
 /* K1 -- fused forward model over a (T, N) block of pixel-timesteps. */

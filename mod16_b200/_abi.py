@@ -16,6 +16,7 @@ OUT_SUM, OUT_DAY_NIGHT, OUT_COMPONENTS = 0x00, 0x10, 0x20
 GATE_GLOBAL, GATE_ELEMENT, GATE_OPEN, GATE_CLOSED = 0x000, 0x100, 0x200, 0x300
 GATE_OPEN_TRACK, GATE_FIXUP = 0x400, 0x500
 FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
+KERNEL_PIPE, KERNEL_STRIDED, KERNEL_EXACT = 1, 2, 3   # mod16_last_forward_kernel() & 0xff
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
@@ -89,6 +90,7 @@ EXPORTS = {
     'mod16_abi_version': (ctypes.c_int, []),
     'mod16_workspace_bytes': (ctypes.c_int64, []),
     'mod16_last_cuda_error': (ctypes.c_int, []),
+    'mod16_last_forward_kernel': (ctypes.c_int, []),
     'mod16_error_string': (ctypes.c_char_p, [ctypes.c_int]),
     'mod16_forward_f32': (ctypes.c_int, [
         ctypes.POINTER(Drivers), ctypes.POINTER(Params), ctypes.POINTER(Out),

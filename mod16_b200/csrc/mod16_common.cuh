@@ -11,6 +11,8 @@ namespace mod16 {
 
 // thread-local record of the last failed CUDA call (mod16_last_cuda_error())
 extern thread_local int g_last_cuda_error;
+// kernel chosen by the last forward call of this thread (mod16_last_forward_kernel())
+extern thread_local int g_last_forward_kernel;
 
 #define M16_CUDA_CHECK(expr)                                   \
   do {                                                         \

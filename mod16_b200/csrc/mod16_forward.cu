@@ -8,6 +8,7 @@
 namespace mod16 {
 
 thread_local int g_last_cuda_error = 0;
+thread_local int g_last_forward_kernel = 0;
 
 template <typename R, int SEM, int OUT>
 __global__ void __launch_bounds__(256)
@@ -139,6 +140,7 @@ static int launch_strided_out(const ForwardArgs<R>& a, uint32_t om, dim3 grid, d
 // One pass of the strided kernel with the gate settings already placed in `a`.
 template <typename R>
 int launch_strided(ForwardArgs<R>& a, uint32_t flags, cudaStream_t st) {
+  g_last_forward_kernel = MOD16_KERNEL_EXACT;
   if (a.T == 0 || a.N == 0) return MOD16_OK;
   const int threads = 256;
   const int64_t bx = (a.N + threads - 1) / threads;
@@ -208,6 +210,7 @@ extern "C" {
 int mod16_abi_version(void) { return MOD16_ABI_VERSION; }
 int64_t mod16_workspace_bytes(void) { return (int64_t)8 << 20; }
 int mod16_last_cuda_error(void) { return mod16::g_last_cuda_error; }
+int mod16_last_forward_kernel(void) { return mod16::g_last_forward_kernel; }
 
 const char* mod16_error_string(int code) {
   switch (code) {

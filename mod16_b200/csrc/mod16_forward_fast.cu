@@ -129,13 +129,15 @@ redo_sweep_kernel(const __grid_constant__ ForwardArgs<float> a) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// a (T, N) array the bulk copies can stream: unit pixel stride, every row 16-byte aligned
+// (rows need not be adjacent: a pixel range of a wider array qualifies)
 static bool dense_tn(const Arr<float>& d, int64_t T, int64_t N) {
-  return d.ptr && d.ns == 1 && aligned16(d.ptr) && (T == 1 || d.ts == N);
+  return d.ptr && d.ns == 1 && aligned16(d.ptr) && (T == 1 || (d.ts >= N && d.ts % 4 == 0));
 }
 
 // The pipelined kernel needs: N % 4 == 0 and 16-byte aligned bases (every bulk copy is a
-// multiple of 16 bytes at a 16-byte aligned address); the eleven per-step drivers dense
-// (T, N); sw_rad_night a scalar or dense; pressure and temp_annual both per pixel / scalar,
+// multiple of 16 bytes at a 16-byte aligned address); the eleven per-step drivers (T, N)
+// with unit pixel stride and 16-byte aligned rows; sw_rad_night a scalar or dense; pressure and temp_annual both per pixel / scalar,
 // or both dense (T, N) (the calibration's annual means, mod16/calibration.py:556-560);
 // parameters from the table (uniform or gathered by land cover) or per-pixel arrays (the
 // reference callers' `params[pft_map].reshape((1, N))`); no r_corr_list.
@@ -186,7 +188,15 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
     src.ptr[n_arr++] = a.drv[MOD16_D_TEMP_ANNUAL].ptr;
     src.ptr[n_arr++] = a.drv[MOD16_D_PRESSURE].ptr;
   }
-  for (int k = 0; k < n_arr; ++k) src.ts[k] = a.N;
+  {
+    int k = 0;
+    for (; k < 11; ++k) src.ts[k] = a.drv[order[k]].ts;
+    if (extra & 1) src.ts[k++] = a.drv[MOD16_D_SW_RAD_NIGHT].ts;
+    if (extra & 2) {
+      src.ts[k++] = a.drv[MOD16_D_TEMP_ANNUAL].ts;
+      src.ts[k++] = a.drv[MOD16_D_PRESSURE].ts;
+    }
+  }
   const int64_t bx = (a.N + PIPE_TILE - 1) / PIPE_TILE;
   if (bx > 2147483647LL) return MOD16_ERR_SHAPE;
   int64_t want_rows = (148 * 6 + bx - 1) / bx;
@@ -241,8 +251,12 @@ int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
   if (a.T == 0 || a.N == 0) return MOD16_OK;
   if (!(flags & MOD16_FORCE_GENERIC)) {
     const int extra = pipe_variant(a, flags);
-    if (extra >= 0) return launch_pipe(a, flags, extra, st);
+    if (extra >= 0) {
+      g_last_forward_kernel = MOD16_KERNEL_PIPE | (extra << 8);
+      return launch_pipe(a, flags, extra, st);
+    }
   }
+  g_last_forward_kernel = MOD16_KERNEL_STRIDED;
   const int threads = 256;
   const int64_t bx = (a.N + threads - 1) / threads;
   if (bx > 2147483647LL) return MOD16_ERR_SHAPE;

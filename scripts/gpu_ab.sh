@@ -5,7 +5,7 @@ out=gpurun_out
 mkdir -p $out
 timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_$tag.log 2>&1; echo "pytest exit $?"; tail -3 $out/pytest_$tag.log
 for k in pipe; do
-  timeout 600 python bench.py --steps 10 --warmup 3 --T 64 --no-cpu --no-e2e --kernel $k > $out/bench_${tag}_$k.json 2> $out/bench_${tag}_$k.err; echo "bench $k exit $?"
+  timeout 600 python bench.py --steps 10 --warmup 3 --T 64 --no-cpu --no-e2e --no-secondary --kernel $k > $out/bench_${tag}_$k.json 2> $out/bench_${tag}_$k.err; echo "bench $k exit $?"
   python - <<PY
 import json
 try:

@@ -3,7 +3,7 @@
 tag=$1; T=$2; shift; shift
 out=gpurun_out; mkdir -p $out
 for v in "$@"; do
-  MOD16_B200_LIB=$PWD/mod16_b200/lib/variants/lib$v.so timeout 600 python bench.py --steps 10 --warmup 3 --T $T --no-cpu --no-e2e > $out/bench_${tag}_$v.json 2> $out/bench_${tag}_$v.err; echo "bench $v exit $?"
+  MOD16_B200_LIB=$PWD/mod16_b200/lib/variants/lib$v.so timeout 600 python bench.py --steps 10 --warmup 3 --T $T --no-cpu --no-e2e --no-secondary > $out/bench_${tag}_$v.json 2> $out/bench_${tag}_$v.err; echo "bench $v exit $?"
   python - <<PY
 import json
 try:

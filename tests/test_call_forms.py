@@ -1,0 +1,229 @@
+'''
+GPU tests of the call forms the reference's own callers use, and of which kernel they reach
+(mod16_last_forward_kernel()):
+
+* `MOD16._et([params[k][pft_map].reshape((1, N)) ...], *drivers)` -- per-pixel parameter
+  arrays, notebooks/MOD16_Forward_Run_example.ipynb cells 32 / 35 -- must run on the
+  bulk-copy pipeline like the land-cover gather does;
+* (T, N) `temp_annual` / `pressure` (the annual means of mod16/calibration.py:556-560
+  broadcast to the drivers' shape);
+* a pixel range of a wider array (what a rank of a pixel-sharded run holds);
+* negative VPD and negative (fill) temperatures, which the fast path now decides itself;
+* the T-chunked plan of mod16_b200/chunked.py against one call on the whole block;
+* the NCCL code paths of mod16_b200/distributed.py in a world of one rank.
+'''
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import parity
+from mod16_b200 import MOD16, _abi, synthetic, utils
+from mod16_b200.forward import run_forward
+from oracle import mod16_oracle as orc
+
+pytestmark = pytest.mark.gpu
+NAMES = list(synthetic.DRIVER_NAMES)
+
+
+def _table():
+    return utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51), MOD16.required_parameters,
+                             default_beta=250.0)
+
+
+def _d64(drv):
+    return [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
+
+
+def _kernel(lib):
+    k = lib.mod16_last_forward_kernel()
+    return k & 0xff, k >> 8
+
+
+@pytest.mark.parametrize('N', [4096, 4100, 484])
+def test_reference_call_form_reaches_the_pipeline(cuda_lib, N):
+    T = 21
+    d = synthetic.host_drivers(T, N, 31, dtype=np.float32)
+    drv = [d[k] for k in NAMES]
+    table = _table()
+    pft = synthetic.host_pft_map(N, 32)
+    vec = [table[i][pft].reshape(1, N) for i in range(11)]
+    with np.errstate(all='ignore'):
+        ref = orc.static_et(vec, *_d64(drv))
+    # float64 parameter arrays + float32 drivers promote like numpy: ask for float32
+    got = MOD16._et(vec, *drv, dtype=np.float32)
+    assert _kernel(cuda_lib) == (_abi.KERNEL_PIPE, 0)
+    parity.assert_parity(got, ref, np.float32, what='per-pixel parameter arrays')
+    by_pft = MOD16._et_by_pft(table, pft, *drv, dtype=np.float32)
+    assert _kernel(cuda_lib) == (_abi.KERNEL_PIPE, 0)
+    # the float32 copies of the parameters differ from the table's doubles in the last bit
+    assert np.allclose(got, by_pft, rtol=2e-5, atol=1e-3)
+    # instance semantics, day / night
+    vec32 = [v.astype(np.float32) for v in vec]
+    run_forward(drv, params=vec32, semantics='instance', out_mode='day_night')
+    assert _kernel(cuda_lib) == (_abi.KERNEL_PIPE, 0)
+
+
+def test_time_varying_annual_temperature_and_pressure(cuda_lib):
+    T, N = 37, 2400
+    d = synthetic.host_drivers(T, N, 41, dtype=np.float32)
+    rng = np.random.default_rng(42)
+    # (T, N) annual means: a few distinct years, as calibration.py:556-560 builds them
+    year = np.repeat(np.arange(4), 10)[:T]
+    d['temp_annual'] = (d['temp_annual'][None, :] + year[:, None]).astype(np.float32)
+    d['pressure'] = (d['pressure'][None, :] * (1 + 1e-3 * year[:, None])).astype(np.float32)
+    d['temp_annual'][rng.random((T, N)) < 0.01] = np.nan    # masked-away NaN (:230-233)
+    drv = [d[k] for k in NAMES]
+    col = list(_table()[:, 4])
+    with np.errstate(all='ignore'):
+        ref = orc.static_et(col, *_d64(drv))
+        rd, rn = orc.static_evapotranspiration(col, *_d64(drv))
+    got = MOD16._et(col, *drv, dtype=np.float32)
+    assert _kernel(cuda_lib) == (_abi.KERNEL_PIPE, 2)
+    parity.assert_parity(got, ref, np.float32, what='(T, N) annual temperature / pressure')
+    gd, gn = MOD16._evapotranspiration(col, *drv, dtype=np.float32)
+    assert _kernel(cuda_lib) == (_abi.KERNEL_PIPE, 2)
+    parity.assert_parity(gd, rd, np.float32, what='day')
+    parity.assert_parity(gn, rn, np.float32, what='night')
+    # with a dense sw_rad_night as well: all fourteen arrays streamed
+    d['sw_rad_night'] = rng.uniform(0, 1e-5, (T, N)).astype(np.float32)
+    drv = [d[k] for k in NAMES]
+    with np.errstate(all='ignore'):
+        ref = orc.static_et(col, *_d64(drv))
+    got = MOD16._et(col, *drv, dtype=np.float32)
+    assert _kernel(cuda_lib) == (_abi.KERNEL_PIPE, 3)
+    parity.assert_parity(got, ref, np.float32, what='fourteen streamed arrays')
+
+
+def test_pixel_range_of_a_wider_array_is_streamed(cuda_lib):
+    dev = torch.device('cuda', 0)
+    T, N = 12, 9600
+    d = synthetic.device_drivers(T, N, 51, dev)
+    lst = [d[k] for k in NAMES]
+    table = _table()
+    pft = torch.from_numpy(synthetic.host_pft_map(N, 52)).to(dev)
+    full = run_forward(lst, pft=pft, table=table, gate='open', dtype=np.float32, device=dev,
+                       as_torch=True)[0]
+    for lo, hi, want in ((0, 4800, _abi.KERNEL_PIPE), (484, 9600, _abi.KERNEL_PIPE),
+                         (486, 9590, _abi.KERNEL_STRIDED)):
+        sl = [v[:, lo:hi] if isinstance(v, torch.Tensor) and v.ndim == 2 else
+              (v[lo:hi] if isinstance(v, torch.Tensor) else v) for v in lst]
+        part = run_forward(sl, pft=pft[lo:hi], table=table, gate='open', dtype=np.float32,
+                           device=dev, as_torch=True)[0]
+        assert _kernel(cuda_lib)[0] == want, (lo, hi)
+        assert torch.equal(part.view(torch.int32), full[:, lo:hi].contiguous().view(torch.int32))
+
+
+@pytest.mark.parametrize('semantics', ['static', 'instance'])
+@pytest.mark.parametrize('out_mode', ['sum', 'day_night', 'components'])
+def test_negative_vpd_and_fill_temperatures(cuda_lib, semantics, out_mode):
+    T, N = 16, 4800
+    d = synthetic.host_drivers(T, N, 61, dtype=np.float32)
+    rng = np.random.default_rng(62)
+    for k in ('vpd_day', 'vpd_night'):           # reanalysis dew point above air temperature
+        m = rng.random((T, N)) < 0.05
+        d[k][m] = -rng.uniform(0, 300, m.sum()).astype(np.float32)
+    for k, fill in (('temp_day', -9999.0), ('temp_night', -32768.0)):
+        d[k][rng.random((T, N)) < 0.01] = fill
+    d['tmin'][rng.random((T, N)) < 0.01] = -9999.0
+    drv = [d[k] for k in NAMES]
+    col = list(_table()[:, 7])
+    with np.errstate(all='ignore'):
+        if semantics == 'static':
+            day, night = orc.static_evapotranspiration(col, *_d64(drv))
+            comps = orc.static_evapotranspiration(col, *_d64(drv), components=True)
+        else:
+            comps = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, col))).evapotranspiration(
+                *_d64(drv), separate=True)
+            day = comps[0][0] + comps[0][1] + comps[0][2]
+            night = comps[1][0] + comps[1][1] + comps[1][2]
+    scale = 1.0 if semantics == 'static' else parity.MASS_SCALE
+    got = run_forward(drv, params=col, semantics=semantics, out_mode=out_mode, dtype=np.float32)
+    assert _kernel(cuda_lib)[0] == _abi.KERNEL_PIPE
+    if out_mode == 'sum':
+        parity.assert_parity(got[0], day + night, np.float32, scale, what='sum')
+    elif out_mode == 'day_night':
+        parity.assert_parity(got[0], day, np.float32, scale, what='day')
+        parity.assert_parity(got[1], night, np.float32, scale, what='night')
+    else:
+        for h in range(2):
+            for c in range(3):
+                parity.assert_parity(got[3 * h + c], comps[h][c], np.float32, scale,
+                                     what='component %d %d' % (h, c))
+    # the fast path took them: almost nothing was left for the double-precision queue
+    assert np.isnan(got[0]).mean() > 0.015
+
+
+def test_chunked_plan_equals_one_call(cuda_lib):
+    from mod16_b200.chunked import ChunkedForward, PER_STEP
+    dev = torch.device('cuda', 0)
+    T, N = 23, 4804
+    d = synthetic.device_drivers(T, N, 71, dev)
+    table = _table()
+    pft = torch.from_numpy(synthetic.host_pft_map(N, 72)).to(dev)
+    lst = [d[k] for k in NAMES]
+    for closed in (False, True):
+        if closed:
+            d['tmin'].fill_(230.0)       # nobody transpires: the whole call's gate is closed
+        flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        one = run_forward(lst, pft=pft, table=table, gate='global', dtype=np.float32,
+                          device=dev, gate_flag=flag, as_torch=True)[0]
+        cf = ChunkedForward(T, N, table, pft, d['temp_annual'], d['pressure'], device=dev,
+                            budget_bytes=2 * len(PER_STEP) * N * 4 * 6)
+        assert len(cf.chunks) == 4 and len(cf.bufs) == 2
+        calls = []
+
+        def fill(k, t0, t1, bufs):
+            calls.append(k)
+            for name in PER_STEP:
+                bufs[name].copy_(d[name][t0:t1])
+        out = torch.full((T, N), -1.0, device=dev)
+        cf.run(fill, out)
+        assert torch.equal(out.view(torch.int32), one.view(torch.int32))
+        assert len(calls) == (8 if closed else 4) and cf.kernel_ms > 0
+
+
+def test_nccl_world_of_one(cuda_lib):
+    'The NCCL branches of distributed.py / chunked.py (all-reduce, all-gather) on one rank.'
+    import torch.distributed as dist
+    from mod16_b200 import distributed as D
+    from mod16_b200.objective import ObjectiveBackend
+    dev = torch.device('cuda', 0)
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('nccl', rank=0, world_size=1, device_id=dev)
+    try:
+        T, N = 9, 960
+        d = synthetic.device_drivers(T, N, 81, dev)
+        lst = [d[k] for k in NAMES]
+        col = list(_table()[:, 7])
+        flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        one = run_forward(lst, params=col, gate='global', dtype=np.float32, device=dev,
+                          gate_flag=flag, as_torch=True)[0]
+        # D.world() sees an initialised group of size 1: force the collective branch
+        size = D.world
+        D.world = lambda group=None: (0, 2)
+        try:
+            got = D.forward_global_gate(lst, params=col, dtype=np.float32, device=dev)[0]
+            assert torch.equal(got.view(torch.int32), one.view(torch.int32))
+            obs = one + 1.0
+            backend = ObjectiveBackend(lst, obs, None, dtype=np.float32, device=dev)
+            draws = torch.from_numpy(synthetic.host_param_draws(
+                40, 5, bplut_column=np.array(col))).to(dev)
+            s0, c0 = backend(draws, as_torch=True)
+            s1, c1 = D.objective_site_sharded(backend, draws)
+            assert torch.equal(s0, s1) and torch.equal(c0, c1)
+            t = torch.arange(6, dtype=torch.float64, device=dev)
+            a, b = D.reduce_objective(t.clone(), t.clone() + 1)
+            assert torch.equal(a, t) and torch.equal(b, t + 1)
+        finally:
+            D.world = size
+        s2, c2 = D.objective_draw_sharded(backend, draws)
+        assert torch.equal(s0, s2) and torch.equal(c0, c2)
+    finally:
+        dist.destroy_process_group()

@@ -176,3 +176,89 @@ def test_gate_protocol_and_reductions_world2(case):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)], res
+
+
+# ---- T-chunked execution (mod16_b200/chunked.py): config 3 on two GPUs ---------------------
+def test_chunk_plan_covers_and_fits():
+    from mod16_b200.chunked import plan_chunks
+    # global 0.05 degree year, two ranks, float32, 120 GiB for two buffer sets
+    N = 7200 * 3600 // 2
+    ch = plan_chunks(365, N, 4, 120 << 30, n_buffers=2)
+    assert ch[0][0] == 0 and ch[-1][1] == 365
+    assert all(b == c for (_, b), (c, _) in zip(ch, ch[1:]))
+    assert max(b - a for a, b in ch) * 2 * 11 * N * 4 <= 120 << 30
+    assert all((b - a) % 2 == 0 for a, b in ch[:-1])
+    assert len(plan_chunks(365, 5760000, 4, 170 << 30, n_buffers=1)) == 1   # a tile-year fits
+    assert len(plan_chunks(365, 5760000, 8, 170 << 30, n_buffers=1)) == 2   # ... not in float64
+    with pytest.raises(ValueError):
+        plan_chunks(10, 1 << 30, 4, 1 << 20)
+
+
+def _oracle_forward_chunk(drivers, *, gate, gate_flag, out, pft=None, table=None, **kw):
+    'Stands in for run_forward in ChunkedForward: open_track / closed on one chunk.'
+    params = BPLUT7
+    drv = [d.numpy() if isinstance(d, torch.Tensor) else d for d in drivers]
+    with np.errstate(all='ignore'):
+        day, night = orc.static_evapotranspiration(
+            params, *drv, gate='open' if gate == 'open_track' else 'closed')
+        if gate == 'open_track':
+            g_surf = (params[7] * orc.ramp_up(drv[8] - 273.15, params[0], params[1]) *
+                      orc.ramp_down(drv[9], params[2], params[3]))
+            if np.any(g_surf / orc.r_correction(drv[11], drv[5]) > 0):
+                gate_flag.fill_(1)
+    out[0].copy_(torch.from_numpy(np.asarray(day + night)))
+    return out
+
+
+def _chunk_worker(rank, size, port, case, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=size)
+    try:
+        from mod16_b200.chunked import ChunkedForward, PER_STEP
+        T, N = 11, 32
+        d = synthetic.host_drivers(T, N, 78)
+        if case != 'open':
+            d['tmin'] = np.full((T, N), 240.0)
+        if case == 'last_chunk_of_last_rank_open':
+            d['tmin'][T - 1, N - 1] = 290.0
+        drv = [d[k] for k in NAMES]
+        with np.errstate(all='ignore'):
+            ref = orc.static_et(BPLUT7, *drv)           # ONE reference call: all days, all pixels
+        lo, hi = D.pixel_range(N, rank, size)
+        n = hi - lo
+        budget = 2 * len(PER_STEP) * n * 8 * 4          # two buffer sets of four steps
+        cf = ChunkedForward(T, n, None, None, torch.from_numpy(d['temp_annual'][lo:hi]),
+                            torch.from_numpy(d['pressure'][lo:hi]), device='cpu',
+                            dtype=np.float64, budget_bytes=budget, forward=_oracle_forward_chunk)
+        calls = []
+
+        def fill(k, t0, t1, bufs):
+            calls.append((k, t0, t1))
+            for name in PER_STEP:
+                bufs[name].copy_(torch.from_numpy(d[name][t0:t1, lo:hi]))
+        out = torch.empty((T, n), dtype=torch.float64)
+        cf.run(fill, out)
+        ok = len(cf.chunks) == 3 and cf.chunks[-1] == (8, 11)
+        ok = ok and np.allclose(out.numpy(), ref[:, lo:hi], rtol=1e-12, atol=1e-12, equal_nan=True)
+        # closed over the whole call: every chunk is filled and evaluated twice
+        ok = ok and len(calls) == (6 if case == 'closed' else 3)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('case', ['open', 'closed', 'last_chunk_of_last_rank_open'])
+def test_chunked_forward_gate_spans_chunks_and_ranks_world2(case):
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_chunk_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)], res
