@@ -92,3 +92,24 @@ def annual_mass_sums(pred_le, years, lhv, **kw):
     labels, idx = np.unique(yr, return_inverse=True)
     return time_aggregate(pred_le, group=idx.astype(np.int32), n_groups=len(labels),
                           divisor=lhv, scale=60 * 60 * 24, clamp_neg=True, **kw)
+
+
+def constrain_by_map(pred_le, years, lhv, annual_precip, **kw):
+    '''
+    The calibration's precipitation constraint (reference mod16/calibration.py:775-796):
+    annual evapotranspiration [mm] per pixel from latent heat flux (K3, ``annual_mass_sums``)
+    against (Y, N) annual precipitation; returns the NEGATIVE normalised RMSD
+    ``-100 * mean(max(annual_ET - annual_precip, 0) ** 2) / sum(annual_precip)`` -- the
+    objective the configuration calls ``nRMSD`` (data/MOD16_calibration_config.yaml:49).
+    A python float, or a 0-d CUDA tensor when ``pred_le`` is a CUDA tensor.
+    '''
+    as_torch = isinstance(pred_le, torch.Tensor) and pred_le.device.type == 'cuda'
+    dev = pick_device([pred_le], kw.get('device'))
+    le = pred_le if as_torch else _dev(pred_le, dev, _TORCH_DT.get(
+        np.asarray(pred_le).dtype, torch.float64))
+    lh = lhv if isinstance(lhv, torch.Tensor) else _dev(lhv, dev, le.dtype)
+    annual = annual_mass_sums(le, years, lh.to(le.dtype), **kw)       # (Y, N) float64, on device
+    precip = _dev(annual_precip, dev, torch.float64)
+    diff = torch.clamp(annual - precip, min=0.0)                      # :791-792
+    val = -100.0 * ((diff * diff).mean() / precip.sum())              # :795-796
+    return val if as_torch else float(val.item())

@@ -164,7 +164,13 @@ def objective_batch(draws, drivers, observed, weights=None, **kw):
 
 
 def rmsd(sse, count):
-    'sqrt(nanmean(((pred - obs) w)^2)) from the statistics; NaN where no pair was valid.'
+    '''
+    sqrt(nanmean(((pred - obs) w)^2)) from the statistics; NaN where no pair was valid.
+    mod17's ``BlackBoxLikelihood.loglik`` (objective "rmsd", the reference's configured
+    ``RMSD``, data/MOD16_calibration_config.yaml:49) returns its negative:
+    ``-np.sqrt(np.nanmean(((predicted - observed) * weights) ** 2))``.  Known answers:
+    tests/test_objective.py::test_objective_definitions_known_answers.
+    '''
     with np.errstate(invalid='ignore', divide='ignore'):
         return np.sqrt(np.asarray(sse) / np.asarray(count))
 
@@ -173,6 +179,11 @@ def nash_sutcliffe(sse, observed, norm=False):
     '''
     Nash-Sutcliffe efficiency from the unweighted statistics: 1 - sse / sum((obs - mean(obs))^2)
     over the non-NaN observations; ``norm`` gives 1 / (2 - NSE) as sensitivity.py:96 asks.
+    Restates ``mod17.science.nash_sutcliffe(predicted, observed, norm)``:
+    ``nse = 1 - nansum((observed - predicted) ** 2) / nansum((observed - nanmean(observed)) ** 2)``
+    (the numerator skips a pair when either value is NaN -- that is ``sse`` --, the
+    denominator runs over every observation present); ``norm`` returns ``1 / (2 - nse)``.
+    Known answers: tests/test_objective.py::test_objective_definitions_known_answers.
     '''
     obs = np.asarray(observed, np.float64)
     obs = obs[~np.isnan(obs)]

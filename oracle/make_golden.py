@@ -459,6 +459,46 @@ def components_fixture(bplut):
     return len(out)
 
 
+def constraint_fixture():
+    '''
+    `constrain_by_map` is a function nested in CalibrationAPI.tune (mod16/calibration.py:775-
+    796); calibration.py itself cannot be imported here (pymc, h5py ... are absent).  Its
+    source text is cut out of the unmodified file with `ast` and executed on its own -- it
+    only needs numpy -- so the golden answers come from the reference's own statements.
+    '''
+    import ast
+    import textwrap
+    path = '/root/reference/mod16/calibration.py'
+    src = open(path).read()
+    node = [n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef)
+            and n.name == 'constrain_by_map']
+    assert len(node) == 1
+    lines = src.split('\n')[node[0].lineno - 1:node[0].end_lineno]
+    scope = {'np': np}
+    exec(compile(textwrap.dedent('\n'.join(lines)), path, 'exec'), scope)
+    ref_fn = scope['constrain_by_map']
+    rng = np.random.default_rng(16201)
+    out = {'lines': np.array([node[0].lineno, node[0].end_lineno])}
+    n = 0
+    for tag, T, N, Y in (('a', 730, 17, 2), ('b', 1461, 5, 4), ('c', 40, 3, 3)):
+        years = np.sort(rng.integers(0, Y, T)) + 2001
+        le = rng.normal(60, 50, (T, N))                # some negative fluxes (:786)
+        temp = rng.uniform(255, 305, (T, N))
+        lhv = ref.latent_heat_vaporization(temp)
+        precip = rng.uniform(200, 1500, (np.unique(years).size, N))
+        if tag == 'c':
+            precip[:] = 1e9                            # never exceeded: the objective is -0
+        want = ref_fn(le.copy(), years, lhv, precip)
+        check('constrain_by_map ' + tag, want, orc.constrain_by_map(le.copy(), years, lhv, precip))
+        for k, v in (('le', le), ('years', years), ('lhv', lhv), ('precip', precip),
+                     ('neg_nrmsd', np.float64(want)),
+                     ('annual', orc.annual_mass_sums(le.copy(), years, lhv))):
+            out['%s_%s' % (tag, k)] = v
+        n += 1
+    np.savez_compressed(os.path.join(GOLDEN, 'constraint.npz'), **out)
+    return n
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     bplut = bplut_c51()
@@ -467,6 +507,7 @@ def main():
     report['verify'] = verify_fixture(bplut)
     report['tables'] = table_fixture(bplut)
     report['components'] = components_fixture(bplut)
+    report['constraint'] = constraint_fixture()
     report['rand_phys_f64'] = random_fixture(
         bplut, 'rand_phys_f64', 24, 96, 16101, 'physical', np.float64, 0.0, 0.0)
     report['rand_phys_fill_f64'] = random_fixture(

@@ -536,3 +536,17 @@ def annual_mass_sums(pred_le, years, lhv_arr):
     for y in np.unique(years):
         annual.append(np.apply_along_axis(lambda x: x.sum(), 0, mass_rate[years == y]))
     return np.stack(annual, axis=0)
+
+
+def constrain_by_map(pred_le, years, lhv_arr, annual_precip):
+    '''
+    The calibration's precipitation constraint, both halves (mod16/calibration.py:775-796, a
+    function nested in `CalibrationAPI.tune`): annual evapotranspiration must not exceed
+    annual precipitation.  Returns the NEGATIVE normalised RMSD
+    `-100 * mean(max(annual_ET - annual_precip, 0)^2) / sum(annual_precip)`.
+    '''
+    pred_precip = annual_mass_sums(pred_le, years, lhv_arr)       # :783-790
+    diff = pred_precip - annual_precip                            # :791
+    diff = np.where(diff < 0, 0, diff)                            # :792
+    nrmsd = 100 * ((diff**2).mean() / annual_precip.sum())        # :795
+    return -nrmsd                                                 # :796

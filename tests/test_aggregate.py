@@ -88,3 +88,20 @@ def test_aggregate_outputs_stay_inside_their_buffers(cuda_lib):
         assert bool((big[:pad] == -5.0).all()) and bool((big[pad + 2 * N:] == -5.0).all())
         ref = torch.stack([x[0::2].double().sum(0), x[1::2].double().sum(0)]).reshape(-1)
         assert torch.allclose(big[pad:pad + 2 * N], ref, rtol=1e-12)
+
+
+def test_constrain_by_map_golden(cuda_lib, golden_dir):
+    'Both halves of the precipitation constraint against the reference\'s own statements.'
+    import os
+    g = np.load(os.path.join(golden_dir, 'constraint.npz'))
+    for tag in 'abc':
+        le, years, lhv, precip = (g['%s_%s' % (tag, k)] for k in ('le', 'years', 'lhv', 'precip'))
+        want = float(g[tag + '_neg_nrmsd'])
+        got = aggregate.constrain_by_map(le, years, lhv, precip)
+        assert abs(got - want) <= 1e-10 * max(abs(want), 1e-12), (tag, got, want)
+        annual = aggregate.annual_mass_sums(le, years, lhv)
+        assert np.allclose(annual, g[tag + '_annual'], rtol=1e-12, atol=1e-9)
+        # float32 fluxes (what K1 writes): the sums are still accumulated in double
+        got32 = aggregate.constrain_by_map(le.astype(np.float32), years, lhv.astype(np.float32),
+                                           precip)
+        assert abs(got32 - want) <= 1e-5 * max(abs(want), 1e-12)

@@ -316,3 +316,42 @@ def test_raw_statistics_and_site_sharding_on_one_gpu(cuda_lib, dtype):
     s0, _, _ = finish_raw(parts[0])
     assert not np.allclose(s0.cpu().numpy() + finish_raw(parts[1])[0].cpu().numpy(), sse,
                            rtol=1e-6)
+
+
+# ---- the objectives' definitions, pinned by contract ------------------------------------------
+# mod17 (EXTERNAL: PyPI `mod17>=0.1.1`, pyproject.toml:22; not under /root/reference) documents
+#   BlackBoxLikelihood.loglik(params, observed, x):  predicted = model(params, *x);
+#       -sqrt(nanmean(((predicted - observed) * weights) ** 2))        [objective "rmsd"]
+#   science.nash_sutcliffe(predicted, observed, norm = False):
+#       nse = 1 - nansum((observed - predicted)**2) / nansum((observed - nanmean(observed))**2)
+#       norm -> 1 / (2 - nse)
+# The call sites are mod16/calibration.py:224-227 and mod16/sensitivity.py:94-96.  The vectors
+# below are worked by hand from those formulas, so that the definition this repository
+# implements is written down and checked in one place.
+def test_objective_definitions_known_answers():
+    from mod16_b200 import objective as obj
+    obs = np.array([1.0, 2.0, 3.0, 4.0])
+    pred = np.array([1.0, 3.0, 2.0, 6.0])
+    sse, n = orc.objective_stats(pred, obs)
+    assert (sse, n) == (6.0, 4)                                   # 0 + 1 + 1 + 4
+    assert obj.rmsd(sse, n) == np.sqrt(1.5)
+    assert orc.rmsd_from_stats(sse, n) == np.sqrt(1.5)
+    # sum((obs - 2.5)^2) = 5  ->  NSE = 1 - 6 / 5 = -0.2,  normalised 1 / 2.2
+    assert abs(obj.nash_sutcliffe(sse, obs) - (-0.2)) < 1e-15
+    assert abs(obj.nash_sutcliffe(sse, obs, norm=True) - 1 / 2.2) < 1e-15
+    assert abs(orc.nse_from_stats(sse, obs, norm=True) - 1 / 2.2) < 1e-15
+    # missing values: a pair counts when both are present (nanmean / nansum of the squared
+    # error); the NSE denominator runs over every observation that is present
+    obs = np.array([1.0, np.nan, 3.0])
+    pred = np.array([2.0, 5.0, np.nan])
+    sse, n = orc.objective_stats(pred, obs)
+    assert (sse, n) == (1.0, 1) and obj.rmsd(sse, n) == 1.0
+    assert obj.nash_sutcliffe(sse, obs) == 0.5                    # 1 - 1 / ((1-2)^2 + (3-2)^2)
+    # weights multiply the error before it is squared
+    sse, n = orc.objective_stats(np.array([1.0, 2.0]), np.array([0.0, 0.0]), np.array([2.0, 1.0]))
+    assert (sse, n) == (8.0, 2) and obj.rmsd(sse, n) == 2.0
+    # no valid pair: NaN, not an exception
+    assert np.isnan(obj.rmsd(0.0, 0.0))
+    # a perfect model: NSE = 1 either way
+    assert obj.nash_sutcliffe(0.0, np.array([1.0, 2.0])) == 1.0
+    assert obj.nash_sutcliffe(0.0, np.array([1.0, 2.0]), norm=True) == 1.0

@@ -186,3 +186,14 @@ def test_gate_modes_of_the_oracle():
     e = orc.static_et(vec, *drv, gate='element')
     day = orc.static_evapotranspiration(vec, *drv, components=True)[0]
     assert np.all((e == g) | (day[2] != 0))
+
+
+def test_constraint_golden(golden_dir):
+    'oracle.constrain_by_map against the answers of the reference\'s own nested function.'
+    g = np.load(os.path.join(golden_dir, 'constraint.npz'))
+    for tag in 'abc':
+        le, years, lhv, precip = (g['%s_%s' % (tag, k)] for k in ('le', 'years', 'lhv', 'precip'))
+        got = orc.constrain_by_map(le.copy(), years, lhv, precip)
+        assert got == float(g[tag + '_neg_nrmsd'])
+        assert np.array_equal(orc.annual_mass_sums(le.copy(), years, lhv), g[tag + '_annual'])
+    assert float(g['c_neg_nrmsd']) == 0.0
