@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 6
+#define MOD16_ABI_VERSION 7
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -65,6 +65,8 @@ enum {
 #define MOD16_ERR_CUDA (-4)     /* a CUDA call failed: see mod16_last_cuda_error() */
 #define MOD16_ERR_PARAMS (-5)   /* parameter source is inconsistent */
 #define MOD16_ERR_WORKSPACE (-6)/* workspace too small */
+#define MOD16_ERR_LAYOUT (-7)   /* raw-format layout the fused kernel cannot stream: convert
+                                   the drivers to float32 first (no silent slow path) */
 
 /* flag word of mod16_forward_* ------------------------------------------------------- */
 /* semantics: which of the reference's two forward paths is reproduced */
@@ -136,6 +138,49 @@ typedef struct mod16_out {
   int64_t workspace_bytes;
 } mod16_out_t;
 
+/*
+ * Drivers in their storage formats: the conversions the reference's
+ * loaders perform on the host before the model is called are applied inside the fused kernel
+ * instead, so that a pixel-timestep costs 24-40 bytes of traffic instead of 48:
+ *   fPAR  uint8 percent        `fpar /= 100`                 (mod16/calibration.py:422)
+ *   LAI   uint8 tenths         `lai /= 10`                   (mod16/calibration.py:423)
+ *   albedo, and optionally every other per-step driver, int16 with scale / offset
+ *   vpd_night = where(vpd_night < 0, 0, vpd_night)           (mod16/calibration.py:401)
+ *   pressure = MOD16.air_pressure(elevation)                 (mod16/__init__.py:415-447,
+ *                                                             mod16/calibration.py:405-408)
+ * physical value = raw * scale + offset, evaluated in float32 (one fused multiply-add); a raw
+ * value equal to `fill` (when has_fill) is a missing value: NaN.  Two layouts are streamed:
+ *   MODIS : sw_albedo int16, fpar uint8, lai uint8, the eight other per-step drivers float32
+ *   PACKED: sw_albedo and the eight other per-step drivers int16, fpar uint8, lai uint8
+ * (all-float32 drivers are accepted too: the plain kernel plus the `prep` conversions).
+ * Requirements: static or instance semantics, OUT_SUM or OUT_DAY_NIGHT, per-step arrays
+ * (T, N) with unit pixel stride and 16-byte aligned rows (N % 16 == 0 for the uint8 rows),
+ * sw_rad_night a scalar, temp_annual / pressure per pixel or scalar (float32), no
+ * r_corr_list.  Anything else returns MOD16_ERR_LAYOUT.
+ */
+#define MOD16_T_F32 0
+#define MOD16_T_I16 1
+#define MOD16_T_U8 2
+#define MOD16_PREP_VPD_NIGHT_CLAMP 0x1u /* vpd_night < 0 -> 0 (a NaN stays NaN) */
+#define MOD16_PREP_ELEVATION 0x2u       /* drv[MOD16_D_PRESSURE] holds elevation in metres */
+
+typedef struct mod16_raw_driver {
+  const void* ptr;   /* device array of `dtype`, or NULL: use `scalar` (a physical value) */
+  int64_t t_stride;  /* ELEMENTS of `dtype` between consecutive time steps */
+  int64_t n_stride;  /* ... between consecutive pixels */
+  double scalar;
+  int32_t dtype;     /* MOD16_T_* */
+  int32_t has_fill;  /* integer types: `fill` marks a missing value */
+  double scale, offset;
+  int64_t fill;
+} mod16_raw_driver_t;
+
+typedef struct mod16_raw_drivers {
+  mod16_raw_driver_t drv[MOD16_N_DRIVERS];
+  uint32_t prep;     /* MOD16_PREP_* */
+  uint32_t reserved;
+} mod16_raw_drivers_t;
+
 int mod16_abi_version(void);
 int64_t mod16_workspace_bytes(void); /* recommended size of mod16_out_t.workspace */
 int mod16_last_cuda_error(void);
@@ -149,6 +194,11 @@ int mod16_last_cuda_error(void);
 #define MOD16_KERNEL_EXACT 3
 int mod16_last_forward_kernel(void);
 const char* mod16_error_string(int code);
+
+/* K1 on storage-format drivers (see mod16_raw_drivers_t); float32 arithmetic and outputs. */
+int mod16_forward_raw_f32(const mod16_raw_drivers_t* drivers, const mod16_params_t* params,
+                          const mod16_out_t* out, int64_t T, int64_t N, uint32_t flags,
+                          void* stream);
 
 /* K1 -- fused forward model over a (T, N) block of pixel-timesteps. */
 int mod16_forward_f32(const mod16_drivers_t* drivers, const mod16_params_t* params,

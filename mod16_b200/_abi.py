@@ -17,10 +17,13 @@ GATE_GLOBAL, GATE_ELEMENT, GATE_OPEN, GATE_CLOSED = 0x000, 0x100, 0x200, 0x300
 GATE_OPEN_TRACK, GATE_FIXUP = 0x400, 0x500
 FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
 KERNEL_PIPE, KERNEL_STRIDED, KERNEL_EXACT = 1, 2, 3   # mod16_last_forward_kernel() & 0xff
+T_F32, T_I16, T_U8 = 0, 1, 2                            # mod16_raw_driver_t.dtype
+PREP_VPD_NIGHT_CLAMP, PREP_ELEVATION = 0x1, 0x2
+ERR_LAYOUT = -7
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                         'libmod16_b200.so')
 
@@ -33,6 +36,19 @@ class Driver(ctypes.Structure):
 class Drivers(ctypes.Structure):
     _fields_ = [('drv', Driver * N_DRIVERS), ('r_corr', Driver * 2),
                 ('has_r_corr', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+class RawDriver(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p), ('t_stride', ctypes.c_int64),
+                ('n_stride', ctypes.c_int64), ('scalar', ctypes.c_double),
+                ('dtype', ctypes.c_int32), ('has_fill', ctypes.c_int32),
+                ('scale', ctypes.c_double), ('offset', ctypes.c_double),
+                ('fill', ctypes.c_int64)]
+
+
+class RawDrivers(ctypes.Structure):
+    _fields_ = [('drv', RawDriver * N_DRIVERS), ('prep', ctypes.c_uint32),
+                ('reserved', ctypes.c_uint32)]
 
 
 class Params(ctypes.Structure):
@@ -82,6 +98,10 @@ class Mod16Error(RuntimeError):
     pass
 
 
+class LayoutError(Mod16Error):
+    'MOD16_ERR_LAYOUT: a storage-format layout the fused kernel cannot stream.'
+
+
 _lib = None
 
 # every symbol include/mod16_b200.h declares; tests/test_abi_symbols.py checks the list
@@ -92,6 +112,9 @@ EXPORTS = {
     'mod16_last_cuda_error': (ctypes.c_int, []),
     'mod16_last_forward_kernel': (ctypes.c_int, []),
     'mod16_error_string': (ctypes.c_char_p, [ctypes.c_int]),
+    'mod16_forward_raw_f32': (ctypes.c_int, [
+        ctypes.POINTER(RawDrivers), ctypes.POINTER(Params), ctypes.POINTER(Out),
+        ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p]),
     'mod16_forward_f32': (ctypes.c_int, [
         ctypes.POINTER(Drivers), ctypes.POINTER(Params), ctypes.POINTER(Out),
         ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p]),
@@ -154,4 +177,5 @@ def check(rc):
         msg = lib.mod16_error_string(rc).decode()
         if rc == -4:
             msg += ' [cudaError %d]' % lib.mod16_last_cuda_error()
-        raise Mod16Error('mod16_b200: %s (code %d)' % (msg, rc))
+        raise (LayoutError if rc == ERR_LAYOUT else Mod16Error)(
+            'mod16_b200: %s (code %d)' % (msg, rc))

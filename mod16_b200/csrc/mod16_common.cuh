@@ -42,9 +42,21 @@ inline void fill_arr(Arr<R>& dst, const mod16_driver_t& src) {
   dst.scalar = (R)src.scalar;
 }
 
+// Storage format of one driver of mod16_forward_raw_f32 (float32 path only).
+struct RawInfo {
+  int dtype;      // MOD16_T_*
+  int has_fill;
+  float scale, offset;
+  int fill;
+};
+
 template <typename R>
 struct ForwardArgs {
   Arr<R> drv[MOD16_N_DRIVERS];
+  // raw-format call: drv[k].ptr points at elements of raw[k].dtype (strides in elements)
+  RawInfo raw[MOD16_N_DRIVERS];
+  int raw_fmt;       // 0: every driver float (the plain entries); else see mod16_forward_pipe.cuh
+  uint32_t prep;     // MOD16_PREP_*
   Arr<R> rc[2];
   int has_rc;
   // parameters

@@ -121,6 +121,12 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
   a.T = T;
   a.N = N;
   a.t_chunk = 1;
+  a.raw_fmt = 0;
+  a.prep = 0;
+  for (int k = 0; k < MOD16_N_DRIVERS; ++k) {
+    a.raw[k].dtype = MOD16_T_F32; a.raw[k].has_fill = 0;
+    a.raw[k].scale = 1.0f; a.raw[k].offset = 0.0f; a.raw[k].fill = 0;
+  }
   return MOD16_OK;
 }
 
@@ -195,6 +201,8 @@ int run_with_gate(ForwardArgs<R>& a, uint32_t flags, cudaStream_t st, PassFn pas
 
 // defined in mod16_forward_fast.cu
 int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st);
+// storage formats of mod16_forward_raw_f32 (mod16_forward_pipe.cuh)
+constexpr int FMT_F32_PREP = 1, FMT_MODIS = 2, FMT_PACKED = 3;
 
 template int build_forward_args<float>(const mod16_drivers_t*, const mod16_params_t*,
                                        const mod16_out_t*, int64_t, int64_t, uint32_t,
@@ -219,6 +227,7 @@ const char* mod16_error_string(int code) {
     case MOD16_ERR_SHAPE: return "bad shape or stride";
     case MOD16_ERR_FLAGS: return "unknown or inconsistent flags";
     case MOD16_ERR_CUDA: return "CUDA call failed (see mod16_last_cuda_error)";
+    case MOD16_ERR_LAYOUT: return "storage-format layout not supported by the fused kernel";
     case MOD16_ERR_PARAMS: return "inconsistent parameter source";
     case MOD16_ERR_WORKSPACE: return "workspace too small";
   }
@@ -248,6 +257,55 @@ int mod16_forward_f32(const mod16_drivers_t* drivers, const mod16_params_t* para
   return mod16::run_with_gate<float>(a, flags, st, [&](mod16::ForwardArgs<float>& x) {
     return fast ? mod16::launch_fast_f32(x, flags, st)
                 : mod16::launch_strided<float>(x, flags, st);
+  });
+}
+
+int mod16_forward_raw_f32(const mod16_raw_drivers_t* drivers, const mod16_params_t* params,
+                          const mod16_out_t* out, int64_t T, int64_t N, uint32_t flags,
+                          void* stream) {
+  if (!drivers) return MOD16_ERR_NULL;
+  if (flags & (MOD16_FORCE_MIRROR | MOD16_FORCE_GENERIC)) return MOD16_ERR_FLAGS;
+  // the float view of the drivers (pointers and strides; element types follow below)
+  mod16_drivers_t plain;
+  for (int k = 0; k < MOD16_N_DRIVERS; ++k) {
+    const mod16_raw_driver_t& r = drivers->drv[k];
+    if (r.dtype != MOD16_T_F32 && r.dtype != MOD16_T_I16 && r.dtype != MOD16_T_U8)
+      return MOD16_ERR_FLAGS;
+    plain.drv[k].ptr = r.ptr;
+    plain.drv[k].t_stride = r.t_stride;
+    plain.drv[k].n_stride = r.n_stride;
+    plain.drv[k].scalar = r.scalar;
+  }
+  plain.has_r_corr = 0;
+  plain.reserved = 0;
+  for (int k = 0; k < 2; ++k) {
+    plain.r_corr[k].ptr = nullptr; plain.r_corr[k].t_stride = plain.r_corr[k].n_stride = 0;
+    plain.r_corr[k].scalar = 0.0;
+  }
+  mod16::ForwardArgs<float> a;
+  int rc = mod16::build_forward_args<float>(&plain, params, out, T, N, flags, a);
+  if (rc != MOD16_OK) return rc;
+  // layout: all float32 (+ conversions), MODIS or PACKED (see the header)
+  bool any_int = false, met_int = false;
+  for (int k = 0; k < MOD16_N_DRIVERS; ++k) {
+    const mod16_raw_driver_t& r = drivers->drv[k];
+    a.raw[k].dtype = r.ptr ? r.dtype : MOD16_T_F32;
+    a.raw[k].has_fill = r.has_fill != 0 && a.raw[k].dtype != MOD16_T_F32;
+    a.raw[k].scale = (float)r.scale;
+    a.raw[k].offset = (float)r.offset;
+    // (no fill value: one no int16 / uint8 element can equal)
+    a.raw[k].fill = a.raw[k].has_fill ? (int)r.fill : (int)0x80000000;
+    if (a.raw[k].dtype != MOD16_T_F32) {
+      any_int = true;
+      if (k != MOD16_D_SW_ALBEDO && k != MOD16_D_FPAR && k != MOD16_D_LAI) met_int = true;
+    }
+  }
+  a.prep = drivers->prep;
+  if (a.prep & ~(MOD16_PREP_VPD_NIGHT_CLAMP | MOD16_PREP_ELEVATION)) return MOD16_ERR_FLAGS;
+  a.raw_fmt = !any_int ? mod16::FMT_F32_PREP : (met_int ? mod16::FMT_PACKED : mod16::FMT_MODIS);
+  cudaStream_t st = (cudaStream_t)stream;
+  return mod16::run_with_gate<float>(a, flags, st, [&](mod16::ForwardArgs<float>& x) {
+    return mod16::launch_fast_f32(x, flags, st);
   });
 }
 

@@ -14,9 +14,9 @@
 namespace mod16 {
 
 int launch_pipe_static(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode, int extra,
-                       dim3 grid, cudaStream_t st);
+                       int fmt, dim3 grid, cudaStream_t st);
 int launch_pipe_instance(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode,
-                         int extra, dim3 grid, cudaStream_t st);
+                         int extra, int fmt, dim3 grid, cudaStream_t st);
 
 template <int SEM, int OUT>
 __global__ void __launch_bounds__(256, 4)
@@ -131,8 +131,9 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // a (T, N) array the bulk copies can stream: unit pixel stride, every row 16-byte aligned
 // (rows need not be adjacent: a pixel range of a wider array qualifies)
-static bool dense_tn(const Arr<float>& d, int64_t T, int64_t N) {
-  return d.ptr && d.ns == 1 && aligned16(d.ptr) && (T == 1 || (d.ts >= N && d.ts % 4 == 0));
+static bool dense_tn(const Arr<float>& d, int64_t T, int64_t N, int esize = 4) {
+  return d.ptr && d.ns == 1 && aligned16(d.ptr) &&
+         (T == 1 || (d.ts >= N && (d.ts * esize) % 16 == 0));
 }
 
 // The pipelined kernel needs: N % 4 == 0 and 16-byte aligned bases (every bulk copy is a
@@ -144,6 +145,27 @@ static bool dense_tn(const Arr<float>& d, int64_t T, int64_t N) {
 // Returns the EXTRA variant (mod16_forward_pipe.cuh), or -1.
 static int pipe_variant(const ForwardArgs<float>& a, uint32_t flags) {
   if (a.N % 4 != 0 || a.has_rc) return -1;
+  if (a.raw_fmt != 0) {  // storage formats: the eleven per-step arrays in the format's types
+    static const int order[] = {
+        MOD16_D_LW_NET_DAY, MOD16_D_LW_NET_NIGHT, MOD16_D_SW_RAD_DAY, MOD16_D_SW_ALBEDO,
+        MOD16_D_TEMP_DAY,   MOD16_D_TEMP_NIGHT,   MOD16_D_TMIN,       MOD16_D_VPD_DAY,
+        MOD16_D_VPD_NIGHT,  MOD16_D_FPAR,         MOD16_D_LAI};
+    if (a.raw_fmt >= FMT_MODIS && a.N % 16 != 0) return -1;  // uint8 rows: 16-byte multiples
+    for (int k = 0; k < 11; ++k) {
+      const int es = pipe_esize(a.raw_fmt, k);
+      const int want = es == 4 ? MOD16_T_F32 : (es == 2 ? MOD16_T_I16 : MOD16_T_U8);
+      if (a.raw[order[k]].dtype != want || !dense_tn(a.drv[order[k]], a.T, a.N, es)) return -1;
+    }
+    if (a.drv[MOD16_D_SW_RAD_NIGHT].ptr) return -1;
+    for (int k : {MOD16_D_PRESSURE, MOD16_D_TEMP_ANNUAL}) {
+      const Arr<float>& d = a.drv[k];
+      if (a.raw[k].dtype != MOD16_T_F32) return -1;
+      if (d.ptr && !(d.ts == 0 && (d.ns == 1 || d.ns == 0))) return -1;
+    }
+    const uint32_t om = flags & MOD16_OUT_MASK;
+    if (om != MOD16_OUT_SUM && om != MOD16_OUT_DAY_NIGHT) return -1;
+    return 0;
+  }
   static const int per_step[] = {
       MOD16_D_LW_NET_DAY, MOD16_D_LW_NET_NIGHT, MOD16_D_SW_RAD_DAY, MOD16_D_SW_ALBEDO,
       MOD16_D_TEMP_DAY,   MOD16_D_TEMP_NIGHT,   MOD16_D_TMIN,       MOD16_D_VPD_DAY,
@@ -182,20 +204,17 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
   PipeSrc src;
   for (int k = 0; k < PIPE_MAX_ARR; ++k) { src.ptr[k] = nullptr; src.ts[k] = 0; }
   int n_arr = 0;
-  for (int k = 0; k < 11; ++k) src.ptr[n_arr++] = a.drv[order[k]].ptr;
-  if (extra & 1) src.ptr[n_arr++] = a.drv[MOD16_D_SW_RAD_NIGHT].ptr;
+  const int fmt = a.raw_fmt;
+  auto add = [&](int d) {   // (strides of the copy engine are in bytes)
+    src.ptr[n_arr] = (const char*)a.drv[d].ptr;
+    src.ts[n_arr] = a.drv[d].ts * pipe_esize(fmt, n_arr);
+    ++n_arr;
+  };
+  for (int k = 0; k < 11; ++k) add(order[k]);
+  if (extra & 1) add(MOD16_D_SW_RAD_NIGHT);
   if (extra & 2) {
-    src.ptr[n_arr++] = a.drv[MOD16_D_TEMP_ANNUAL].ptr;
-    src.ptr[n_arr++] = a.drv[MOD16_D_PRESSURE].ptr;
-  }
-  {
-    int k = 0;
-    for (; k < 11; ++k) src.ts[k] = a.drv[order[k]].ts;
-    if (extra & 1) src.ts[k++] = a.drv[MOD16_D_SW_RAD_NIGHT].ts;
-    if (extra & 2) {
-      src.ts[k++] = a.drv[MOD16_D_TEMP_ANNUAL].ts;
-      src.ts[k++] = a.drv[MOD16_D_PRESSURE].ts;
-    }
+    add(MOD16_D_TEMP_ANNUAL);
+    add(MOD16_D_PRESSURE);
   }
   const int64_t bx = (a.N + PIPE_TILE - 1) / PIPE_TILE;
   if (bx > 2147483647LL) return MOD16_ERR_SHAPE;
@@ -212,8 +231,8 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
   const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1 : 2);
   const bool is_static = (flags & MOD16_SEM_MASK) == MOD16_SEM_STATIC;
   if (a.redo_cap > 0) M16_CUDA_CHECK(cudaMemsetAsync(a.redo_ws, 0, 8, st));
-  const int rc = is_static ? launch_pipe_static(a, src, out_mode, extra, grid, st)
-                           : launch_pipe_instance(a, src, out_mode, extra, grid, st);
+  const int rc = is_static ? launch_pipe_static(a, src, out_mode, extra, fmt, grid, st)
+                           : launch_pipe_instance(a, src, out_mode, extra, fmt, grid, st);
   if (rc != MOD16_OK) return rc;
   if (a.redo_cap > 0) {
 #define M16_REDO(S, O)                                                                  \
@@ -252,10 +271,11 @@ int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
   if (!(flags & MOD16_FORCE_GENERIC)) {
     const int extra = pipe_variant(a, flags);
     if (extra >= 0) {
-      g_last_forward_kernel = MOD16_KERNEL_PIPE | (extra << 8);
+      g_last_forward_kernel = MOD16_KERNEL_PIPE | (extra << 8) | (a.raw_fmt << 12);
       return launch_pipe(a, flags, extra, st);
     }
   }
+  if (a.raw_fmt != 0) return MOD16_ERR_LAYOUT;  // (no strided kernel for storage formats)
   g_last_forward_kernel = MOD16_KERNEL_STRIDED;
   const int threads = 256;
   const int64_t bx = (a.N + threads - 1) / threads;

@@ -63,10 +63,25 @@ constexpr uint32_t PIPE_ROWB = PIPE_TILE * sizeof(float);  // bytes per array ro
 __host__ __device__ constexpr int pipe_n_arr(int extra) {
   return 11 + ((extra & 1) ? 1 : 0) + ((extra & 2) ? 2 : 0);
 }
+// Storage formats of the streamed arrays (FMT): 0 float32, no loader conversions (the plain
+// entries); 1 float32 + the `prep` conversions; 2 MODIS (sw_albedo int16, fpar / lai uint8);
+// 3 PACKED (every other per-step driver int16 as well).  Stage order of the arrays:
+// lw_d lw_n sw_d alb t_d t_n tmin vpd_d vpd_n fpar lai [sw_n] [t_ann p].
+constexpr int FMT_F32 = 0, FMT_F32_PREP = 1, FMT_MODIS = 2, FMT_PACKED = 3;
+__host__ __device__ constexpr int pipe_esize(int fmt, int k) {
+  return fmt < FMT_MODIS ? 4 : (k == 9 || k == 10) ? 1 : (k == 3 || fmt == FMT_PACKED) ? 2 : 4;
+}
+// element offset (in units of PIPE_TILE bytes) of array k inside one sub-step of a stage
+__host__ __device__ constexpr int pipe_eoff(int fmt, int k) {
+  int o = 0;
+  for (int j = 0; j < k; ++j) o += pipe_esize(fmt, j);
+  return o;
+}
 // as many stages as fit into 227 KB of shared memory next to ~8 KB of static data, at most
 // PIPE_MAX_STAGES (more copies in flight than that buy nothing)
-__host__ __device__ constexpr int pipe_n_stages(int extra) {
-  const int fit = (int)((232448u - 8192u) / ((uint32_t)(PIPE_SUB * pipe_n_arr(extra)) * PIPE_ROWB));
+__host__ __device__ constexpr int pipe_n_stages(int extra, int fmt = 0) {
+  const int fit = (int)((232448u - 8192u) /
+                        ((uint32_t)(PIPE_SUB * pipe_eoff(fmt, pipe_n_arr(extra))) * PIPE_TILE));
   return fit < PIPE_MAX_STAGES ? fit : PIPE_MAX_STAGES;
 }
 // stage slot of an optional array (the first eleven are fixed, see launch_pipe)
@@ -74,8 +89,8 @@ __host__ __device__ constexpr int pipe_slot_swn(int extra) { return 11; }
 __host__ __device__ constexpr int pipe_slot_tann(int extra) { return (extra & 1) ? 12 : 11; }
 __host__ __device__ constexpr int pipe_slot_p(int extra) { return pipe_slot_tann(extra) + 1; }
 
-struct PipeSrc {  // streamed arrays in stage order: base pointer and elements per time step
-  const float* ptr[PIPE_MAX_ARR];
+struct PipeSrc {  // streamed arrays in stage order: base pointer and BYTES per time step
+  const char* ptr[PIPE_MAX_ARR];
   int64_t ts[PIPE_MAX_ARR];
 };
 
@@ -84,23 +99,51 @@ struct PipeSrc {  // streamed arrays in stage order: base pointer and elements p
 // arms the barrier and starts the row copies of `n_sub` time steps.  (Measured: this form
 // issues > 50 copies/us, an elected thread inside a divergent branch only 18 --
 // profiles/r01_issuebench.txt.)
-template <int NARR>
+template <int NARR, int FMT>
 __device__ __forceinline__ void pipe_issue(const PipeSrc& src, int n_sub, uint32_t dst,
                                            uint32_t bar, int64_t t, int64_t tile0,
-                                           uint32_t row_bytes) {
+                                           uint32_t n_live) {
+  constexpr uint32_t SUBE = pipe_eoff(FMT, NARR);   // bytes per pixel of one sub-step
   if (elect_one()) {
-    mbar_expect_tx(bar, row_bytes * (uint32_t)(NARR * n_sub));
+    mbar_expect_tx(bar, n_live * SUBE * (uint32_t)n_sub);
 #pragma unroll
     for (int u = 0; u < PIPE_SUB; ++u) {
       if (u < n_sub) {
 #pragma unroll
         for (int k = 0; k < NARR; ++k)
-          bulk_g2s(dst + (uint32_t)(u * NARR + k) * PIPE_ROWB,
-                   src.ptr[k] + (t + u) * src.ts[k] + tile0, row_bytes, bar);
+          bulk_g2s(dst + (uint32_t)(u * SUBE + pipe_eoff(FMT, k)) * PIPE_TILE,
+                   src.ptr[k] + (t + u) * src.ts[k] + tile0 * pipe_esize(FMT, k),
+                   n_live * (uint32_t)pipe_esize(FMT, k), bar);
       }
     }
   }
   __syncwarp();
+}
+
+// One streamed driver of this thread's pixel at the two time steps of a stage, as the floats
+// the model computes with: storage formats are converted with one packed FMA; the fill value
+// (an impossible one when the driver has none, see mod16_forward_raw_f32) becomes NaN.
+template <int FMT, int K>
+__device__ __forceinline__ fast::F2 pipe_load(uint32_t s0, uint32_t s1, uint32_t tid,
+                                              const ForwardArgs<float>& a, int drv_index) {
+  constexpr int ES = pipe_esize(FMT, K);
+  constexpr uint32_t OFF = (uint32_t)pipe_eoff(FMT, K) * PIPE_TILE;
+  const uint32_t a0 = s0 + OFF + tid * ES, a1 = s1 + OFF + tid * ES;
+  if (ES == 4) return fast::F2{lds1(a0), lds1(a1)};
+  int qx, qy;
+  if (ES == 2) {
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(qx) : "r"(a0));
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(qy) : "r"(a1));
+  } else {
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(qx) : "r"(a0));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(qy) : "r"(a1));
+  }
+  const RawInfo& r = a.raw[drv_index];
+  fast::F2 v = fast::vfma(fast::F2{(float)qx, (float)qy}, r.scale, r.offset);
+  const float qnan = __int_as_float(0x7fc00000);
+  v.x = qx == r.fill ? qnan : v.x;
+  v.y = qy == r.fill ? qnan : v.y;
+  return v;
 }
 
 // ---- rare-path helpers ---------------------------------------------------------------------
@@ -162,18 +205,19 @@ __device__ __forceinline__ uint32_t keep_u32(uint32_t x) {
   return y;
 }
 
-template <int SEM, int OUT, int EXTRA>
+template <int SEM, int OUT, int EXTRA, int FMT>
 __global__ void __launch_bounds__(PIPE_THREADS, 1)
 forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
                     const __grid_constant__ PipeSrc src) {
   using fast::F2;
   using fast::M2;
+  static_assert(FMT < FMT_MODIS || EXTRA == 0, "storage formats: the eleven per-step arrays");
   constexpr int NARR = pipe_n_arr(EXTRA);
-  constexpr int NST = pipe_n_stages(EXTRA);
+  constexpr int NST = pipe_n_stages(EXTRA, FMT);
   constexpr bool SWN = (EXTRA & 1) != 0;   // sw_rad_night streamed
   constexpr bool PXT = (EXTRA & 2) != 0;   // temp_annual / pressure streamed
-  constexpr uint32_t SUBB = NARR * PIPE_ROWB;    // bytes per sub-step
-  constexpr uint32_t STAGEB = PIPE_SUB * SUBB;   // bytes per stage
+  constexpr uint32_t SUBB = pipe_eoff(FMT, NARR) * PIPE_TILE;   // bytes per sub-step
+  constexpr uint32_t STAGEB = PIPE_SUB * SUBB;                  // bytes per stage
   // [stage][sub-step][array][PIPE_TILE]
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ SharedLut lut;
@@ -190,7 +234,6 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   const int niter = (nsteps + PIPE_SUB - 1) / PIPE_SUB;  // stage uses; the last may hold 1 step
   const int64_t left = a.N - tile0;
   const int n_live = (int)(left < PIPE_TILE ? left : PIPE_TILE);
-  const uint32_t row_bytes = (uint32_t)n_live * (uint32_t)sizeof(float);
   const uint32_t full0 = smem_u32(&full[0]), empty0 = smem_u32(&empty[0]);
   const uint32_t data0 = smem_u32(dyn_smem);
   const bool producer = tid >= PIPE_CONSUMERS;
@@ -206,8 +249,8 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     }
     __syncwarp();
     for (int s = 0; s < NST && s < niter; ++s)
-      pipe_issue<NARR>(src, nsteps - s * PIPE_SUB >= PIPE_SUB ? PIPE_SUB : 1,
-                       data0 + s * STAGEB, full0 + 8 * s, t0 + s * PIPE_SUB, tile0, row_bytes);
+      pipe_issue<NARR, FMT>(src, nsteps - s * PIPE_SUB >= PIPE_SUB ? PIPE_SUB : 1,
+                       data0 + s * STAGEB, full0 + 8 * s, t0 + s * PIPE_SUB, tile0, (uint32_t)n_live);
   }
   if (a.par_mode != 2) stage_lut<SEM>(a, lut);  // (contains __syncthreads)
   else __syncthreads();                         // (the barriers are visible to everyone)
@@ -218,9 +261,9 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
 #pragma unroll 1
     for (int i = NST; i < niter; ++i) {
       mbar_wait(empty0 + 8 * stage, phase);  // all fifteen warps have read the stage
-      pipe_issue<NARR>(src, nsteps - i * PIPE_SUB >= PIPE_SUB ? PIPE_SUB : 1,
+      pipe_issue<NARR, FMT>(src, nsteps - i * PIPE_SUB >= PIPE_SUB ? PIPE_SUB : 1,
                        data0 + (uint32_t)stage * STAGEB, full0 + 8 * stage,
-                       t0 + (int64_t)i * PIPE_SUB, tile0, row_bytes);
+                       t0 + (int64_t)i * PIPE_SUB, tile0, (uint32_t)n_live);
       if (++stage == NST) { stage = 0; phase ^= 1u; }
     }
     return;
@@ -260,6 +303,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       float p = 1e5f, ta = 0.f;
       if (live) {
         p = a.drv[MOD16_D_PRESSURE].at(0, n);   // per pixel or scalar (checked on the host)
+        if (FMT != FMT_F32 && (a.prep & MOD16_PREP_ELEVATION)) p = pressure_from_elevation(p);
         ta = a.drv[MOD16_D_TEMP_ANNUAL].at(0, n);
       }
       const PixConst x1 = fast::make_pix_const(p, ta, c1, SEM);
@@ -271,7 +315,9 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   const float swn_scalar = a.drv[MOD16_D_SW_RAD_NIGHT].scalar;
   const int gate = a.gate;
   constexpr int n_out = OUT == 0 ? 1 : (OUT == 1 ? 2 : 6);
-  const uint32_t my0 = keep_u32(data0 + (uint32_t)tid * 4u);  // this thread's pixel in a row
+  // this thread's pixel in a row (float32 rows; storage formats index per array)
+  const uint32_t my0 = keep_u32(FMT < FMT_MODIS ? data0 + (uint32_t)tid * 4u : data0);
+  const bool clamp_vpd_n = FMT != FMT_F32 && (a.prep & MOD16_PREP_VPD_NIGHT_CLAMP) != 0;
   const uint32_t full_k = keep_u32(full0), empty_k = keep_u32(empty0);
   const int64_t t_stride = a.N;
   int64_t off = t0 * t_stride + tile0 + tid;        // running output offset
@@ -292,9 +338,24 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       const uint32_t s0 = my0 + stage * STAGEB;
       const uint32_t s1 = TWO ? s0 + SUBB : s0;
 #define M16_IN(k) F2{lds1(s0 + (k) * PIPE_ROWB), lds1(s1 + (k) * PIPE_ROWB)}
-      in.lw_d = M16_IN(0);  in.lw_n = M16_IN(1);  in.sw_d = M16_IN(2);  in.alb = M16_IN(3);
-      in.t_d = M16_IN(4);   in.t_n = M16_IN(5);   in.tmin = M16_IN(6);  in.vpd_d = M16_IN(7);
-      in.vpd_n = M16_IN(8); in.fpar = M16_IN(9);  in.lai = M16_IN(10);
+      if (FMT < FMT_MODIS) {
+        in.lw_d = M16_IN(0);  in.lw_n = M16_IN(1);  in.sw_d = M16_IN(2);  in.alb = M16_IN(3);
+        in.t_d = M16_IN(4);   in.t_n = M16_IN(5);   in.tmin = M16_IN(6);  in.vpd_d = M16_IN(7);
+        in.vpd_n = M16_IN(8); in.fpar = M16_IN(9);  in.lai = M16_IN(10);
+      } else {
+#define M16_RAW(k, d) pipe_load<FMT, k>(s0, s1, (uint32_t)tid, a, d)
+        in.lw_d = M16_RAW(0, MOD16_D_LW_NET_DAY);  in.lw_n = M16_RAW(1, MOD16_D_LW_NET_NIGHT);
+        in.sw_d = M16_RAW(2, MOD16_D_SW_RAD_DAY);  in.alb = M16_RAW(3, MOD16_D_SW_ALBEDO);
+        in.t_d = M16_RAW(4, MOD16_D_TEMP_DAY);     in.t_n = M16_RAW(5, MOD16_D_TEMP_NIGHT);
+        in.tmin = M16_RAW(6, MOD16_D_TMIN);        in.vpd_d = M16_RAW(7, MOD16_D_VPD_DAY);
+        in.vpd_n = M16_RAW(8, MOD16_D_VPD_NIGHT);  in.fpar = M16_RAW(9, MOD16_D_FPAR);
+        in.lai = M16_RAW(10, MOD16_D_LAI);
+#undef M16_RAW
+      }
+      if (FMT != FMT_F32 && clamp_vpd_n) {   // where(vpd_night < 0, 0, vpd_night): NaN stays
+        in.vpd_n.x = in.vpd_n.x < 0.0f ? 0.0f : in.vpd_n.x;
+        in.vpd_n.y = in.vpd_n.y < 0.0f ? 0.0f : in.vpd_n.y;
+      }
       if (SWN) in.sw_n = M16_IN(pipe_slot_swn(EXTRA));
       else in.sw_n = F2{swn_scalar, swn_scalar};
       if (PXT) {  // per-step annual mean temperature and pressure: rebuild the pixel terms
@@ -409,14 +470,15 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   }
 }
 
-template <int SEM, int OUT, int EXTRA>
+template <int SEM, int OUT, int EXTRA, int FMT>
 static int launch_pipe_inst(const ForwardArgs<float>& a, const PipeSrc& src, dim3 grid,
                             cudaStream_t st) {
-  constexpr size_t smem = (size_t)pipe_n_stages(EXTRA) * PIPE_SUB * pipe_n_arr(EXTRA) * PIPE_ROWB;
+  constexpr size_t smem = (size_t)pipe_n_stages(EXTRA, FMT) * PIPE_SUB *
+                          pipe_eoff(FMT, pipe_n_arr(EXTRA)) * PIPE_TILE;
   // (the attribute is per function AND per device: set before every launch, it is cheap)
-  M16_CUDA_CHECK(cudaFuncSetAttribute(forward_pipe_kernel<SEM, OUT, EXTRA>,
+  M16_CUDA_CHECK(cudaFuncSetAttribute(forward_pipe_kernel<SEM, OUT, EXTRA, FMT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  forward_pipe_kernel<SEM, OUT, EXTRA><<<grid, PIPE_THREADS, smem, st>>>(a, src);
+  forward_pipe_kernel<SEM, OUT, EXTRA, FMT><<<grid, PIPE_THREADS, smem, st>>>(a, src);
   M16_CUDA_CHECK(cudaGetLastError());
   return MOD16_OK;
 }
@@ -424,18 +486,25 @@ static int launch_pipe_inst(const ForwardArgs<float>& a, const PipeSrc& src, dim
 // Instantiated per semantics in mod16_forward_pipe_{static,instance}.cu (parallel builds).
 // EXTRA 2 / 3 (time-varying annual temperature / pressure) exist for the summed and the
 // day / night outputs; `separate=True` with such drivers takes the strided kernel.
+// Storage formats (FMT > 0) exist for the summed and the day / night outputs of the eleven
+// per-step arrays.
 template <int SEM>
 int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode, int extra,
-                    dim3 grid, cudaStream_t st) {
-#define M16_PIPE(O, E) \
-  if (out_mode == O && extra == E) return launch_pipe_inst<SEM, O, E>(a, src, grid, st)
-  M16_PIPE(0, 0); M16_PIPE(0, 1); M16_PIPE(0, 2); M16_PIPE(0, 3);
-  M16_PIPE(1, 0); M16_PIPE(1, 1); M16_PIPE(1, 2); M16_PIPE(1, 3);
-  M16_PIPE(2, 0); M16_PIPE(2, 1);
+                    int fmt, dim3 grid, cudaStream_t st) {
+#define M16_PIPE(O, E, F) \
+  if (out_mode == O && extra == E && fmt == F) \
+    return launch_pipe_inst<SEM, O, E, F>(a, src, grid, st)
+  M16_PIPE(0, 0, 0); M16_PIPE(0, 1, 0); M16_PIPE(0, 2, 0); M16_PIPE(0, 3, 0);
+  M16_PIPE(1, 0, 0); M16_PIPE(1, 1, 0); M16_PIPE(1, 2, 0); M16_PIPE(1, 3, 0);
+  M16_PIPE(2, 0, 0); M16_PIPE(2, 1, 0);
+  M16_PIPE(0, 0, 1); M16_PIPE(0, 0, 2); M16_PIPE(0, 0, 3);
+  M16_PIPE(1, 0, 1); M16_PIPE(1, 0, 2); M16_PIPE(1, 0, 3);
 #undef M16_PIPE
   return MOD16_ERR_FLAGS;
 }
 
-inline bool pipe_has_variant(int out_mode, int extra) { return out_mode < 2 || extra < 2; }
+inline bool pipe_has_variant(int out_mode, int extra, int fmt = 0) {
+  return fmt == 0 ? (out_mode < 2 || extra < 2) : (out_mode < 2 && extra == 0);
+}
 
 }  // namespace mod16

@@ -3,7 +3,7 @@
 
 namespace mod16 {
 int launch_pipe_instance(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode,
-                         int extra, dim3 grid, cudaStream_t st) {
-  return launch_pipe_sem<SEM_INSTANCE>(a, src, out_mode, extra, grid, st);
+                         int extra, int fmt, dim3 grid, cudaStream_t st) {
+  return launch_pipe_sem<SEM_INSTANCE>(a, src, out_mode, extra, fmt, grid, st);
 }
 }  // namespace mod16

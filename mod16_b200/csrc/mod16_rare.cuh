@@ -56,22 +56,54 @@ __device__ __forceinline__ void load_column(const ForwardArgs<float>& a, int64_t
   }
 }
 
+// MOD16.air_pressure (:415-447): P = 101325 (1 - 0.0065 z / 288.15)^5.256, in double
+__device__ __forceinline__ float pressure_from_elevation(float z) {
+  return (float)(101325.0 * pow(1.0 - (0.0065 * (double)z) / 288.15, 5.256));
+}
+
+// A storage-format element as the float the fused kernel computes with (one FMA, like the
+// hot path); `fill` -> NaN.
+__device__ __forceinline__ float dequant(int q, const RawInfo& r) {
+  if (q == r.fill) return __int_as_float(0x7fc00000);
+  return fmaf((float)q, r.scale, r.offset);
+}
+
+// Driver k of one element for any call form: float arrays (plain entries) or storage
+// formats with the loaders' conversions (mod16_forward_raw_f32).
+__device__ __forceinline__ float drv_at(const ForwardArgs<float>& a, int k, int64_t t, int64_t n) {
+  const Arr<float>& d = a.drv[k];
+  if (a.raw_fmt == 0) return d.at(t, n);
+  float v;
+  if (!d.ptr) {
+    v = d.scalar;
+  } else {
+    const RawInfo& r = a.raw[k];
+    const int64_t i = t * d.ts + n * d.ns;
+    if (r.dtype == MOD16_T_I16) v = dequant((int)__ldg((const short*)d.ptr + i), r);
+    else if (r.dtype == MOD16_T_U8) v = dequant((int)__ldg((const unsigned char*)d.ptr + i), r);
+    else v = __ldg(d.ptr + i);
+  }
+  if (k == MOD16_D_VPD_NIGHT && (a.prep & MOD16_PREP_VPD_NIGHT_CLAMP)) v = v < 0.0f ? 0.0f : v;
+  if (k == MOD16_D_PRESSURE && (a.prep & MOD16_PREP_ELEVATION)) v = pressure_from_elevation(v);
+  return v;
+}
+
 __device__ __forceinline__ StepIn load_step(const ForwardArgs<float>& a, int64_t t, int64_t n) {
   StepIn in;
-  in.lw_d = a.drv[MOD16_D_LW_NET_DAY].at(t, n);
-  in.lw_n = a.drv[MOD16_D_LW_NET_NIGHT].at(t, n);
-  in.sw_d = a.drv[MOD16_D_SW_RAD_DAY].at(t, n);
-  in.sw_n = a.drv[MOD16_D_SW_RAD_NIGHT].at(t, n);
-  in.alb = a.drv[MOD16_D_SW_ALBEDO].at(t, n);
-  in.t_d = a.drv[MOD16_D_TEMP_DAY].at(t, n);
-  in.t_n = a.drv[MOD16_D_TEMP_NIGHT].at(t, n);
-  in.t_ann = a.drv[MOD16_D_TEMP_ANNUAL].at(t, n);
-  in.tmin = a.drv[MOD16_D_TMIN].at(t, n);
-  in.vpd_d = a.drv[MOD16_D_VPD_DAY].at(t, n);
-  in.vpd_n = a.drv[MOD16_D_VPD_NIGHT].at(t, n);
-  in.p = a.drv[MOD16_D_PRESSURE].at(t, n);
-  in.fpar = a.drv[MOD16_D_FPAR].at(t, n);
-  in.lai = a.drv[MOD16_D_LAI].at(t, n);
+  in.lw_d = drv_at(a, MOD16_D_LW_NET_DAY, t, n);
+  in.lw_n = drv_at(a, MOD16_D_LW_NET_NIGHT, t, n);
+  in.sw_d = drv_at(a, MOD16_D_SW_RAD_DAY, t, n);
+  in.sw_n = drv_at(a, MOD16_D_SW_RAD_NIGHT, t, n);
+  in.alb = drv_at(a, MOD16_D_SW_ALBEDO, t, n);
+  in.t_d = drv_at(a, MOD16_D_TEMP_DAY, t, n);
+  in.t_n = drv_at(a, MOD16_D_TEMP_NIGHT, t, n);
+  in.t_ann = drv_at(a, MOD16_D_TEMP_ANNUAL, t, n);
+  in.tmin = drv_at(a, MOD16_D_TMIN, t, n);
+  in.vpd_d = drv_at(a, MOD16_D_VPD_DAY, t, n);
+  in.vpd_n = drv_at(a, MOD16_D_VPD_NIGHT, t, n);
+  in.p = drv_at(a, MOD16_D_PRESSURE, t, n);
+  in.fpar = drv_at(a, MOD16_D_FPAR, t, n);
+  in.lai = drv_at(a, MOD16_D_LAI, t, n);
   in.rc_d = a.has_rc ? a.rc[0].at(t, n) : 0.0f;
   in.rc_n = a.has_rc ? a.rc[1].at(t, n) : 0.0f;
   return in;

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _abi, hostcopy
+from .rawio import RawDriver, DTYPE_CODE, dequantize, prep_word
 
 _TORCH_DT = {np.dtype('float32'): torch.float32, np.dtype('float64'): torch.float64}
 
@@ -37,7 +38,7 @@ def _shape(x):
 
 def _arrayish(x):
     'python sequences (lists, tuples) and array-likes without .shape become numpy arrays.'
-    if _is_scalar(x) or isinstance(x, (np.ndarray, torch.Tensor)):
+    if _is_scalar(x) or isinstance(x, (np.ndarray, torch.Tensor, RawDriver)):
         return x
     return np.asarray(x)
 
@@ -56,7 +57,9 @@ def result_dtype(values, dtype=None):
     for v in values:
         if isinstance(v, (int, float, bool)):
             continue  # weak python scalar
-        if isinstance(v, torch.Tensor):
+        if isinstance(v, RawDriver):
+            kinds.append(np.dtype('float32'))
+        elif isinstance(v, torch.Tensor):
             kinds.append(np.dtype(str(v.dtype).replace('torch.', '')))
         elif isinstance(v, (np.ndarray, np.generic)):
             kinds.append(v.dtype)
@@ -74,6 +77,8 @@ def pick_device(values, device=None):
     if device is not None:
         return torch.device(device)
     for v in values:
+        if isinstance(v, RawDriver):
+            v = v.raw
         if isinstance(v, torch.Tensor) and v.device.type == 'cuda':
             return v.device
     if not torch.cuda.is_available():
@@ -136,9 +141,10 @@ class _Staged(object):
         self.keep.append(t)
         return t
 
-    def fill(self, slot, x, T, N, ndim):
+    def fill(self, slot, x, T, N, ndim, keep_dtype=False):
         '''
         Describes input ``x`` (broadcastable to the call's (T, N) view) in ``slot``.
+        ``keep_dtype``: stage the array in its own element type (storage formats).
         '''
         if _is_scalar(x):
             slot.ptr = None
@@ -146,7 +152,12 @@ class _Staged(object):
             slot.n_stride = 0
             slot.scalar = float(x)
             return
-        t = self.tensor(x)
+        if keep_dtype:
+            own = x.dtype if isinstance(x, torch.Tensor) else \
+                getattr(torch, np.asarray(x).dtype.name)
+            t = self.tensor(x, own)
+        else:
+            t = self.tensor(x)
         shp = tuple(t.shape)
         if len(self.full_shape) > 2 and len(shp) >= 2:
             # more than two axes: leading axes fold into time; materialise the broadcast
@@ -219,7 +230,7 @@ def _view_2d(shape):
 def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static',
                 out_mode='sum', gate='global', dtype=None, r_corr_list=None, device=None,
                 stream=None, force=0, as_torch=None, gate_flag=None, out=None,
-                workspace=None):
+                workspace=None, prep=None):
     '''
     Launches K1 once.
 
@@ -229,6 +240,11 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     pft, table : uint8 land-cover code per pixel and the dense 11 x 13 BPLUT table
     out_mode : 'sum' | 'day_night' | 'components'
     gate     : 'global' (reference) | 'element' | 'open' | 'closed' | 'open_track' | 'fixup'
+
+    drivers may hold ``rawio.RawDriver`` objects (storage formats: uint8 / int16 with scale,
+    offset and fill value); ``prep`` names loader conversions applied on the device:
+    'vpd_night_clamp' (calibration.py:401), 'elevation' (the ``pressure`` driver holds
+    elevation in metres, calibration.py:405-408).  Both select the float32 path.
 
     out      : optional list of preallocated CUDA tensors ((T, N), contiguous) to write into
     workspace : optional int64 CUDA tensor, scratch of the float32 path (default: a cached
@@ -249,8 +265,13 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     np_dtype = result_dtype(everything, dtype)
     dev = pick_device(everything + ([pft] if pft is not None else []), device)
     if as_torch is None:
-        as_torch = any(isinstance(v, torch.Tensor) and v.device.type == 'cuda'
-                       for v in everything)
+        as_torch = any((isinstance(v, torch.Tensor) and v.device.type == 'cuda') or
+                       (isinstance(v, RawDriver) and v.is_cuda()) for v in everything)
+    prep = prep_word(prep)
+    raw = prep != 0 or any(isinstance(v, RawDriver) for v in drivers)
+    if raw and (np_dtype != np.dtype('float32') or r_corr_list is not None or force):
+        # storage formats belong to the float32 kernels: other call forms see plain arrays
+        drivers, prep, raw = _plain_drivers(drivers, prep, dev, np_dtype), 0, False
 
     shapes = [_shape(v) for v in everything]
     if pft is not None:
@@ -260,15 +281,43 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     T, N = _view_2d(full_shape)
 
     with torch.cuda.device(dev), launch_stream(dev, stream) as (s, caller_stream):
-        return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
-                              semantics, out_mode, gate, r_corr_list, force, as_torch,
-                              gate_flag, out, workspace, full_shape, T, N, caller_stream)
+        try:
+            return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
+                                  semantics, out_mode, gate, r_corr_list, force, as_torch,
+                                  gate_flag, out, workspace, full_shape, T, N, caller_stream,
+                                  prep if raw else None)
+        except _abi.LayoutError:
+            # a storage-format layout the fused kernel cannot stream: same arithmetic as
+            # torch operations on the device first, then the plain float32 entry
+            drivers = _plain_drivers(drivers, prep, dev, np_dtype)
+            return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
+                                  semantics, out_mode, gate, r_corr_list, force, as_torch,
+                                  gate_flag, out, workspace, full_shape, T, N, caller_stream,
+                                  None)
+
+
+def _plain_drivers(drivers, prep, dev, np_dtype):
+    'Storage-format drivers and loader conversions as plain device tensors of `np_dtype`.'
+    t_dtype = _TORCH_DT[np_dtype]
+    out = []
+    for k, v in enumerate(drivers):
+        clamp = k == 10 and (prep & _abi.PREP_VPD_NIGHT_CLAMP)
+        if isinstance(v, RawDriver):
+            v = dequantize(v, dev, prep_clamp=clamp).to(t_dtype)
+        elif clamp:
+            v = torch.as_tensor(v).to(dev)
+            v = torch.where(v < 0, torch.zeros_like(v), v)
+        if k == 11 and (prep & _abi.PREP_ELEVATION):       # MOD16.air_pressure (:415-447)
+            z = torch.as_tensor(v).to(dev).double()
+            v = (101325.0 * torch.pow(1.0 - (0.0065 * z) / 288.15, 5.256)).to(t_dtype)
+        out.append(v)
+    return out
 
 
 def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, semantics,
                    out_mode, gate, r_corr_list, force, as_torch, gate_flag, out, workspace,
-                   full_shape, T, N, caller_stream):
-    'Body of run_forward; the current stream is `s`.'
+                   full_shape, T, N, caller_stream, prep=None):
+    'Body of run_forward; the current stream is `s`.  `prep` not None: the storage-format entry.'
     params = plist if plist else None
     st = _Staged(dev, np_dtype)
     st.full_shape = full_shape
@@ -281,12 +330,27 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
                 t = t.to(st.t_dtype)
             drivers[k] = t
             st.keep.append(t)
-    cd = _abi.Drivers()
-    for k, v in enumerate(drivers):
-        st.fill(cd.drv[k], v, T, N, len(full_shape))
-    cd.has_r_corr = 1 if r_corr_list is not None else 0
-    for k, v in enumerate(extra[:2]):
-        st.fill(cd.r_corr[k], v, T, N, len(full_shape))
+    if prep is not None:
+        cd = _abi.RawDrivers()
+        cd.prep = prep
+        for k, v in enumerate(drivers):
+            slot = cd.drv[k]
+            slot.dtype, slot.has_fill, slot.scale, slot.offset, slot.fill = _abi.T_F32, 0, 1.0, 0.0, 0
+            if isinstance(v, RawDriver):
+                st.fill(slot, v.raw, T, N, len(full_shape), keep_dtype=True)
+                slot.dtype = DTYPE_CODE[v.np_dtype]
+                slot.scale, slot.offset = v.scale, v.offset
+                if v.fill is not None and slot.dtype != _abi.T_F32:
+                    slot.has_fill, slot.fill = 1, int(v.fill)
+            else:
+                st.fill(slot, v, T, N, len(full_shape))
+    else:
+        cd = _abi.Drivers()
+        for k, v in enumerate(drivers):
+            st.fill(cd.drv[k], v, T, N, len(full_shape))
+        cd.has_r_corr = 1 if r_corr_list is not None else 0
+        for k, v in enumerate(extra[:2]):
+            st.fill(cd.r_corr[k], v, T, N, len(full_shape))
 
     cp = _abi.Params()
     if pft is not None:
@@ -349,7 +413,10 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
         co.workspace = ws.data_ptr()
         co.workspace_bytes = ws.numel() * ws.element_size()
         st.keep.append(ws)
-    fn = lib.mod16_forward_f32 if np_dtype == np.dtype('float32') else lib.mod16_forward_f64
+    if prep is not None:
+        fn = lib.mod16_forward_raw_f32
+    else:
+        fn = lib.mod16_forward_f32 if np_dtype == np.dtype('float32') else lib.mod16_forward_f64
     _abi.check(fn(ctypes.byref(cd), ctypes.byref(cp), ctypes.byref(co), T, N, flags,
                   ctypes.c_void_p(handle)))
     outs = [o.reshape(full_shape) for o in outs]

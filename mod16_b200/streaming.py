@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from .forward import run_forward
+from .rawio import RawDriver
 from .synthetic import DRIVER_NAMES, PER_PIXEL
 
 _PER_STEP = [k for k in DRIVER_NAMES if k not in PER_PIXEL and k != 'sw_rad_night']
@@ -55,9 +56,15 @@ class StreamedForward(object):
     N : pixels per time step
     slab_T : time steps per slab (device memory used: 2 x 12 x slab_T x N x itemsize)
     table, pft : dense 11 x 13 BPLUT table and uint8 land-cover code per pixel
+    formats : optional dict name -> (numpy dtype, scale, offset, fill) of the per-step drivers
+        that arrive in a storage format (``rawio.RawDriver`` entries of ``host`` in ``run``):
+        their slabs cross the bus and sit in HBM as stored -- uint8 / int16 -- and the fused
+        kernel converts them while it reads
+    prep : loader conversions applied on the device, see ``run_forward``
     '''
 
-    def __init__(self, N, slab_T, table, pft, device=None, dtype=np.float32, gate='global'):
+    def __init__(self, N, slab_T, table, pft, device=None, dtype=np.float32, gate='global',
+                 formats=None, prep=None):
         self.N, self.slab_T = int(N), int(slab_T)
         self.device = torch.device(device if device is not None else
                                    ('cuda', torch.cuda.current_device()))
@@ -67,8 +74,13 @@ class StreamedForward(object):
         self.gate = gate
         with torch.cuda.device(self.device):
             self.pft = torch.as_tensor(np.asarray(pft, np.uint8)).to(self.device)
+            self.formats = dict(formats or {})
+            self.prep = prep
+            kinds = dict((k, getattr(torch, np.dtype(self.formats[k][0]).name)
+                          if k in self.formats else self.t_dtype) for k in _PER_STEP)
+            kinds['out'] = self.t_dtype
             self.bufs = [dict((k, torch.empty((self.slab_T, self.N), device=self.device,
-                                              dtype=self.t_dtype)) for k in _PER_STEP + ['out'])
+                                              dtype=kinds[k])) for k in _PER_STEP + ['out'])
                          for _ in range(2)]
             self.flags = [torch.zeros(1, device=self.device, dtype=torch.int32) for _ in range(2)]
             self.s_in = torch.cuda.Stream(self.device)
@@ -105,7 +117,8 @@ class StreamedForward(object):
                     if ev_run[b] is not None:
                         self.s_in.wait_event(ev_run[b])   # kernel that read this set is done
                     for k in _PER_STEP:
-                        buf[k][:rows].copy_(host[k][t0:t1], non_blocking=True)
+                        src = host[k].raw if isinstance(host[k], RawDriver) else host[k]
+                        buf[k][:rows].copy_(src[t0:t1], non_blocking=True)
                         self.h2d_bytes += rows * self.N * buf[k].element_size()
                     ev_in = torch.cuda.Event()
                     ev_in.record(self.s_in)
@@ -113,13 +126,14 @@ class StreamedForward(object):
                     self.s_run.wait_event(ev_in)
                     if ev_out[b] is not None:
                         self.s_run.wait_event(ev_out[b])  # previous result left the buffer
-                    drv = [buf[k][:rows] if k in buf else
+                    drv = [(RawDriver(buf[k][:rows], *self.formats[k][1:]) if k in self.formats
+                            else buf[k][:rows]) if k in buf else
                            (per_pixel[k] if k in per_pixel else host.get(k, 0))
                            for k in DRIVER_NAMES]
                     run_forward(drv, pft=self.pft, table=self.table, semantics='static',
                                 out_mode='sum', gate=self.gate, dtype=self.np_dtype,
                                 device=dev, stream=self.s_run, gate_flag=self.flags[b],
-                                out=[buf['out'][:rows]])
+                                out=[buf['out'][:rows]], prep=self.prep)
                     self.launches += (2 if self.gate == 'global' else 1) * \
                         (3 if self.np_dtype == np.float32 else 1)
                     ev_run[b] = torch.cuda.Event()
