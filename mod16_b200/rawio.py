@@ -61,14 +61,19 @@ class RawDriver(object):
         return RawDriver(self.raw[idx], self.scale, self.offset, self.fill)
 
     def physical(self, dtype=np.float64):
-        'The values the model sees, for checks on the host (numpy; fill -> NaN).'
+        '''
+        The values the model sees, for checks on the host: exactly the float32 numbers the
+        kernel's fused multiply-add ``raw * float32(scale) + float32(offset)`` produces
+        (formed in double, rounded once), fill -> NaN; returned as ``dtype``.
+        '''
         raw = self.raw.cpu().numpy() if isinstance(self.raw, torch.Tensor) else np.asarray(self.raw)
         if self.np_dtype == np.dtype('float32'):
             return raw.astype(dtype)
-        out = raw.astype(dtype) * dtype(self.scale) + dtype(self.offset)
+        out = (raw.astype(np.float64) * np.float64(np.float32(self.scale)) +
+               np.float64(np.float32(self.offset))).astype(np.float32)
         if self.fill is not None:
             out[raw == self.fill] = np.nan
-        return out
+        return out.astype(dtype)
 
 
 def quantize(x, dtype, scale=1.0, offset=0.0, fill=None):

@@ -66,8 +66,8 @@ class StreamedForward(object):
     def __init__(self, N, slab_T, table, pft, device=None, dtype=np.float32, gate='global',
                  formats=None, prep=None):
         self.N, self.slab_T = int(N), int(slab_T)
-        self.device = torch.device(device if device is not None else
-                                   ('cuda', torch.cuda.current_device()))
+        self.device = torch.device(device) if device is not None else \
+            torch.device('cuda', torch.cuda.current_device())
         self.np_dtype = np.dtype(dtype)
         self.t_dtype = torch.float32 if self.np_dtype == np.float32 else torch.float64
         self.table = np.asarray(table, np.float64)

@@ -152,8 +152,8 @@ def test_negative_vpd_and_fill_temperatures(cuda_lib, semantics, out_mode):
             for c in range(3):
                 parity.assert_parity(got[3 * h + c], comps[h][c], np.float32, scale,
                                      what='component %d %d' % (h, c))
-    # (the fill temperatures came out as NaN: 1 % of the days, 1 % of the nights)
-    assert np.isnan(got[0]).mean() > 0.008
+    if out_mode != 'components':   # the fill temperatures came out as NaN: 1 % of the days
+        assert np.isnan(got[0]).mean() > 0.008
 
 
 def test_chunked_plan_equals_one_call(cuda_lib):

