@@ -612,6 +612,110 @@ def global_year(args, device, world, rank, steps, warm):
     return res if rank == 0 else None
 
 
+# int16 packings of the meteorological drivers for the PACKED storage layout (netCDF-style
+# scale / offset): name -> (scale, offset, fill)
+PACKED_MET = {'lw_net_day': (0.01, 0.0, -32768), 'lw_net_night': (0.01, 0.0, -32768),
+              'sw_rad_day': (0.02, 0.0, -32768), 'temp_day': (0.01, 273.15, -32768),
+              'temp_night': (0.01, 273.15, -32768), 'tmin': (0.01, 273.15, -32768),
+              'vpd_day': (0.25, 0.0, -32768), 'vpd_night': (0.25, 0.0, -32768)}
+MODIS_NATIVE = {'fpar': (np.uint8, 0.01, 0.0, 255), 'lai': (np.uint8, 0.1, 0.0, 255),
+                'sw_albedo': (np.int16, 0.001, 0.0, 32767)}
+
+
+def end_to_end(args, device, world, rank, numa, drv, pft, table, T, N, np_dtype, t_dtype,
+               barrier):
+    """
+    The same metric through the public API with HOST buffers: every step's drivers are copied
+    from pinned host memory to the device and its ET back inside the timed region
+    (mod16_b200.streaming.StreamedForward: slabs of time steps, copies overlapped with the
+    kernel).  Three input formats, same physical values:
+      packed  -- the drivers as an archive stores them: fPAR / LAI uint8, albedo and the
+                 meteorological fields int16 with scale / offset (20 B per pixel-timestep);
+                 the fused kernel converts while it reads (mod16_forward_raw_f32)
+      modis   -- fPAR / LAI uint8, albedo int16, meteorology float32 (36 B)
+      float32 -- every driver a float32 array, the reference's in-memory form (44 B)
+    `e2e` reports the packed leg (host -> ET is PCIe-bound: bytes per unit are what counts);
+    the other two are listed under `legs`.
+    """
+    import torch
+    import torch.distributed as dist
+    from mod16_b200 import rawio, synthetic
+    from mod16_b200.streaming import StreamedForward
+    names = [k for k in synthetic.DRIVER_NAMES
+             if k not in synthetic.PER_PIXEL and k != 'sw_rad_night']
+    Te = min(args.e2e_T, T)
+    try:  # as many time steps as a third of the free host memory holds pinned
+        import psutil
+        room = psutil.virtual_memory().available / 3.0 / max(world, 1)
+        Te = max(4, min(Te, int(room // (12 * N * np_dtype.itemsize))))
+    except Exception:
+        Te = min(Te, 16)
+    tq = torch.tensor([Te], device=device, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(tq, op=dist.ReduceOp.MIN)
+    Te = int(tq.item())
+    slab = max(1, min(8, Te // 4))
+    per_pixel = dict((k, drv[k].cpu().pin_memory()) for k in synthetic.PER_PIXEL)
+    legs = {}
+    layouts = ['float32'] + (['modis', 'packed'] if np_dtype == np.float32 else [])
+    for layout in layouts:
+        fmt = {}
+        if layout in ('modis', 'packed'):
+            fmt.update(MODIS_NATIVE)
+        if layout == 'packed':
+            fmt.update(dict((k, (np.int16,) + v) for k, v in PACKED_MET.items()))
+        host = dict(per_pixel)
+        host['sw_rad_night'] = 0
+        for k in names:
+            if k in fmt:
+                q = rawio.quantize(drv[k][:Te], fmt[k][0], *fmt[k][1:])
+                pinned = torch.empty(q.raw.shape, dtype=q.raw.dtype, pin_memory=True)
+                pinned.copy_(q.raw)
+                host[k] = rawio.RawDriver(pinned, q.scale, q.offset, q.fill)
+                del q
+            else:
+                host[k] = torch.empty((Te, N), dtype=t_dtype, pin_memory=True)
+                host[k].copy_(drv[k][:Te])
+        out_host = torch.empty((Te, N), dtype=t_dtype, pin_memory=True)
+        runner = StreamedForward(N, slab, table, pft.cpu().numpy(), device=device,
+                                 dtype=np_dtype, gate=args.gate, formats=fmt)
+        runner.run(host, out_host)
+        barrier()
+        runner.h2d_bytes = runner.d2h_bytes = runner.launches = 0
+        reps = 3 if Te > 64 else max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            runner.run(host, out_host)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        ok = bool(np.isfinite(out_host[:1, :4096].numpy()).all())
+        assert ok, 'implausible ET from the end-to-end leg'
+        legs[layout] = {'value': world * reps * Te * N / dt, 'unit': 'pixel-timesteps/s',
+                        'h2d_bytes_per_step': runner.h2d_bytes // reps,
+                        'd2h_bytes_per_step': runner.d2h_bytes // reps,
+                        'h2d_bytes_per_unit': runner.h2d_bytes / reps / (Te * N)}
+        del host, out_host, runner
+        torch.cuda.empty_cache()
+    head = 'packed' if 'packed' in legs else 'float32'
+    e2e = dict(legs[head])
+    e2e['input_format'] = {
+        'packed': 'storage formats: fPAR / LAI uint8, albedo + meteorology int16 (scale, '
+                  'offset, fill), converted inside the fused kernel; float32 arithmetic and '
+                  'output; parity: tests/test_raw_formats.py',
+        'float32': 'float32 arrays'}[head]
+    e2e['legs'] = legs
+    e2e['sample'] = ('%d of the %d steps x %d pixels per GPU from pinned host memory through '
+                     'mod16_b200.streaming.StreamedForward (slabs of %d steps, copies '
+                     'overlapped with the kernel)%s' % (
+                         Te, T, N, slab,
+                         '' if numa is None else '; rank bound to NUMA node %d' % numa))
+    return e2e
+
+
 def secondary_lines(args, device, world, rank, drv_list, drv, pft, table, out):
     """
     Bounded runs of the other BASELINE.json configurations (and of the other entry points of
@@ -828,55 +932,8 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        # the whole resident block goes through the host: as many of its time steps as a
-        # third of the free host memory holds (pinned), all 365 on a box with >= 300 GB free
-        Te = min(args.e2e_T, T)
-        try:
-            import psutil
-            room = psutil.virtual_memory().available / 3.0 / max(world, 1)
-            Te = max(4, min(Te, int(room // (12 * N * np_dtype.itemsize))))
-        except Exception:
-            Te = min(Te, 16)
-        tq = torch.tensor([Te], device=device, dtype=torch.int64)
-        if world > 1:
-            dist.all_reduce(tq, op=dist.ReduceOp.MIN)
-        Te = int(tq.item())
-        names = [k for k in synthetic.DRIVER_NAMES
-                 if k not in synthetic.PER_PIXEL and k != 'sw_rad_night']
-        host = {}
-        for k in names:
-            host[k] = torch.empty((Te, N), dtype=t_dtype, pin_memory=True)
-            host[k].copy_(drv[k][:Te])
-        for k in synthetic.PER_PIXEL:
-            host[k] = drv[k].cpu().pin_memory()
-        host['sw_rad_night'] = 0
-        out_host = torch.empty((Te, N), dtype=t_dtype, pin_memory=True)
-        slab = max(1, min(8, Te // 4))
-        runner = StreamedForward(N, slab, table, pft.cpu().numpy(), device=device,
-                                 dtype=np_dtype, gate=args.gate)
-        runner.run(host, out_host)
-        barrier()
-        runner.h2d_bytes = runner.d2h_bytes = runner.launches = 0
-        reps = 3 if Te > 64 else max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            runner.run(host, out_host)
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {'value': world * reps * Te * N / dt, 'unit': 'pixel-timesteps/s',
-               'h2d_bytes_per_step': runner.h2d_bytes // reps,
-               'd2h_bytes_per_step': runner.d2h_bytes // reps,
-               'sample': '%d of the %d steps x %d pixels per GPU from pinned host memory through '
-                         'mod16_b200.streaming.StreamedForward (slabs of %d steps, copies '
-                         'overlapped with the kernel)%s' % (Te, T, N, slab, '' if numa is None
-                                                            else '; rank bound to NUMA node %d'
-                                                            % numa)}
-        assert np.isfinite(out_host[:1, :4096].numpy()).all()
-        del host, out_host, runner
+        e2e = end_to_end(args, device, world, rank, numa, drv, pft, table, T, N, np_dtype,
+                         t_dtype, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:   # (reported at N = 1 only)
