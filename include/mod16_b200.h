@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 7
+#define MOD16_ABI_VERSION 8
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -78,6 +78,23 @@ enum {
 #define MOD16_OUT_DAY_NIGHT 0x10u  /* out[0] = day, out[1] = night */
 #define MOD16_OUT_COMPONENTS 0x20u /* out[0..2] = day canopy, soil, transpiration;
                                       out[3..5] = night  (separate=True, :789-790) */
+#define MOD16_OUT_ANNUAL 0x30u     /* float32 static path only, no per-step output: out[0] is
+                                      a zero-initialised uint64 (n_groups, N) array that
+                                      receives, per pixel and group of time steps (year),
+                                      the evapotranspiration sum [mm] of the calibration's
+                                      precipitation constraint -- max(LE, 0) * 86400 /
+                                      lambda((T_day + T_night) / 2), mod16/calibration.py:
+                                      783-790, :838-842 -- in units of 2^-32 mm.  Integer
+                                      accumulation: the sums do not depend on the launch
+                                      geometry or on the order of the atomic adds.  A NaN
+                                      element adds 2^54: a sum >= 2^54 reads as NaN, like
+                                      the reference's `x.sum()`.  Groups of at most 1000
+                                      steps.  gate_flag is required; if more elements need
+                                      the double-precision pass than the workspace (plus 512
+                                      per block) holds, MOD16_ANNUAL_OVERFLOW is OR-ed into
+                                      *gate_flag and the sums are incomplete: rerun with a
+                                      larger workspace. */
+#define MOD16_ANNUAL_OVERFLOW 0x40000000
 #define MOD16_OUT_MASK 0xF0u
 /* the static path's batch-global transpiration gate `if np.any(g_surf > 0)` (:343) */
 #define MOD16_GATE_GLOBAL 0x000u     /* call-exact: optimistic pass + device-side fix-up */
@@ -136,6 +153,11 @@ typedef struct mod16_out {
      inside the main kernel (same results, slow).  Contents are scratch. */
   void* workspace;
   int64_t workspace_bytes;
+  /* MOD16_OUT_ANNUAL: device int32[T], group (year) index of every time step (indices
+     outside [0, n_groups) are skipped) */
+  const int32_t* group;
+  int32_t n_groups;
+  int32_t reserved;
 } mod16_out_t;
 
 /*

@@ -12,7 +12,7 @@ N_DRIVERS = 14
 
 # flag words (mirror include/mod16_b200.h)
 SEM_STATIC, SEM_INSTANCE = 0x0, 0x1
-OUT_SUM, OUT_DAY_NIGHT, OUT_COMPONENTS = 0x00, 0x10, 0x20
+OUT_SUM, OUT_DAY_NIGHT, OUT_COMPONENTS, OUT_ANNUAL = 0x00, 0x10, 0x20, 0x30
 GATE_GLOBAL, GATE_ELEMENT, GATE_OPEN, GATE_CLOSED = 0x000, 0x100, 0x200, 0x300
 GATE_OPEN_TRACK, GATE_FIXUP = 0x400, 0x500
 FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
@@ -20,10 +20,11 @@ KERNEL_PIPE, KERNEL_STRIDED, KERNEL_EXACT = 1, 2, 3   # mod16_last_forward_kerne
 T_F32, T_I16, T_U8 = 0, 1, 2                            # mod16_raw_driver_t.dtype
 PREP_VPD_NIGHT_CLAMP, PREP_ELEVATION = 0x1, 0x2
 ERR_LAYOUT = -7
+ANNUAL_OVERFLOW = 0x40000000
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                         'libmod16_b200.so')
 
@@ -60,7 +61,9 @@ class Params(ctypes.Structure):
 
 class Out(ctypes.Structure):
     _fields_ = [('out', ctypes.c_void_p * 6), ('gate_flag', ctypes.c_void_p),
-                ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_int64)]
+                ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_int64),
+                ('group', ctypes.c_void_p), ('n_groups', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)]
 
 
 class Aggregate(ctypes.Structure):

@@ -113,3 +113,17 @@ def constrain_by_map(pred_le, years, lhv, annual_precip, **kw):
     diff = torch.clamp(annual - precip, min=0.0)                      # :791-792
     val = -100.0 * ((diff * diff).mean() / precip.sum())              # :795-796
     return val if as_torch else float(val.item())
+
+
+def constrain_by_map_fused(params, drivers, years, annual_precip, **kw):
+    '''
+    ``constrain_by_map(MOD16._et(params, *drivers), years, lhv, annual_precip)`` with ``lhv``
+    from the mean of day and night temperature (reference mod16/calibration.py:775-796,
+    :838-849) in ONE kernel pass: the annual sums are an epilogue of the forward model
+    (``MOD16._annual_et``), only the (Y, N) remainder runs as torch operations.
+    '''
+    from .model import MOD16
+    annual = MOD16._annual_et(params, years, *drivers, as_torch=True, **kw)
+    precip = _dev(annual_precip, annual.device, torch.float64)
+    diff = torch.clamp(annual - precip, min=0.0)
+    return float((-100.0 * ((diff * diff).mean() / precip.sum())).item())

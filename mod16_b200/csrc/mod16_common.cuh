@@ -67,6 +67,8 @@ struct ForwardArgs {
   double table[MOD16_N_PARAMS][MOD16_N_PFT];
   // outputs
   R* out[6];
+  const int* group;   // MOD16_OUT_ANNUAL: group (year) of every time step; out[0] = uint64 sums
+  int n_groups;
   int* gate_flag;
   unsigned long long* redo_ws;  // [0] = count, [1 ..] = queued linear indices t * N + n
   long long redo_cap;           // entries the queue can hold (0: no queue)

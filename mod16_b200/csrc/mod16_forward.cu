@@ -70,8 +70,15 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
   const uint32_t sem = flags & MOD16_SEM_MASK, om = flags & MOD16_OUT_MASK,
                  gm = flags & MOD16_GATE_MASK;
   if (sem > MOD16_SEM_INSTANCE) return MOD16_ERR_FLAGS;
-  if (om != MOD16_OUT_SUM && om != MOD16_OUT_DAY_NIGHT && om != MOD16_OUT_COMPONENTS)
+  if (om != MOD16_OUT_SUM && om != MOD16_OUT_DAY_NIGHT && om != MOD16_OUT_COMPONENTS &&
+      om != MOD16_OUT_ANNUAL)
     return MOD16_ERR_FLAGS;
+  if (om == MOD16_OUT_ANNUAL) {   // float32 static path; needs the group index of every step
+    if (sizeof(R) != sizeof(float) || sem != MOD16_SEM_STATIC) return MOD16_ERR_FLAGS;
+    if ((!out->group && T > 0) || out->n_groups < 1 || !out->gate_flag) return MOD16_ERR_NULL;
+  }
+  a.group = out->group;
+  a.n_groups = out->n_groups;
   if (gm > MOD16_GATE_FIXUP) return MOD16_ERR_FLAGS;
   for (int k = 0; k < MOD16_N_DRIVERS; ++k) {
     if (drv->drv[k].t_stride < 0 || drv->drv[k].n_stride < 0) return MOD16_ERR_SHAPE;
@@ -98,7 +105,8 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
     if (n_arr && (a.par_stride[k] < 0 || a.par_stride[k] > 1)) return MOD16_ERR_SHAPE;
     for (int c = 0; c < MOD16_N_PFT; ++c) a.table[k][c] = par->table[k][c];
   }
-  const int n_out = om == MOD16_OUT_SUM ? 1 : (om == MOD16_OUT_DAY_NIGHT ? 2 : 6);
+  const int n_out = (om == MOD16_OUT_SUM || om == MOD16_OUT_ANNUAL) ? 1
+                    : (om == MOD16_OUT_DAY_NIGHT ? 2 : 6);
   for (int k = 0; k < 6; ++k) {
     a.out[k] = k < n_out ? (R*)out->out[k] : nullptr;
     if (k < n_out && !a.out[k] && T * N > 0) return MOD16_ERR_NULL;

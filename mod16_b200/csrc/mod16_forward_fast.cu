@@ -127,6 +127,14 @@ redo_sweep_kernel(const __grid_constant__ ForwardArgs<float> a) {
   }
 }
 
+// MOD16_OUT_ANNUAL, fix-up pass of the call-exact gate: forget the open pass's sums
+__global__ void annual_clear_kernel(unsigned long long* acc, int64_t n, const int* gate_flag) {
+  if (*((volatile const int*)gate_flag) != 0) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    acc[i] = 0ULL;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // a (T, N) array the bulk copies can stream: unit pixel stride, every row 16-byte aligned
@@ -188,7 +196,8 @@ static int pipe_variant(const ForwardArgs<float>& a, uint32_t flags) {
     extra |= 2;
   }
   const uint32_t om = flags & MOD16_OUT_MASK;
-  const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1 : 2);
+  const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1
+                       : (om == MOD16_OUT_ANNUAL ? 3 : 2));
   if (!pipe_has_variant(out_mode, extra)) return -1;
   return extra;
 }
@@ -228,9 +237,17 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
   a.t_chunk = (int)chunk;
   dim3 grid((unsigned)bx, (unsigned)by);
   const uint32_t om = flags & MOD16_OUT_MASK;
-  const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1 : 2);
+  const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1
+                       : (om == MOD16_OUT_ANNUAL ? 3 : 2));
   const bool is_static = (flags & MOD16_SEM_MASK) == MOD16_SEM_STATIC;
   if (a.redo_cap > 0) M16_CUDA_CHECK(cudaMemsetAsync(a.redo_ws, 0, 8, st));
+  if (out_mode == 3 && a.skip_if_flag) {
+    // the fix-up pass of the call-exact gate recomputes everything: the sums of the open
+    // pass go (only if the fix-up will run at all, i.e. the flag stayed 0)
+    annual_clear_kernel<<<148 * 8, 256, 0, st>>>((unsigned long long*)a.out[0],
+                                                 (int64_t)a.n_groups * a.N, a.gate_flag);
+    M16_CUDA_CHECK(cudaGetLastError());
+  }
   const int rc = is_static ? launch_pipe_static(a, src, out_mode, extra, fmt, grid, st)
                            : launch_pipe_instance(a, src, out_mode, extra, fmt, grid, st);
   if (rc != MOD16_OK) return rc;
@@ -242,7 +259,10 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
     redo_sweep_kernel<S, O><<<148 * 4, SWEEP_THREADS, 0, st>>>(a);                      \
     M16_CUDA_CHECK(cudaGetLastError());                                                 \
   } while (0)
-    if (is_static) {
+    if (is_static && out_mode == 3) {   // (no marker sweep: nothing per step to mark)
+      redo_queue_kernel<SEM_STATIC, 3><<<148 * 4, 128, 0, st>>>(a);
+      M16_CUDA_CHECK(cudaGetLastError());
+    } else if (is_static) {
       if (out_mode == 0) M16_REDO(SEM_STATIC, 0);
       else if (out_mode == 1) M16_REDO(SEM_STATIC, 1);
       else M16_REDO(SEM_STATIC, 2);
@@ -275,7 +295,8 @@ int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
       return launch_pipe(a, flags, extra, st);
     }
   }
-  if (a.raw_fmt != 0) return MOD16_ERR_LAYOUT;  // (no strided kernel for storage formats)
+  // (no strided kernel for storage formats, nor for the annual sums)
+  if (a.raw_fmt != 0 || (flags & MOD16_OUT_MASK) == MOD16_OUT_ANNUAL) return MOD16_ERR_LAYOUT;
   g_last_forward_kernel = MOD16_KERNEL_STRIDED;
   const int threads = 256;
   const int64_t bx = (a.N + threads - 1) / threads;

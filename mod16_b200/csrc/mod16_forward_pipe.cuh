@@ -156,7 +156,8 @@ __device__ __forceinline__ fast::F2 pipe_load(uint32_t s0, uint32_t s1, uint32_t
 // finds (the counter past the capacity tells them to run).  One in-place double evaluation
 // here would hold the whole block.  Inlined on purpose: a CALL inside the time loop keeps
 // the loop's uniform values out of the uniform registers.
-__device__ __forceinline__ void pipe_defer(const ForwardArgs<float>& a, int ts, uint32_t* redo_q,
+template <int SEM, int OUT>
+__device__ __forceinline__ bool pipe_defer(const ForwardArgs<float>& a, int ts, uint32_t* redo_q,
                                            int* redo_n) {
   const int tid = (int)threadIdx.x;
   const int64_t n = (int64_t)blockIdx.x * PIPE_TILE + tid;
@@ -171,7 +172,23 @@ __device__ __forceinline__ void pipe_defer(const ForwardArgs<float>& a, int ts, 
     queued = slot < PIPE_QCAP;
     if (queued) redo_q[slot] = (uint32_t)ts << 10 | (uint32_t)tid;
   }
-  if (!queued) st_stream1(a.out[0] + t * a.N + n, __int_as_float(REDO_MARK));
+  if (queued) return false;
+  if (OUT == 3) {
+    // the annual sums have no per-step output to carry a marker: with a workspace the element
+    // goes to the block's own queue; when that is full too the call reports it (bit 30 of
+    // the gate word: the sums are incomplete, see MOD16_OUT_ANNUAL in the header)
+    if (a.redo_cap > 0) {
+      const int slot = atomicAdd(redo_n, 1);
+      if (slot < PIPE_QCAP) {
+        redo_q[slot] = (uint32_t)ts << 10 | (uint32_t)tid;
+        return false;
+      }
+    }
+    atomicOr(a.gate_flag, MOD16_ANNUAL_OVERFLOW);
+    return false;
+  }
+  st_stream1(a.out[0] + t * a.N + n, __int_as_float(REDO_MARK));
+  return false;
 }
 
 // The masked-driver rule (fast::nan_halves) for ONE element of the modes that cannot decide
@@ -190,7 +207,11 @@ __device__ __forceinline__ int pipe_rule(const ForwardArgs<float>& a, int ts, fl
   c.vpd_off = vpd_off; c.inv_dvpd = inv_dvpd;
   bool g_pos;
   const int h = fast::nan_halves<SEM>(in, c, a.has_rc != 0, g_pos);
-  if (OUT == 2 || !(OUT == 0 ? h != 0 : h == 3)) return -1;
+  if (OUT == 2 || !((OUT == 0 || OUT == 3) ? h != 0 : h == 3)) return -1;
+  if (OUT == 3) {
+    annual_add(a, t, n, kAnnualNaN);
+    return g_pos ? 1 : 0;
+  }
   const float qnan = __int_as_float(0x7fc00000);
   st_stream1(a.out[0] + t * a.N + n, qnan);
   if (OUT == 1) st_stream1(a.out[1] + t * a.N + n, qnan);
@@ -311,10 +332,13 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     }
   }
   // the masked-driver rule is decided from registers for the static total of a sane column
-  const bool rule_in_regs = OUT == 0 && SEM == SEM_STATIC && c1.ok != 0.0f;
+  const bool rule_in_regs = (OUT == 0 || OUT == 3) && SEM == SEM_STATIC && c1.ok != 0.0f;
+  // MOD16_OUT_ANNUAL: this pixel's running sum of the current group (year), 2^-32 mm
+  unsigned long long acc_run = 0ULL;
+  int acc_g = -1;
   const float swn_scalar = a.drv[MOD16_D_SW_RAD_NIGHT].scalar;
   const int gate = a.gate;
-  constexpr int n_out = OUT == 0 ? 1 : (OUT == 1 ? 2 : 6);
+  constexpr int n_out = OUT == 3 ? 0 : (OUT == 0 ? 1 : (OUT == 1 ? 2 : 6));
   // this thread's pixel in a row (float32 rows; storage formats index per array)
   const uint32_t my0 = keep_u32(FMT < FMT_MODIS ? data0 + (uint32_t)tid * 4u : data0);
   const bool clamp_vpd_n = FMT != FMT_F32 && (a.prep & MOD16_PREP_VPD_NIGHT_CLAMP) != 0;
@@ -399,7 +423,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
           }
         }
         flags |= done_j;
-        pipe_defer(a, i * PIPE_SUB + j, redo_q, &redo_n);
+        any_pos |= pipe_defer<SEM, OUT>(a, i * PIPE_SUB + j, redo_q, &redo_n);
       }
     }
 
@@ -408,7 +432,17 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     F2 gs;
     const M2 late = fast::step_core<F2, SEM, false>(in, tc_d, tc_n, pc, px, gate, r, g_pos, gs);
     F2 res[6];
-    if (OUT == 0) {
+    unsigned long long q_x = 0ULL, q_y = 0ULL;   // OUT_ANNUAL: the two steps' mass, fixed point
+    int g_x = -1, g_y = -1;
+    if (OUT == 3) {
+      const F2 tcm = 0.5f * (tc_d + tc_n);
+      const F2 lam = fast::vfma(tcm, -2361.0f, 2.501e6f);                      // :121
+      const F2 mm = (fast::vmax(r.tot, 0.0f) * (86400.0f * 4294967296.0f)) * fast::vrcp(lam);
+      q_x = __float2ull_rn(fminf(mm.x, 1.0e16f));
+      q_y = __float2ull_rn(fminf(mm.y, 1.0e16f));
+      g_x = __ldg(a.group + (int64_t)blockIdx.y * a.t_chunk + i * PIPE_SUB);
+      g_y = TWO ? __ldg(a.group + (int64_t)blockIdx.y * a.t_chunk + i * PIPE_SUB + 1) : g_x;
+    } else if (OUT == 0) {
       res[0] = r.tot;
     } else if (OUT == 1) {
       res[0] = r.tot_day; res[1] = r.tot_night;
@@ -416,7 +450,10 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       res[0] = r.day.canopy;   res[1] = r.day.soil;   res[2] = r.day.trans;
       res[3] = r.night.canopy; res[4] = r.night.soil; res[5] = r.night.trans;
     }
-    if (flags == 0u && !(late.x || late.y)) {
+    if (OUT == 3 && flags == 0u && !(late.x || late.y) && g_x == acc_g && g_y == acc_g) {
+      gs_max = fmaxf(gs_max, fmaxf(gs.x, gs.y));
+      acc_run += q_x + q_y;
+    } else if (OUT != 3 && flags == 0u && !(late.x || late.y)) {
       gs_max = fmaxf(gs_max, fmaxf(gs.x, gs.y));
 #pragma unroll
       for (int k = 0; k < n_out; ++k) {
@@ -427,17 +464,31 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
 #pragma unroll
       for (int j = 0; j < PIPE_SUB; ++j) {
         if (flags & (j == 0 ? DONE_X : DONE_Y)) continue;
+        unsigned long long q_j = j == 0 ? q_x : q_y;
         if (flags & (j == 0 ? MASKED_X : MASKED_Y)) {
           // (g_surf > 0 from Tmin, VPD, T, P of the hot path; NaN > 0 is false)
-          st_stream1(a.out[0] + off + j * t_stride, __int_as_float(0x7fc00000));
+          if (OUT == 3) q_j = kAnnualNaN;
+          else st_stream1(a.out[0] + off + j * t_stride, __int_as_float(0x7fc00000));
           any_pos |= j == 0 ? g_pos.x : g_pos.y;
         } else if (j == 0 ? late.x : late.y) {
-          pipe_defer(a, i * PIPE_SUB + j, redo_q, &redo_n);
+          any_pos |= pipe_defer<SEM, OUT>(a, i * PIPE_SUB + j, redo_q, &redo_n);
+          continue;
         } else {
           any_pos |= j == 0 ? g_pos.x : g_pos.y;
 #pragma unroll
           for (int k = 0; k < n_out; ++k)
             st_stream1(a.out[k] + off + j * t_stride, j == 0 ? res[k].x : res[k].y);
+        }
+        if (OUT == 3) {   // into the running sum; a new group flushes the old one
+          const int g_j = j == 0 ? g_x : g_y;
+          if (g_j != acc_g) {
+            if (acc_g >= 0 && acc_g < a.n_groups && acc_run != 0ULL)
+              atomicAdd((unsigned long long*)a.out[0] + (int64_t)acc_g * a.N + tile0 + tid,
+                        acc_run);
+            acc_g = g_j;
+            acc_run = 0ULL;
+          }
+          acc_run += q_j;
         }
       }
     }
@@ -448,16 +499,18 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   for (int i = 0; i < nfull; ++i) consume(std::true_type(), i);
   if (nsteps & 1) consume(std::false_type(), nfull);
   any_pos |= gs_max > 0.0f;
+  if (OUT == 3 && live && acc_g >= 0 && acc_g < a.n_groups && acc_run != 0ULL)
+    atomicAdd((unsigned long long*)a.out[0] + (int64_t)acc_g * a.N + tile0 + tid, acc_run);
   // the block-local deferred pass: consumers only (named barrier 1), one element each; when
   // the block's queue overflowed, every thread also looks for markers in its own column
-  if (a.redo_cap == 0) {
+  if (a.redo_cap == 0 || OUT == 3) {
     asm volatile("bar.sync 1, %0;" ::"n"(PIPE_CONSUMERS) : "memory");
     const int total = redo_n < PIPE_QCAP ? redo_n : PIPE_QCAP;
     for (int e = tid; e < total; e += PIPE_CONSUMERS) {
       const uint32_t q = redo_q[e];
       any_pos |= fix_exact_one<SEM, OUT>(a, t0 + (int64_t)(q >> 10), tile0 + (q & 1023u));
     }
-    if (redo_n > PIPE_QCAP && live) {
+    if (OUT != 3 && redo_n > PIPE_QCAP && live) {
       for (int ts = 0; ts < nsteps; ++ts) {
         const int64_t o = (t0 + ts) * a.N + tile0 + tid;
         if (__float_as_int(((volatile float*)a.out[0])[o]) == REDO_MARK)
@@ -499,11 +552,13 @@ int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mod
   M16_PIPE(2, 0, 0); M16_PIPE(2, 1, 0);
   M16_PIPE(0, 0, 1); M16_PIPE(0, 0, 2); M16_PIPE(0, 0, 3);
   M16_PIPE(1, 0, 1); M16_PIPE(1, 0, 2); M16_PIPE(1, 0, 3);
+  if constexpr (SEM == SEM_STATIC) { M16_PIPE(3, 0, 0); }
 #undef M16_PIPE
   return MOD16_ERR_FLAGS;
 }
 
 inline bool pipe_has_variant(int out_mode, int extra, int fmt = 0) {
+  if (out_mode == 3) return extra == 0 && fmt == 0;   // annual sums: the plain tile layout
   return fmt == 0 ? (out_mode < 2 || extra < 2) : (out_mode < 2 && extra == 0);
 }
 

@@ -109,10 +109,30 @@ __device__ __forceinline__ StepIn load_step(const ForwardArgs<float>& a, int64_t
   return in;
 }
 
+// ---- MOD16_OUT_ANNUAL: annual evapotranspiration sums in 2^-32 mm ------------------------------
+constexpr unsigned long long kAnnualNaN = 1ULL << 54;   // what a NaN element adds
+// max(LE, 0) * 86400 / lambda(tc_mean) [mm day-1] as fixed point (calibration.py:783-786,
+// :838-842; lambda = (2.501 - 0.002361 Tc) 1e6, :121).  A float times 2^32 converts exactly.
+__device__ __forceinline__ unsigned long long annual_fixed(float le, float tc_mean) {
+  if (le != le) return kAnnualNaN;
+  const float lam = fmaf(tc_mean, -2361.0f, 2.501e6f);
+  const float mm = fminf(fmaxf(le, 0.0f) * (86400.0f * 4294967296.0f) / lam, 1.0e16f);
+  return __float2ull_rn(mm);
+}
+__device__ __forceinline__ void annual_add(const ForwardArgs<float>& a, int64_t t, int64_t n,
+                                           unsigned long long q) {
+  const int g = __ldg(a.group + t);
+  if (g >= 0 && g < a.n_groups && q != 0ULL)
+    atomicAdd((unsigned long long*)a.out[0] + (int64_t)g * a.N + n, q);
+}
+
 template <int OUT>
 __device__ __forceinline__ void store_exact(const ForwardArgs<float>& a, int64_t o,
-                                            const fast::StepOut& r) {
-  if (OUT == 0) {
+                                            const fast::StepOut& r, const StepIn& in) {
+  if (OUT == 3) {
+    const float tcm = 0.5f * (fast::celsius<float>(in.t_d) + fast::celsius<float>(in.t_n));
+    annual_add(a, o / a.N, o % a.N, annual_fixed(r.tot, tcm));
+  } else if (OUT == 0) {
     a.out[0][o] = r.tot;
   } else if (OUT == 1) {
     a.out[0][o] = r.tot_day;
@@ -132,7 +152,7 @@ __device__ __noinline__ bool fix_exact_one(const ForwardArgs<float>& a, int64_t 
   fast::StepOut r;
   bool g_pos;
   fast::pixel_step_exact<SEM>(in, col, a.has_rc != 0, a.gate, r, g_pos);
-  store_exact<OUT>(a, t * a.N + n, r);
+  store_exact<OUT>(a, t * a.N + n, r, in);
   return g_pos;
 }
 
@@ -162,7 +182,7 @@ __device__ __noinline__ int rare_one(const ForwardArgs<float>& a, int64_t t, int
   if (rule_only) return -1;
   fast::StepOut r;
   fast::pixel_step_exact<SEM>(in, col, a.has_rc != 0, a.gate, r, g_pos);
-  store_exact<OUT>(a, o, r);
+  store_exact<OUT>(a, o, r, in);
   return g_pos ? 1 : 0;
 }
 

@@ -230,7 +230,7 @@ def _view_2d(shape):
 def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static',
                 out_mode='sum', gate='global', dtype=None, r_corr_list=None, device=None,
                 stream=None, force=0, as_torch=None, gate_flag=None, out=None,
-                workspace=None, prep=None):
+                workspace=None, prep=None, groups=None, n_groups=None):
     '''
     Launches K1 once.
 
@@ -238,7 +238,11 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     params  : sequence of 11 values in ``required_parameters`` order, each a scalar or a
               per-pixel array ((N,), (1, N)); or None when ``pft``/``table`` are given
     pft, table : uint8 land-cover code per pixel and the dense 11 x 13 BPLUT table
-    out_mode : 'sum' | 'day_night' | 'components'
+    out_mode : 'sum' | 'day_night' | 'components' | 'annual' (float32 static path: no
+               per-step output, one (n_groups, N) float64 array of evapotranspiration sums
+               [mm] per pixel and group of time steps -- ``groups`` holds the group (year)
+               index of every step; the reduction of the calibration's precipitation
+               constraint, mod16/calibration.py:783-790, fused into the kernel)
     gate     : 'global' (reference) | 'element' | 'open' | 'closed' | 'open_track' | 'fixup'
 
     drivers may hold ``rawio.RawDriver`` objects (storage formats: uint8 / int16 with scale,
@@ -280,7 +284,17 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     full_shape = tuple(np.broadcast_shapes(*shapes))
     T, N = _view_2d(full_shape)
 
+    if out_mode == 'annual':
+        if groups is None:
+            groups = np.zeros(T, np.int32)
+        if np_dtype != np.dtype('float32') or semantics != 'static' or len(full_shape) != 2:
+            raise _abi.LayoutError('out_mode="annual" belongs to the float32 static path on '
+                                   '(T, N) drivers')
     with torch.cuda.device(dev), launch_stream(dev, stream) as (s, caller_stream):
+        if out_mode == 'annual':
+            return _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate, as_torch,
+                               full_shape, T, N, caller_stream, prep if raw else None, groups,
+                               n_groups)
         try:
             return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
                                   semantics, out_mode, gate, r_corr_list, force, as_torch,
@@ -294,6 +308,36 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
                                   semantics, out_mode, gate, r_corr_list, force, as_torch,
                                   gate_flag, out, workspace, full_shape, T, N, caller_stream,
                                   None)
+
+
+def _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate, as_torch, full_shape,
+                T, N, caller_stream, prep, groups, n_groups):
+    '''
+    out_mode='annual': integer accumulators on the device (2^-32 mm, order-independent), the
+    double-precision queue sized for an eighth of the call (no per-step output exists that
+    could carry overflow markers), the result as float64 millimetres (NaN where a step of
+    the pixel's group was NaN, like the reference's ``x.sum()``).
+    '''
+    g = torch.as_tensor(np.asarray(groups.cpu() if isinstance(groups, torch.Tensor) else groups))
+    if g.numel() != T:
+        raise ValueError('groups must hold one index per time step')
+    g = g.to(device=dev, dtype=torch.int32)
+    G = int(n_groups) if n_groups is not None else (int(g.max().item()) + 1 if T else 1)
+    acc = torch.zeros((G, N), device=dev, dtype=torch.int64)
+    ws = torch.empty(max(1 << 20, T * N // 8 + 1024), device=dev, dtype=torch.int64)
+    flag = torch.zeros(1, device=dev, dtype=torch.int32)
+    _run_on_stream(lib, s, dev, np_dtype, drivers, [], plist, pft, table, 'static', 'annual',
+                   gate, None, 0, True, flag, [acc], ws, full_shape, T, N, caller_stream, prep,
+                   groups=(g, G))
+    if int(flag.item()) & _abi.ANNUAL_OVERFLOW:
+        raise _abi.Mod16Error(
+            'out_mode="annual": more than an eighth of the elements need the double-precision '
+            'pass (unmasked fill values?); mask them, or use out_mode="sum" with '
+            'aggregate.annual_mass_sums')
+    out = acc.to(torch.float64) * (1.0 / 4294967296.0)
+    out = torch.where(acc >= (1 << 54), torch.full_like(out, float('nan')), out)
+    hand_over((out,), caller_stream)
+    return [out if as_torch else out.cpu().numpy()]
 
 
 def _plain_drivers(drivers, prep, dev, np_dtype):
@@ -316,7 +360,7 @@ def _plain_drivers(drivers, prep, dev, np_dtype):
 
 def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, semantics,
                    out_mode, gate, r_corr_list, force, as_torch, gate_flag, out, workspace,
-                   full_shape, T, N, caller_stream, prep=None):
+                   full_shape, T, N, caller_stream, prep=None, groups=None):
     'Body of run_forward; the current stream is `s`.  `prep` not None: the storage-format entry.'
     params = plist if plist else None
     st = _Staged(dev, np_dtype)
@@ -386,12 +430,14 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
         for j in range(_abi.N_PFT):
             cp.table[i][j] = tab[i, j]
 
-    n_out = {'sum': 1, 'day_night': 2, 'components': 6}[out_mode]
+    n_out = {'sum': 1, 'day_night': 2, 'components': 6, 'annual': 1}[out_mode]
     flags = {'static': _abi.SEM_STATIC, 'instance': _abi.SEM_INSTANCE}[semantics]
     flags |= {'sum': _abi.OUT_SUM, 'day_night': _abi.OUT_DAY_NIGHT,
-              'components': _abi.OUT_COMPONENTS}[out_mode]
+              'components': _abi.OUT_COMPONENTS, 'annual': _abi.OUT_ANNUAL}[out_mode]
     flags |= _abi.GATE_FLAGS[gate] | force
-    if out is not None:
+    if out_mode == 'annual':
+        outs = list(out)                    # (n_groups, N) int64 accumulators, zeroed
+    elif out is not None:
         outs = list(out)
         if len(outs) != n_out or any(
                 (not o.is_cuda) or o.dtype != st.t_dtype or o.numel() != T * N
@@ -402,6 +448,9 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
     else:
         outs = [torch.empty((T, N), device=dev, dtype=st.t_dtype) for _ in range(n_out)]
     co = _abi.Out()
+    if groups is not None:
+        co.group, co.n_groups = groups[0].data_ptr(), groups[1]
+        st.keep.append(groups[0])
     for k, o in enumerate(outs):
         co.out[k] = o.data_ptr()
     if gate_flag is None:
@@ -419,6 +468,8 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
         fn = lib.mod16_forward_f32 if np_dtype == np.dtype('float32') else lib.mod16_forward_f64
     _abi.check(fn(ctypes.byref(cd), ctypes.byref(cp), ctypes.byref(co), T, N, flags,
                   ctypes.c_void_p(handle)))
+    if out_mode == 'annual':
+        return outs
     outs = [o.reshape(full_shape) for o in outs]
     if as_torch:
         # Staged copies were allocated and used on `s` alone: the caching allocator's stream

@@ -81,6 +81,26 @@ class MOD16(ComponentMixin):
         return run_forward(drivers, pft=pft, table=table, semantics='static',
                            out_mode='sum', **kw)[0]
 
+    @staticmethod
+    def _annual_et(params, years, *drivers, **kw):
+        '''
+        Annual evapotranspiration [mm] per pixel of ``_et(params, *drivers)`` -- the model-side
+        half of the calibration's precipitation constraint (``constrain_by_map``, reference
+        mod16/calibration.py:775-790 with ``lhv = latent_heat_vaporization((temp_day +
+        temp_night) / 2)``, :838-842) -- accumulated inside the fused kernel: the (T, N)
+        latent heat flux is never written.  ``years`` labels every time step; rows of the
+        (Y, N) float64 result follow ``np.unique(years)``.  ``params`` may also be the pair
+        ``(table, pft)`` for a land-cover gather.
+        '''
+        import torch
+        yr = np.asarray(years.cpu() if isinstance(years, torch.Tensor) else years)
+        labels, idx = np.unique(yr, return_inverse=True)
+        if isinstance(params, tuple) and len(params) == 2:
+            kw.update(table=params[0], pft=params[1])
+            params = None
+        return run_forward(drivers, params=params, semantics='static', out_mode='annual',
+                           groups=idx.astype(np.int32), n_groups=len(labels), **kw)[0]
+
     # -- instance interface ----------------------------------------------------------------
     def _vector(self):
         return [getattr(self, k) for k in self.required_parameters]

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mod16_b200 import MOD16, synthetic, utils
 from mod16_b200.forward import run_forward
 frac = float(sys.argv[1]) if len(sys.argv) > 1 else 0.3
-mode = sys.argv[2] if len(sys.argv) > 2 else 'masked'   # masked | negvpd | fill
+mode = sys.argv[2] if len(sys.argv) > 2 else 'masked'   # masked | negvpd | negvpd2 | filltemp | fill
 T, N = 64, 2400 * 2400
 dev = torch.device('cuda', 0)
 d = synthetic.device_drivers(T, N, 1, dev)
@@ -17,6 +17,13 @@ if mode == 'masked':       # whole pixels masked (NaN fPAR / LAI at every step)
         d[k][:, mask] = float('nan')
 elif mode == 'negvpd':     # scattered supersaturated elements (negative VPD): double code
     d['vpd_day'][torch.rand((T, N), device=dev) < frac] = -50.0
+elif mode == 'negvpd2':    # both VPDs negative at random elements
+    for k in ('vpd_day', 'vpd_night'):
+        d[k][torch.rand((T, N), device=dev) < frac] *= -0.1
+elif mode == 'filltemp':   # unmasked fill temperatures on whole pixels (-9999): NaN from registers
+    mask = torch.rand(N, device=dev) < frac
+    for k in ('temp_day', 'temp_night', 'tmin'):
+        d[k][:, mask] = -9999.0
 else:                      # unmasked fill values on whole pixels: double code, garbage out
     mask = torch.rand(N, device=dev) < frac
     d['fpar'][:, mask] = 2.55

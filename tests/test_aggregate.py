@@ -105,3 +105,61 @@ def test_constrain_by_map_golden(cuda_lib, golden_dir):
         got32 = aggregate.constrain_by_map(le.astype(np.float32), years, lhv.astype(np.float32),
                                            precip)
         assert abs(got32 - want) <= 1e-5 * max(abs(want), 1e-12)
+
+
+@pytest.mark.parametrize('T,N,by_pft', [(730, 4800, True), (366, 964, False), (41, 480, False)])
+def test_annual_sums_fused_into_the_forward_kernel(cuda_lib, T, N, by_pft):
+    '''
+    out_mode='annual' (MOD16._annual_et): the annual ET of `_et` without ever writing the
+    (T, N) flux, against the oracle's `constrain_by_map` ingredients on the same inputs.
+    '''
+    from mod16_b200 import MOD16, utils
+    from mod16_b200.forward import run_forward
+    d = synthetic.host_drivers(T, N, 1601, dtype=np.float32)
+    rng = np.random.default_rng(1602)
+    d['lai'][rng.random((T, N)) < 0.001] = np.nan          # a NaN step poisons its pixel-year
+    d['temp_day'][rng.random((T, N)) < 0.0005] = -9999.0
+    d['sw_rad_day'][:, :7] = 0.0                           # negative fluxes are dropped (:786)
+    names = list(synthetic.DRIVER_NAMES)
+    drv = [d[k] for k in names]
+    d64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
+    years = 2001 + (np.arange(T) * 3) // max(T, 1)         # three unequal "years"
+    table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51), MOD16.required_parameters,
+                              default_beta=250.0)
+    if by_pft:
+        pft = synthetic.host_pft_map(N, 1603)
+        params = (table, pft)
+        vec = [table[i][pft].reshape(1, N) for i in range(11)]
+    else:
+        params = vec = list(table[:, 7])
+    with np.errstate(all='ignore'):
+        le = orc.static_et(vec, *d64)
+        lhv = orc.lhv(0.5 * (d64[5] + d64[6]))             # calibration.py:838-842
+        want = orc.annual_mass_sums(le.copy(), years, lhv)
+    got = MOD16._annual_et(params, years, *drv)
+    assert got.shape == want.shape == (3, N) and got.dtype == np.float64
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.isnan(want).mean() > 0.01
+    assert np.all(np.abs(got - want)[ok] <= 1e-5 * np.maximum(np.abs(want[ok]), 1.0)), \
+        np.abs(got - want)[ok].max()
+    # integer accumulation: bit-identical again, and whatever the launch geometry
+    again = MOD16._annual_et(params, years, *drv)
+    assert np.array_equal(again, got, equal_nan=True)
+    h = (N // 2) // 4 * 4
+    half = MOD16._annual_et(params if not by_pft else (table, pft[:h]), years,
+                            *[v[..., :h] if isinstance(v, np.ndarray) else v for v in drv])
+    assert np.array_equal(half, got[:, :h], equal_nan=True)
+    # the objective itself (nRMSD), and the same from the unfused pieces
+    precip = rng.uniform(100, 900, (3, N))
+    keep = ~np.isnan(want).any(axis=0)
+    cols = np.flatnonzero(keep)[: (keep.sum() // 4) * 4]
+    sub = [v[..., cols] if isinstance(v, np.ndarray) else v for v in drv]
+    sub64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in sub]
+    p_sub = (table, pft[cols]) if by_pft else params
+    v_sub = [table[i][pft[cols]].reshape(1, -1) for i in range(11)] if by_pft else vec
+    with np.errstate(all='ignore'):
+        ref = orc.constrain_by_map(orc.static_et(v_sub, *sub64), years,
+                                   orc.lhv(0.5 * (sub64[5] + sub64[6])), precip[:, cols])
+    val = aggregate.constrain_by_map_fused(p_sub, sub, years, precip[:, cols])
+    assert abs(val - ref) <= 1e-5 * abs(ref), (val, ref)

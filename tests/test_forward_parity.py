@@ -447,3 +447,33 @@ def test_double_queue_overflow_takes_the_sweep(cuda_lib):
     got = run_forward(drv, params=BPLUT7, semantics='static', out_mode='sum', dtype=np.float32,
                       workspace=none)[0]
     parity.assert_parity(got, rd + rn, np.float32, what='no workspace')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_land_cover_codes_outside_the_table(cuda_lib, dtype):
+    '''
+    A land-cover code above 12 (254 = water, 255 = fill in MCD12Q1): numpy's fancy index
+    `params[key][pft_map]` raises IndexError in the reference's callers
+    (Forward_Run_example.ipynb cell 32); the kernels cannot raise per pixel and answer NaN --
+    the documented deviation.  Codes 0 and 11 gather the BPLUT's own NaN columns.
+    '''
+    T, N = 6, 960
+    d = synthetic.host_drivers(T, N, 171, dtype=dtype)
+    drv = [d[k] for k in NAMES]
+    table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51), MOD16.required_parameters,
+                              default_beta=250.0)
+    pft = synthetic.host_pft_map(N, 172)
+    pft[5], pft[6], pft[100], pft[481], pft[959] = 13, 254, 255, 0, 11
+    got = MOD16._et_by_pft(table, pft, *drv, dtype=dtype)
+    bad = np.zeros(N, bool)
+    bad[[5, 6, 100, 481, 959]] = True
+    assert np.isnan(got[:, bad]).all() and not np.isnan(got[:, ~bad]).any()
+    ok = np.flatnonzero(~bad)
+    vec = [table[i][pft[ok]].reshape(1, -1) for i in range(11)]
+    d64 = [v[..., ok].astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
+    with np.errstate(all='ignore'):
+        ref = orc.static_et(vec, *d64)
+    parity.assert_parity(got[:, ok], ref, dtype, what='codes inside the table')
+    with pytest.raises(IndexError):
+        [table[i][pft] for i in range(11)]

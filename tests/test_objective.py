@@ -355,3 +355,35 @@ def test_objective_definitions_known_answers():
     # a perfect model: NSE = 1 either way
     assert obj.nash_sutcliffe(0.0, np.array([1.0, 2.0])) == 1.0
     assert obj.nash_sutcliffe(0.0, np.array([1.0, 2.0]), norm=True) == 1.0
+
+
+@pytest.mark.gpu
+def test_calibration_config_at_full_size(cuda_lib):
+    '''
+    BASELINE config 4 at its full size: 10^5 parameter draws x 300 tower sites x 3652 days
+    (10 years of daily data), 30 % of the observations missing -- the batch the calibration's
+    likelihood loop amounts to (calibration.py:224-227, one `_et` call per MCMC proposal).
+    The oracle cannot loop over 10^5 draws: a sample of draws is checked against one oracle
+    call each (valid-pair counts exactly, RMSD within the float32 bound), and size-independent
+    properties hold for all of them -- every draw sees the same valid pairs, the statistics
+    of a draw do not depend on the batch it is evaluated in, a repeated call is bit-identical.
+    '''
+    from mod16_b200.objective import ObjectiveBackend
+    T, N, D = 3652, 300, 100000
+    drv, d64, draws, obs, w = _problem(T, N, D, 16004)
+    backend = ObjectiveBackend(drv, obs, w, dtype=np.float32)
+    sse, cnt = backend(draws)
+    assert sse.shape == (D,) and np.isfinite(sse).all()
+    valid = int((~np.isnan(obs)).sum())
+    assert 0.6 * T * N < valid < 0.75 * T * N
+    assert (cnt == valid).all()                 # physical drivers: no NaN predictions
+    pick = np.array([0, 1, 4999, 31337, 65536, 99999])
+    ref_sse, ref_cnt, tol = _reference_stats(d64, draws[pick], obs, w)
+    _check(sse[pick], cnt[pick], ref_sse, ref_cnt, tol, np.float32)
+    s2, c2 = backend(draws)                     # no floating-point atomics anywhere
+    assert np.array_equal(s2, sse) and np.array_equal(c2, cnt)
+    s3, c3 = backend(draws[pick])               # a batch of six takes the double-precision kernel
+    r_big, r_small = np.sqrt(sse[pick] / cnt[pick]), np.sqrt(s3 / c3)
+    assert np.array_equal(c3, cnt[pick]) and np.all(np.abs(r_big - r_small) <= tol)
+    rm = np.sqrt(sse / cnt)
+    assert 10.0 < rm.min() < rm.max() < 1000.0  # plausible RMSD range, W m-2
