@@ -108,7 +108,7 @@ enum {
 /* kernel selection (testing / profiling): default picks the vectorised kernel when the
    layout allows 128-bit loads, else the strided one */
 #define MOD16_FORCE_GENERIC 0x1000u
-#define MOD16_FORCE_MIRROR 0x2000u  /* f32: op-for-op transcription instead of fast math */
+#define MOD16_FORCE_MIRROR 0x2000u  /* op-for-op transcription instead of the rearranged math */
 
 typedef struct mod16_driver {
   const void* ptr;   /* device array of float / double, or NULL: use `scalar` */
@@ -209,11 +209,12 @@ int mod16_last_cuda_error(void);
 /* Which kernel the last mod16_forward_* call of this thread launched (for tests and
    profiling): 0 none yet; MOD16_KERNEL_PIPE | (variant << 8) the bulk-copy pipeline
    (variant bit 0: sw_rad_night streamed, bit 1: temp_annual / pressure streamed);
-   MOD16_KERNEL_STRIDED the float32 strided kernel; MOD16_KERNEL_EXACT the op-for-op kernel
-   (float64 entry, MOD16_FORCE_MIRROR). */
+   MOD16_KERNEL_STRIDED the float32 strided kernel; MOD16_KERNEL_FAST64 the float64 entry's
+   kernel; MOD16_KERNEL_EXACT the op-for-op kernel (MOD16_FORCE_MIRROR, either precision). */
 #define MOD16_KERNEL_PIPE 1
 #define MOD16_KERNEL_STRIDED 2
 #define MOD16_KERNEL_EXACT 3
+#define MOD16_KERNEL_FAST64 4  /* float64 entry: rearranged algebra in double */
 int mod16_last_forward_kernel(void);
 const char* mod16_error_string(int code);
 

@@ -16,7 +16,7 @@ OUT_SUM, OUT_DAY_NIGHT, OUT_COMPONENTS, OUT_ANNUAL = 0x00, 0x10, 0x20, 0x30
 GATE_GLOBAL, GATE_ELEMENT, GATE_OPEN, GATE_CLOSED = 0x000, 0x100, 0x200, 0x300
 GATE_OPEN_TRACK, GATE_FIXUP = 0x400, 0x500
 FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
-KERNEL_PIPE, KERNEL_STRIDED, KERNEL_EXACT = 1, 2, 3   # mod16_last_forward_kernel() & 0xff
+KERNEL_PIPE, KERNEL_STRIDED, KERNEL_EXACT, KERNEL_FAST64 = 1, 2, 3, 4  # last_forward_kernel & 0xff
 T_F32, T_I16, T_U8 = 0, 1, 2                            # mod16_raw_driver_t.dtype
 PREP_VPD_NIGHT_CLAMP, PREP_ELEVATION = 0x1, 0x2
 ERR_LAYOUT = -7

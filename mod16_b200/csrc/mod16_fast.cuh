@@ -83,8 +83,12 @@ M16_HD bool mand(bool a, bool b) { return a && b; }
 M16_HD bool mnot(bool a) { return !a; }
 M16_HD float vsel(bool m, float a, float b) { return m ? a : b; }
 M16_HD bool many(bool m) { return m; }
-template <class V> M16_HD V splat(float c);
-template <> M16_HD float splat<float>(float c) { return c; }
+// the scalar type constants are written in
+template <class V> struct ScalarOf { typedef float type; };
+template <> struct ScalarOf<double> { typedef double type; };
+template <class V> struct Splat;
+template <> struct Splat<float> { static M16_HD float of(float c) { return c; } };
+template <class V> M16_HD V splat(typename ScalarOf<V>::type c) { return Splat<V>::of(c); }
 
 // ---- packed pair -----------------------------------------------------------------------
 #if M16_DEV
@@ -115,7 +119,7 @@ inline F2 vfma(F2 a, F2 b, F2 c) { return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y,
 #endif
 M16_HD F2 operator-(F2 a) { return F2{-a.x, -a.y}; }
 M16_HD F2 operator-(F2 a, F2 b) { return a + (-b); }
-template <> M16_HD F2 splat<F2>(float c) { return F2{c, c}; }
+template <> struct Splat<F2> { static M16_HD F2 of(float c) { return F2{c, c}; } };
 M16_HD F2 operator*(F2 a, float b) { return a * splat<F2>(b); }
 M16_HD F2 operator*(float a, F2 b) { return splat<F2>(a) * b; }
 M16_HD F2 operator+(F2 a, float b) { return a + splat<F2>(b); }
@@ -160,12 +164,34 @@ M16_HD F2 vstep_ge_and(F2 a, float b, M2 m) {
   return F2{(a.x >= b && m.x) ? 1.0f : 0.0f, (a.y >= b && m.y) ? 1.0f : 0.0f};
 }
 
+// ---- double (the float64 entry: same rearranged algebra, IEEE division and libdevice
+// exp2 / log2 instead of the approximations) -----------------------------------------------
+M16_HD double vfma(double a, double b, double c) { return fma(a, b, c); }
+M16_HD double vrcp(double a) { return 1.0 / a; }
+M16_HD double vex2(double a) { return exp2(a); }
+M16_HD double vlg2(double a) { return log2(a); }
+M16_HD double vsat(double a) { return a != a ? 0.0 : (a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a)); }
+M16_HD double vabs(double a) { return fabs(a); }
+M16_HD double vmax(double a, double b) { return fmax(a, b); }
+M16_HD double vmin(double a, double b) { return fmin(a, b); }
+M16_HD bool vlt(double a, double b) { return a < b; }
+M16_HD bool vle(double a, double b) { return a <= b; }
+M16_HD bool vgt(double a, double b) { return a > b; }
+M16_HD bool vge(double a, double b) { return a >= b; }
+M16_HD bool veq(double a, double b) { return a == b; }
+M16_HD double vsel(bool m, double a, double b) { return m ? a : b; }
+template <> struct Splat<double> { static M16_HD double of(double c) { return c; } };
+M16_HD double vstep_ge(double a, double b) { return a >= b ? 1.0 : 0.0; }
+M16_HD double vstep_ge_and(double a, double b, bool m) { return (a >= b && m) ? 1.0 : 0.0; }
+
 template <class V> struct MaskOf;
 template <> struct MaskOf<float> { typedef bool type; };
 template <> struct MaskOf<F2> { typedef M2 type; };
+template <> struct MaskOf<double> { typedef bool type; };
 template <class V> M16_HD typename MaskOf<V>::type mask_splat(bool b);
 template <> M16_HD bool mask_splat<float>(bool b) { return b; }
 template <> M16_HD M2 mask_splat<F2>(bool b) { return M2{b, b}; }
+template <> M16_HD bool mask_splat<double>(bool b) { return b; }
 
 // normalisation of the common factor m (keeps every scaled quantity O(1..1e3))
 constexpr double kLam0 = 2.45e6;          // lambda / kLam0 ~ 1
@@ -201,16 +227,16 @@ struct alignas(16) PftConst : PftConstV<float> {
   float tann_lo_hi, tann_lo_lo, pad0, pad1;  // 273.15 + tmin_{open|close} as a float pair
 };
 
-M16_HD PftConst make_pft_const(const double v[11], int sem) {
-  PftConst c;
-  c.inv_dtmin = (float)(1.0 / (v[1] - v[0]));
-  c.tmin_bias = (float)(-(273.15 + v[0]) / (v[1] - v[0]));  // Tmin in kelvin goes in (:325)
-  c.inv_dvpd = (float)(1.0 / (v[3] - v[2]));
-  c.vpd_off = (float)(v[3] / (v[3] - v[2]));
-  c.gl_sh = (float)v[4]; c.gl_wv = (float)v[5]; c.g_cut = (float)v[6]; c.csl = (float)v[7];
-  c.rbl_max = (float)v[9];
-  c.rbl_delta = (float)(v[9] - v[8]);
-  c.inv_beta = (float)(1.0 / v[10]);
+template <class S>
+M16_HD void fill_pft_const(PftConstV<S>& c, const double v[11]) {
+  c.inv_dtmin = (S)(1.0 / (v[1] - v[0]));
+  c.tmin_bias = (S)(-(273.15 + v[0]) / (v[1] - v[0]));  // Tmin in kelvin goes in (:325)
+  c.inv_dvpd = (S)(1.0 / (v[3] - v[2]));
+  c.vpd_off = (S)(v[3] / (v[3] - v[2]));
+  c.gl_sh = (S)v[4]; c.gl_wv = (S)v[5]; c.g_cut = (S)v[6]; c.csl = (S)v[7];
+  c.rbl_max = (S)v[9];
+  c.rbl_delta = (S)(v[9] - v[8]);
+  c.inv_beta = (S)(1.0 / v[10]);
   // the rearranged algebra assumes the column is physically sane; anything else (NaN
   // columns of PFT 0 / 11, zero-width ramps, non-positive conductances) goes to the
   // op-for-op code
@@ -218,7 +244,12 @@ M16_HD PftConst make_pft_const(const double v[11], int sem) {
   for (int k = 0; k < 11; ++k) ok = ok && (v[k] == v[k]) && (v[k] > -1e30) && (v[k] < 1e30);
   ok = ok && (v[1] - v[0] > 1e-3) && (v[3] - v[2] > 1e-3) && (v[4] > 1e-12) && (v[5] > 1e-12) &&
        (v[6] >= 0.0) && (v[7] >= 0.0) && (v[8] > 1e-6) && (v[9] > 1e-6) && (v[10] > 1e-6);
-  c.ok = ok ? 1.0f : 0.0f;
+  c.ok = ok ? (S)1 : (S)0;
+}
+
+M16_HD PftConst make_pft_const(const double v[11], int sem) {
+  PftConst c;
+  fill_pft_const<float>(c, v);
   double lo = 273.15 + (sem == SEM_STATIC ? v[1] : v[0]);
   c.tann_lo_hi = (float)lo;
   c.tann_lo_lo = (float)(lo - (double)c.tann_lo_hi);
@@ -237,18 +268,22 @@ struct PixConstV {
 };
 typedef PixConstV<float> PixConst;
 
-M16_HD PixConst make_pix_const(float p, float t_ann, const PftConst& c, int sem) {
-  PixConst x;
-  x.pa = 0.348444f * (p * 0.01f);
-  x.ip = p * (float)(kKappa175 / 101300.0);
-  x.gp = p * (float)(kT0 / (kEps * kLam0 * kKappa));
+// `lo` = 273.15 + tmin_open (static, strict) or + tmin_close (instance), in double
+template <class S>
+M16_HD PixConstV<S> make_pix_const_s(S p, double t_ann, double lo, bool column_ok, int sem) {
+  PixConstV<S> x;
+  x.pa = (S)0.348444 * (p * (S)0.01);
+  x.ip = p * (S)(kKappa175 / 101300.0);
+  x.gp = p * (S)(kT0 / (kEps * kLam0 * kKappa));
   // the window is decided in double: a float32 T_ann must fall on the same side of
   // 298.15 and of 273.15 + tmin as it does in the float64 reference
-  const double ta = (double)t_ann;
-  const double lo = (double)c.tann_lo_hi + (double)c.tann_lo_lo;
-  x.window = (ta < 273.15 + 25) && (sem == SEM_STATIC ? (ta > lo) : (ta >= lo));
-  x.ok = (p >= 3.0e4f) && (p <= 1.2e5f) && (c.ok != 0.0f);
+  x.window = (t_ann < 273.15 + 25) && (sem == SEM_STATIC ? (t_ann > lo) : (t_ann >= lo));
+  x.ok = (p >= (S)3.0e4) && (p <= (S)1.2e5) && column_ok;
   return x;
+}
+M16_HD PixConst make_pix_const(float p, float t_ann, const PftConst& c, int sem) {
+  return make_pix_const_s<float>(p, (double)t_ann,
+                                 (double)c.tann_lo_hi + (double)c.tann_lo_lo, c.ok != 0.0f, sem);
 }
 
 M16_HD PixConstV<F2> pair_pix(const PixConst& a, const PixConst& b) {
@@ -278,6 +313,16 @@ template <class V> M16_HD V celsius(V t) {
   return (t - hi) - lo;
 }
 
+template <> M16_HD double celsius<double>(double t) { return t - 273.15; }   // (:216 ...)
+
+// q^-1.75 (:292): lg2 / ex2 on the special-function unit, or two square roots in double
+M16_HD float vpow_m175(float q) { return vex2(-1.75f * vlg2(q)); }
+M16_HD F2 vpow_m175(F2 q) { return vex2(-1.75f * vlg2(q)); }
+M16_HD double vpow_m175(double q) {
+  const double r = sqrt(q);
+  return 1.0 / ((q * r) * sqrt(r));
+}
+
 template <class V>
 struct StepInV {  // one pixel-timestep (or pair) of float drivers
   V lw_d, lw_n, sw_d, sw_n, alb, t_d, t_n, tmin, vpd_d, vpd_n, fpar, lai;
@@ -301,6 +346,10 @@ M16_HD F2 vmin3(F2 a, F2 b, F2 c) {
 M16_HD float vminabs3(float a, float b, float c) {
   return fminf(fminf(fabsf(a), fabsf(b)), fabsf(c));
 }
+M16_HD double vmin3(double a, double b, double c) { return fmin(fmin(a, b), c); }
+M16_HD double vminabs3(double a, double b, double c) {
+  return fmin(fmin(fabs(a), fabs(b)), fabs(c));
+}
 M16_HD F2 vminabs3(F2 a, F2 b, F2 c) {
   return F2{fminf(fminf(fabsf(a.x), fabsf(b.x)), fabsf(c.x)),
             fminf(fminf(fabsf(a.y), fabsf(b.y)), fabsf(c.y))};
@@ -309,6 +358,15 @@ M16_HD F2 vminabs3(F2 a, F2 b, F2 c) {
 // Width of every discontinuity guard after scaling: an element is re-evaluated in double
 // when one of its scaled distances to a switch is below kGuard in magnitude.
 constexpr float kGuard = 1.0e-4f;
+// Per scalar type: the guard width, and the centre c of the guarded interval (0, 2 c) of rh
+// next to the clamp at 0, where rh = 1 - VPD / SVP has lost its leading digits to
+// cancellation and rh^(VPD / beta) inherits the relative error.
+template <class S> M16_HD S guard_width();
+template <> M16_HD float guard_width<float>() { return kGuard; }
+template <> M16_HD double guard_width<double>() { return 1.0e-9; }
+template <class S> M16_HD S guard_rh0();
+template <> M16_HD float guard_rh0<float>() { return 1.0e-3f; }
+template <> M16_HD double guard_rh0<double>() { return 1.0e-5; }
 
 // One half-day, fast form.  STATIC night never transpires (its gate is never open).
 // Returns the three components.  `guard` receives the smaller of the half's two scaled
@@ -321,46 +379,48 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
                           typename MaskOf<V>::type& g_pos, typename MaskOf<V>::type& need,
                           V& gs_out, V& guard_a, V& guard_b) {
   typedef typename MaskOf<V>::type M;
+  typedef typename ScalarOf<V>::type K;
   // saturation vapour pressure 610.8 exp(17.27 Tc / (Tc + 237.3)) and its reciprocal (:1365)
-  const V xe = ((float)(17.27 * 1.4426950408889634) * tc) * vrcp(tc + 237.3f);
+  const V xe = (K(17.27 * 1.4426950408889634) * tc) * vrcp(tc + K(237.3));
   const V e = vex2(xe);                             // SVP / 610.8
-  const V ies = (float)(1.0 / 610.8) * vex2(-xe);   // 1 / SVP
-  V rh = vfma(-vpd, ies, 1.0f);
-  if (SEM == SEM_STATIC) rh = vmax(rh, splat<V>(0.0f));  // :280-281 (no upper clamp)
+  const V ies = K(1.0 / 610.8) * vex2(-xe);   // 1 / SVP
+  V rh = vfma(-vpd, ies, K(1.0));
+  if (SEM == SEM_STATIC) rh = vmax(rh, splat<V>(K(0.0)));  // :280-281 (no upper clamp)
   else rh = vsat(rh);                                    // :671-673
   // discontinuities in rh: the f_wet jump at 0.7 (:282), guarded for |rh - 0.7| < 4e-6, and
   // rh -> 0+, where rh^(vpd/beta) is ill-conditioned (:376), guarded for 0 < rh < 2e-3
   // (rh == 0 exactly -- the clamp -- is NOT guarded: |0 - 1e-3| * 0.1 == kGuard).
-  guard_a = vfma(rh, 25.0f, -17.5f);       // (rh - 0.7) * 25      : 4e-6 -> kGuard
-  guard_b = vfma(rh, 0.1f, -kGuard);       // (rh - 1e-3) * 0.1    : 1e-3 -> kGuard
+  guard_a = vfma(rh, K(25.0), K(-17.5));       // (rh - 0.7) * 25      : 4e-6 -> kGuard
+  // (rh - c) * (kGuard / c): |.| < kGuard  <=>  0 < rh < 2 c   (float: c = 1e-3)
+  guard_b = vfma(rh, guard_width<K>() / guard_rh0<K>(), -guard_width<K>());
   const V rh2 = rh * rh;
-  const V fw = vstep_ge(rh, 0.7f) * (rh2 * rh2);                          // :282
-  const V omfw = 1.0f - fw;
+  const V fw = vstep_ge(rh, K(0.7)) * (rh2 * rh2);                          // :282
+  const V omfw = K(1.0) - fw;
   // scaled slope S, psychrometric constant G and vapour-pressure term K (see kKappa)
-  const V q = t * (float)(kKappa / kT0);
-  const V d2 = vfma(tc, (float)kR, (float)(239.0 * kR));
+  const V q = t * K(kKappa / kT0);
+  const V d2 = vfma(tc, K(kR), K(239.0 * kR));
   const V dd = d2 * d2;
-  const V lam_n = vfma(tc, (float)(-2361.0 / kLam0), (float)(2.501e6 / kLam0));    // :121
+  const V lam_n = vfma(tc, K(-2361.0 / kLam0), K(2.501e6 / kLam0));    // :121
   const V S = (e * lam_n) * q;                                                       // :1397
   const V G = (x.gp * q) * dd;                                                       // :1289
   const V Kv = (lam_n * dd) * vpd;
   // X = rho T (:409-412); B = X / r_r = 4 sigma T^4 / Cp (:298-299)
-  const V X = vfma(rh, vfma(tc, -0.252f, 2.0582f), x.pa);
+  const V X = vfma(rh, vfma(tc, K(-0.252), K(2.0582)), x.pa);
   const V q2 = q * q;
   const V B = q2 * q2;
   // 1 / r_corr = (P / 101300) (T / 293.15)^-1.75 (:292), or the supplied r_corr_list entry
   V inv_rc;
   if (HAS_RC) {
     inv_rc = vrcp(rc);
-    need = mor(need, mnot(mand(vgt(rc, splat<V>(1e-6f)), vlt(rc, splat<V>(1e6f)))));
+    need = mor(need, mnot(mand(vgt(rc, splat<V>(K(1e-6))), vlt(rc, splat<V>(K(1e6))))));
   } else {
-    inv_rc = x.ip * vex2(-1.75f * vlg2(q));
+    inv_rc = x.ip * vpow_m175(q);
   }
   const V m_v = vsat(vfma(-vpd, c.inv_dvpd, c.vpd_off));  // reversed ramp on VPD (:326)
   const V Kf = Kv * fpar;
   const V SA = S * a_can;
-  V il = splat<V>(0.0f);
-  if (SEM == SEM_INSTANCE) il = (float)(1.0 / kLam0) * vrcp(lam_n);  // 1 / lambda (:959 ...)
+  V il = splat<V>(K(0.0));
+  if (SEM == SEM_INSTANCE) il = K(1.0 / kLam0) * vrcp(lam_n);  // 1 / lambda (:959 ...)
 
   HalfV<V> o;
   // -- wet canopy (:305-320): e = fw ce X (S Ac + Kf Y) / (S ce X + G Y), Y = X / r_aw
@@ -373,44 +433,44 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
     if (SEM == SEM_STATIC) {
       o.canopy = num * r;  // the (lai f_wet <= 1e-7) mask changes less than 1e-6 W m-2
     } else {
-      const V ev = (vmax(num, splat<V>(0.0f)) * r) * il;                        // :959
-      o.canopy = vsel(vle(lai, splat<V>(1e-7f)), splat<V>(0.0f), ev);           // :934-935, :961
+      const V ev = (vmax(num, splat<V>(K(0.0))) * r) * il;                        // :959
+      o.canopy = vsel(vle(lai, splat<V>(K(1e-7))), splat<V>(K(0.0)), ev);           // :934-935, :961
     }
   }
   // -- transpiration (:323-349, :1233-1258)
   g_pos = mask_splat<V>(false);
-  gs_out = splat<V>(0.0f);
+  gs_out = splat<V>(K(0.0));
   if (DAY || SEM == SEM_INSTANCE) {
-    V gs = splat<V>(0.0f);
+    V gs = splat<V>(K(0.0));
     if (DAY) {
       const V m_t = vsat(vfma(tmin, c.inv_dtmin, c.tmin_bias));                 // :325
       gs = ((c.csl * m_t) * m_v) * inv_rc;                                      // :327-328
     }
-    g_pos = vgt(gs, splat<V>(0.0f));
+    g_pos = vgt(gs, splat<V>(K(0.0)));
     gs_out = gs;
     const V sc = vfma(c.g_cut, inv_rc, gs);                                     // :329
     const V gbl = gl * omfw;                                                    // :333
     // lai > 0 and 1 - f_wet > 0 (:336): with gl_sh > 0 (PftConst::ok) and lai >= 0 (domain)
     // that is gbl > 0 -- rh > 1 (negative VPD, static) makes 1 - f_wet and gbl negative
-    const M ok = vgt(gbl, splat<V>(0.0f));
-    const V prod = vsel(ok, gbl * sc, splat<V>(1e-7f));  // g_canopy = prod / tot (:334-337)
-    const V tot = vsel(ok, gbl + sc, splat<V>(1.0f));
+    const M ok = vgt(gbl, splat<V>(K(0.0)));
+    const V prod = vsel(ok, gbl * sc, splat<V>(K(1e-7)));  // g_canopy = prod / tot (:334-337)
+    const V tot = vsel(ok, gbl + sc, splat<V>(K(1.0)));
     const V Yd = vfma(c.gl_sh, X, B);                    // X / r_a_dry (:340)
-    const V ac = (SEM == SEM_INSTANCE) ? vmax(SA, splat<V>(0.0f)) : SA;         // :1251
+    const V ac = (SEM == SEM_INSTANCE) ? vmax(SA, splat<V>(K(0.0))) : SA;         // :1251
     const V num = vfma(Kf, Yd, ac);
     const V den = vfma((S + G) * prod, X, (G * Yd) * tot);
     V tr = (num * ((omfw * prod) * X)) * vrcp(den);
     if (SEM == SEM_STATIC) {
       // the gate without a branch: open -> keep; closed -> drop; per element -> g_surf > 0
-      const float g_el = gate == GATE_ELEMENT ? 1.0f : 0.0f;
-      const float g_op = (gate == GATE_CLOSED || gate == GATE_ELEMENT) ? 0.0f : 1.0f;
-      o.trans = vsel(vgt(vfma(gs, g_el, g_op), splat<V>(0.0f)), tr, splat<V>(0.0f));
+      const K g_el = gate == GATE_ELEMENT ? K(1.0) : K(0.0);
+      const K g_op = (gate == GATE_CLOSED || gate == GATE_ELEMENT) ? K(0.0) : K(1.0);
+      o.trans = vsel(vgt(vfma(gs, g_el, g_op), splat<V>(K(0.0))), tr, splat<V>(K(0.0)));
     } else {
-      const M dead = mor(mnot(ok), vle(prod, 1e-7f * tot));                     // :1258
-      o.trans = vsel(dead, splat<V>(0.0f), tr * il);
+      const M dead = mor(mnot(ok), vle(prod, K(1e-7) * tot));                     // :1258
+      o.trans = vsel(dead, splat<V>(K(0.0)), tr * il);
     }
   } else {
-    o.trans = splat<V>(0.0f);
+    o.trans = splat<V>(K(0.0));
   }
   // -- bare soil (:357-376): q = X (S As r_t + Kv (1 - fpar) W) / (r_t (S X + G W)),
   //    W = X + r_t B, r_t = r_tot / r_corr
@@ -425,7 +485,7 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
     if (SEM == SEM_STATIC) {
       o.soil = qn * mix;
     } else {
-      qn = vmax(qn, splat<V>(0.0f));                                            // :858-861
+      qn = vmax(qn, splat<V>(K(0.0)));                                            // :858-861
       o.soil = (qn * mix) * il;                                                 // :864
     }
   }
@@ -445,6 +505,7 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
 // nan_halves below) is NaN: a sum of absolute values, so infinities cannot cancel into NaN.
 template <class V>
 M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in, V tc_d, V tc_n, V& nan_probe) {
+  typedef typename ScalarOf<V>::type K;
   const V sa = (vabs(in.lw_d) + vabs(in.lw_n)) + vabs(in.sw_d);
   const V sb = vabs(in.sw_n) + vabs(in.tmin);
   const V s2 = ((vabs(in.lai) + vabs(in.fpar)) + (vabs(in.vpd_d) + vabs(in.vpd_n))) +
@@ -456,9 +517,9 @@ M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in, V tc_d, V tc_n, 
   // ONE magnitude test: radiation terms and Tmin weigh twelve times (|.| < 9000 each: a fill
   // value fails), everything else once (< 1.1e5); the sum sees every driver, so a NaN or an
   // infinity anywhere fails it (fmin / fmax below would drop a NaN operand)
-  const V mag = vfma(sa + sb, 11.0f, nan_probe + sb);
-  return mand(mand(vlt(mag, splat<V>(1.1e5f)), vge(lo, splat<V>(0.0f))),
-              mand(vgt(vlo, splat<V>(-1000.0f)), vlt(tmag, splat<V>(66.85f))));
+  const V mag = vfma(sa + sb, K(11.0), nan_probe + sb);
+  return mand(mand(vlt(mag, splat<V>(K(1.1e5))), vge(lo, splat<V>(K(0.0)))),
+              mand(vgt(vlo, splat<V>(K(-1000.0))), vlt(tmag, splat<V>(K(66.85)))));
 }
 template <class V>
 M16_HD typename MaskOf<V>::type in_domain(const StepInV<V>& in) {
@@ -507,28 +568,29 @@ M16_HD typename MaskOf<V>::type step_core(const StepInV<V>& in, V tc_d, V tc_n,
                                           int gate, StepOutV<V>& o,
                                           typename MaskOf<V>::type& g_pos, V& gs_day) {
   typedef typename MaskOf<V>::type M;
+  typedef typename ScalarOf<V>::type K;
   M need = mask_splat<V>(false);
-  const V oma = 1.0f - in.alb;
+  const V oma = K(1.0) - in.alb;
   const V a_d = vfma(in.sw_d, oma, in.lw_d);            // :225
   const V a_n = in.lw_n;                                 // :226
   const V a_nc = vfma(in.sw_n, oma, in.lw_n);            // :272 (night: sw_rad_night)
   // soil heat flux (:229-241)
-  const V cond = vstep_ge_and(in.t_d - in.t_n, 5.0f, x.window);  // 1 inside the window, else 0
-  V g_d = cond * vfma(tc_d, 4.73f, -20.87f);
-  V g_n = cond * vfma(tc_n, 4.73f, -20.87f);
-  const V lim_d = 0.39f * a_d, lim_n = 0.39f * a_n;
+  const V cond = vstep_ge_and(in.t_d - in.t_n, K(5.0), x.window);  // 1 inside the window, else 0
+  V g_d = cond * vfma(tc_d, K(4.73), K(-20.87));
+  V g_n = cond * vfma(tc_n, K(4.73), K(-20.87));
+  const V lim_d = K(0.39) * a_d, lim_n = K(0.39) * a_n;
   // |G| > 0.39 |A| switches G to 0.39 A (:239); within kGuard of equality the decision is
   // the double code's.  A_day > 0 gates both limits below (:245-252).
   const V gd_d = vabs(g_d) - vabs(lim_d), gd_n = vabs(g_n) - vabs(lim_n);
-  g_d = vsel(vgt(gd_d, splat<V>(0.0f)), lim_d, g_d);
-  g_n = vsel(vgt(gd_n, splat<V>(0.0f)), lim_n, g_n);
-  const M a_pos = vgt(a_d, splat<V>(0.0f));
+  g_d = vsel(vgt(gd_d, splat<V>(K(0.0))), lim_d, g_d);
+  g_n = vsel(vgt(gd_n, splat<V>(K(0.0))), lim_n, g_n);
+  const M a_pos = vgt(a_d, splat<V>(K(0.0)));
   V r_d = a_d - g_d;                                     // A - G, day
   V r_n = a_n - g_n;
-  r_d = vsel(mand(a_pos, vlt(r_d, splat<V>(0.0f))), splat<V>(0.0f), r_d);  // :245-247 (G := A)
-  const V floor_n = -0.5f * a_d;
+  r_d = vsel(mand(a_pos, vlt(r_d, splat<V>(K(0.0)))), splat<V>(K(0.0)), r_d);  // :245-247 (G := A)
+  const V floor_n = K(-0.5) * a_d;
   r_n = vsel(mand(a_pos, vlt(r_n, floor_n)), floor_n, r_n);  // :248-252 (G := A_n + A_d / 2)
-  const V omf = 1.0f - in.fpar;
+  const V omf = K(1.0) - in.fpar;
   const V gl = c.gl_sh * in.lai, gw = c.gl_wv * in.lai;  // shared by the two half-days
   M unused = mask_splat<V>(false);
   V gs_unused, ga_d, gb_d, ga_n, gb_n;
@@ -540,7 +602,7 @@ M16_HD typename MaskOf<V>::type step_core(const StepInV<V>& in, V tc_d, V tc_n,
                                              gate, unused, need, gs_unused, ga_n, gb_n);
   // every discontinuity guard in one compare: the smallest scaled distance to a switch
   const V dist = vminabs3(vminabs3(gd_d, gd_n, a_d), vminabs3(ga_d, gb_d, ga_n), gb_n);
-  need = mor(need, vlt(dist, splat<V>(kGuard)));
+  need = mor(need, vlt(dist, splat<V>(guard_width<K>())));
   if (SEM == SEM_STATIC) {  // :380
     o.tot_day = (o.day.trans + o.day.canopy) + o.day.soil;
     o.tot_night = (o.night.trans + o.night.canopy) + o.night.soil;

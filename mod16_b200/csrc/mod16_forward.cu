@@ -207,8 +207,9 @@ int run_with_gate(ForwardArgs<R>& a, uint32_t flags, cudaStream_t st, PassFn pas
   return MOD16_ERR_FLAGS;
 }
 
-// defined in mod16_forward_fast.cu
+// defined in mod16_forward_fast.cu / mod16_forward_fast64.cu
 int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st);
+int launch_fast_f64(ForwardArgs<double>& a, uint32_t flags, cudaStream_t st);
 // storage formats of mod16_forward_raw_f32 (mod16_forward_pipe.cuh)
 constexpr int FMT_F32_PREP = 1, FMT_MODIS = 2, FMT_PACKED = 3;
 
@@ -249,8 +250,10 @@ int mod16_forward_f64(const mod16_drivers_t* drivers, const mod16_params_t* para
   int rc = mod16::build_forward_args<double>(drivers, params, out, T, N, flags, a);
   if (rc != MOD16_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool fast = !(flags & MOD16_FORCE_MIRROR);
   return mod16::run_with_gate<double>(a, flags, st, [&](mod16::ForwardArgs<double>& x) {
-    return mod16::launch_strided<double>(x, flags, st);
+    return fast ? mod16::launch_fast_f64(x, flags, st)
+                : mod16::launch_strided<double>(x, flags, st);
   });
 }
 

@@ -154,8 +154,75 @@ static void run_nan_halves(int sem, const float* drv, const double* par, int64_t
 }
 #endif
 
+#ifdef HM_WITH_FAST
+// The float64 entry's fast path (forward_fast64_kernel): the rearranged algebra in double,
+// the op-for-op code for the elements it flags.  out rows as in run_fast.
+static void run_fast64(int sem, int gate, const double* drv, const double* par, const double* rc,
+                       int has_rc, int64_t n, double* out, uint8_t* gpos) {
+  for (int64_t i = 0; i < n; ++i) {
+    Drivers<double> d;
+    const double* c = drv;
+    d.lw_d = c[0 * n + i]; d.lw_n = c[1 * n + i]; d.sw_d = c[2 * n + i];
+    d.sw_n = c[3 * n + i]; d.alb = c[4 * n + i];  d.t_d = c[5 * n + i];
+    d.t_n = c[6 * n + i];  d.t_ann = c[7 * n + i]; d.tmin = c[8 * n + i];
+    d.vpd_d = c[9 * n + i]; d.vpd_n = c[10 * n + i]; d.p = c[11 * n + i];
+    d.fpar = c[12 * n + i]; d.lai = c[13 * n + i];
+    d.rc_d = has_rc ? rc[i] : 0.0;
+    d.rc_n = has_rc ? rc[n + i] : 0.0;
+    double col[11];
+    for (int k = 0; k < 11; ++k) col[k] = par[k * n + i];
+    Params<double> q;
+    q.tmin_close = col[0]; q.tmin_open = col[1]; q.vpd_open = col[2]; q.vpd_close = col[3];
+    q.gl_sh = col[4]; q.gl_wv = col[5]; q.g_cuticular = col[6]; q.csl = col[7];
+    q.rbl_min = col[8]; q.rbl_max = col[9]; q.beta = col[10];
+    q.tann_lo = 273.15 + (sem == SEM_STATIC ? col[1] : col[0]);
+    fast::PftConstV<double> pc;
+    fast::fill_pft_const<double>(pc, col);
+    const fast::PixConstV<double> px =
+        fast::make_pix_const_s<double>(d.p, d.t_ann, q.tann_lo, pc.ok != 0.0, sem);
+    fast::StepInV<double> in;
+    in.lw_d = d.lw_d; in.lw_n = d.lw_n; in.sw_d = d.sw_d; in.sw_n = d.sw_n; in.alb = d.alb;
+    in.t_d = d.t_d; in.t_n = d.t_n; in.tmin = d.tmin; in.vpd_d = d.vpd_d; in.vpd_n = d.vpd_n;
+    in.fpar = d.fpar; in.lai = d.lai; in.rc_d = d.rc_d; in.rc_n = d.rc_n;
+    fast::StepOutV<double> r;
+    bool g = false, need;
+    if (sem == SEM_STATIC)
+      need = has_rc ? fast::step_fast<double, SEM_STATIC, true>(in, pc, px, gate, r, g)
+                    : fast::step_fast<double, SEM_STATIC, false>(in, pc, px, gate, r, g);
+    else
+      need = has_rc ? fast::step_fast<double, SEM_INSTANCE, true>(in, pc, px, gate, r, g)
+                    : fast::step_fast<double, SEM_INSTANCE, false>(in, pc, px, gate, r, g);
+    if (need) {
+      Half<double> day, night;
+      if (sem == SEM_STATIC) pixel_step<double, SEM_STATIC>(d, q, has_rc != 0, gate, day, night, g);
+      else pixel_step<double, SEM_INSTANCE>(d, q, has_rc != 0, gate, day, night, g);
+      r.day.canopy = day.canopy; r.day.soil = day.soil; r.day.trans = day.trans;
+      r.night.canopy = night.canopy; r.night.soil = night.soil; r.night.trans = night.trans;
+      if (sem == SEM_STATIC) {
+        r.tot_day = half_total<double, SEM_STATIC>(day);
+        r.tot_night = half_total<double, SEM_STATIC>(night);
+      } else {
+        r.tot_day = half_total<double, SEM_INSTANCE>(day);
+        r.tot_night = half_total<double, SEM_INSTANCE>(night);
+      }
+      r.tot = r.tot_day + r.tot_night;
+    }
+    out[0 * n + i] = r.day.canopy;   out[1 * n + i] = r.day.soil;
+    out[2 * n + i] = r.day.trans;    out[3 * n + i] = r.night.canopy;
+    out[4 * n + i] = r.night.soil;   out[5 * n + i] = r.night.trans;
+    out[6 * n + i] = r.tot_day;      out[7 * n + i] = r.tot_night;
+    out[8 * n + i] = r.tot;
+    gpos[i] = (g ? 1 : 0) | (need ? 2 : 0);
+  }
+}
+#endif
+
 extern "C" {
 #ifdef HM_WITH_FAST
+void hm_fast_f64(int sem, int gate, const double* drv, const double* par, const double* rc,
+                 int has_rc, int64_t n, double* out, uint8_t* gpos) {
+  run_fast64(sem, gate, drv, par, rc, has_rc, n, out, gpos);
+}
 void hm_nan_halves(int sem, const float* drv, const double* par, int64_t n, uint8_t* h,
                    uint8_t* gpos) {
   run_nan_halves(sem, drv, par, n, h, gpos);

@@ -247,3 +247,54 @@ def test_masked_driver_rule_is_sound(semantics):
             g_surf = (col[7] * orc.ramp_up(d64[8] - 273.15, col[0], col[1]) *
                       orc.ramp_down(d64[9], col[2], col[3])) / orc.r_correction(d64[11], d64[5])
         assert np.array_equal(g[h > 0], (g_surf > 0)[h > 0])
+
+
+# ---- the float64 entry's fast path (forward_fast64_kernel) -----------------------------------
+@pytest.mark.parametrize('semantics', ['static', 'instance'])
+@pytest.mark.parametrize('kind,nan', [('physical', 0.0), ('stress', 0.0), ('physical', 0.01),
+                                      ('stress', 0.01)])
+def test_float64_fast_path_within_1e10_of_the_oracle(semantics, kind, nan):
+    'The rearranged algebra in double: 1e-10 like the op-for-op code, and rarely guarded.'
+    T, N = 60, 400
+    d = synthetic.host_drivers(T, N, 4242, kind=kind, dtype=np.float64, nan_frac=nan,
+                               fill_frac=nan)
+    rng = np.random.default_rng(5)
+    d['vpd_day'][rng.random((T, N)) < 0.03] *= -0.1        # supersaturated air
+    drv = [d[k] for k in NAMES]
+    table = _table()
+    pft = synthetic.host_pft_map(N, 4243)
+    vec = [table[i][pft].reshape(1, N) for i in range(11)]
+    r = hostmath.forward(vec, drv, semantics, 'element', dtype=np.float64, fast=True)
+    with np.errstate(all='ignore'):
+        if semantics == 'static':
+            day, night = orc.static_evapotranspiration(vec, *drv, gate='element', components=True)
+            scale = 1.0
+        else:
+            day = [np.empty((T, N)) for _ in range(3)]
+            night = [np.empty((T, N)) for _ in range(3)]
+            for code in np.unique(pft):
+                m = pft == code
+                sub = [v[:, m] if isinstance(v, np.ndarray) and v.ndim == 2 else
+                       (v[m] if isinstance(v, np.ndarray) else v) for v in drv]
+                out = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, table[:, code]))) \
+                    .evapotranspiration(*sub, separate=True)
+                for c in range(3):
+                    day[c][:, m], night[c][:, m] = out[0][c], out[1][c]
+            scale = parity.MASS_SCALE
+    for c in range(3):
+        parity.assert_parity(r['day'][c], day[c], np.float64, scale, what='day %d' % c)
+        parity.assert_parity(r['night'][c], night[c], np.float64, scale, what='night %d' % c)
+    tot = (day[0] + day[1] + day[2]) + (night[0] + night[1] + night[2])
+    parity.assert_parity(r['tot'], tot, np.float64, scale, what='total')
+    if nan == 0.0:
+        assert r['guarded'].mean() < 2e-3, r['guarded'].mean()
+
+
+def test_float64_fast_path_equals_the_op_for_op_code_on_a_plain_element():
+    drv = [-30., -20., 300., 0., 0.15, 295., 285., 283., 280., 1200., 300., 95000., 0.5, 2.0]
+    a = hostmath.forward(BPLUT7, drv, 'static', 'element', dtype=np.float64, fast=True)
+    b = hostmath.forward(BPLUT7, drv, 'static', 'element', dtype=np.float64)
+    for h in ('day', 'night'):
+        for c in range(3):
+            assert abs(a[h][c] - b[h][c]) <= 1e-12 * max(abs(b[h][c]), 1.0)
+    assert not a['guarded'].any()
