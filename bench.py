@@ -809,7 +809,7 @@ def secondary_lines(args, device, world, rank, drv_list, drv, pft, table, out):
 
 
 def f64_kernel_name():
-    return 'forward_strided_kernel<double>'
+    return 'forward_fast64_kernel'
 
 
 def main():
