@@ -95,6 +95,14 @@ enum {
                                       *gate_flag and the sums are incomplete: rerun with a
                                       larger workspace. */
 #define MOD16_ANNUAL_OVERFLOW 0x40000000
+#define MOD16_OUT_POTENTIAL 0x40u  /* float32, streamable layouts (else MOD16_ERR_LAYOUT):
+                                      out[0] = day + night total as MOD16_OUT_SUM, and the
+                                      potential terms in W m-2: out[1] potential
+                                      transpiration (day, mod16/__init__.py:547-602); out[2],
+                                      out[3] evaporation from the saturated soil fraction and
+                                      POTENTIAL evaporation from the unsaturated fraction,
+                                      day (potential_soil_evaporation, :450-545); out[4],
+                                      out[5] the same at night */
 #define MOD16_OUT_MASK 0xF0u
 /* the static path's batch-global transpiration gate `if np.any(g_surf > 0)` (:343) */
 #define MOD16_GATE_GLOBAL 0x000u     /* call-exact: optimistic pass + device-side fix-up */

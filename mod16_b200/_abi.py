@@ -12,7 +12,7 @@ N_DRIVERS = 14
 
 # flag words (mirror include/mod16_b200.h)
 SEM_STATIC, SEM_INSTANCE = 0x0, 0x1
-OUT_SUM, OUT_DAY_NIGHT, OUT_COMPONENTS, OUT_ANNUAL = 0x00, 0x10, 0x20, 0x30
+OUT_SUM, OUT_DAY_NIGHT, OUT_COMPONENTS, OUT_ANNUAL, OUT_POTENTIAL = 0x00, 0x10, 0x20, 0x30, 0x40
 GATE_GLOBAL, GATE_ELEMENT, GATE_OPEN, GATE_CLOSED = 0x000, 0x100, 0x200, 0x300
 GATE_OPEN_TRACK, GATE_FIXUP = 0x400, 0x500
 FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000

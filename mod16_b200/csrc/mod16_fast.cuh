@@ -354,7 +354,7 @@ struct StepInV {  // one pixel-timestep (or pair) of float drivers
 };
 
 template <class V>
-struct HalfV { V canopy, soil, trans; };
+struct HalfV { V canopy, soil, trans, pt, sat, unsat; };  // (pt, sat, unsat: see Half<R>)
 
 template <class V>
 struct StepOutV {  // components and totals of one pixel-timestep (or pair)
@@ -447,6 +447,8 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
   if (SEM == SEM_INSTANCE) il = K(1.0 / kLam0) * vrcp(lam_n);  // 1 / lambda (:959 ...)
 
   HalfV<V> o;
+  // potential transpiration (:602): alpha (1 - f_wet) s A_c / (s + gamma), daytime
+  o.pt = DAY ? (K(1.26) * (SA * omfw)) * vrcp(S + G) : splat<V>(K(0.0));
   // -- wet canopy (:305-320): e = fw ce X (S Ac + Kf Y) / (S ce X + G Y), Y = X / r_aw
   {
     const V ceX = (gw * fw) * X;
@@ -506,6 +508,8 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
     V qn = (num * X) * vrcp(den);
     const V pw = vex2((vpd * c.inv_beta) * vlg2(rh));  // rh^(vpd/beta), 1 when rh == 1
     const V mix = vfma(omfw, pw, fw);
+    o.sat = qn * fw;        // :371 / :542   (W m-2, before the instance path's clamps)
+    o.unsat = qn * omfw;    // :373 / :544
     if (SEM == SEM_STATIC) {
       o.soil = qn * mix;
     } else {
@@ -694,6 +698,8 @@ static void pixel_step_exact(const StepIn& in, const double col[11], bool has_rc
   o.day.canopy = (float)dd.canopy; o.day.soil = (float)dd.soil; o.day.trans = (float)dd.trans;
   o.night.canopy = (float)nn.canopy; o.night.soil = (float)nn.soil;
   o.night.trans = (float)nn.trans;
+  o.day.pt = (float)dd.pt; o.day.sat = (float)dd.sat; o.day.unsat = (float)dd.unsat;
+  o.night.pt = 0.0f; o.night.sat = (float)nn.sat; o.night.unsat = (float)nn.unsat;
   // totals are formed in double: garbage-in elements (finite fills) cancel catastrophically
   const double td = half_total<double, SEM>(dd), tn = half_total<double, SEM>(nn);
   o.tot_day = (float)td; o.tot_night = (float)tn; o.tot = (float)(td + tn);

@@ -71,8 +71,9 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
                  gm = flags & MOD16_GATE_MASK;
   if (sem > MOD16_SEM_INSTANCE) return MOD16_ERR_FLAGS;
   if (om != MOD16_OUT_SUM && om != MOD16_OUT_DAY_NIGHT && om != MOD16_OUT_COMPONENTS &&
-      om != MOD16_OUT_ANNUAL)
+      om != MOD16_OUT_ANNUAL && om != MOD16_OUT_POTENTIAL)
     return MOD16_ERR_FLAGS;
+  if (om == MOD16_OUT_POTENTIAL && sizeof(R) != sizeof(float)) return MOD16_ERR_FLAGS;
   if (om == MOD16_OUT_ANNUAL) {   // float32 static path; needs the group index of every step
     if (sizeof(R) != sizeof(float) || sem != MOD16_SEM_STATIC) return MOD16_ERR_FLAGS;
     if ((!out->group && T > 0) || out->n_groups < 1 || !out->gate_flag) return MOD16_ERR_NULL;

@@ -207,7 +207,7 @@ __device__ __forceinline__ int pipe_rule(const ForwardArgs<float>& a, int ts, fl
   c.vpd_off = vpd_off; c.inv_dvpd = inv_dvpd;
   bool g_pos;
   const int h = fast::nan_halves<SEM>(in, c, a.has_rc != 0, g_pos);
-  if (OUT == 2 || !((OUT == 0 || OUT == 3) ? h != 0 : h == 3)) return -1;
+  if (OUT == 2 || OUT == 4 || !((OUT == 0 || OUT == 3) ? h != 0 : h == 3)) return -1;
   if (OUT == 3) {
     annual_add(a, t, n, kAnnualNaN);
     return g_pos ? 1 : 0;
@@ -339,6 +339,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   const float swn_scalar = a.drv[MOD16_D_SW_RAD_NIGHT].scalar;
   const int gate = a.gate;
   constexpr int n_out = OUT == 3 ? 0 : (OUT == 0 ? 1 : (OUT == 1 ? 2 : 6));
+  constexpr bool RULE = OUT != 2 && OUT != 4;   // outputs a NaN total decides without the double code
   // this thread's pixel in a row (float32 rows; storage formats index per array)
   const uint32_t my0 = keep_u32(FMT < FMT_MODIS ? data0 + (uint32_t)tid * 4u : data0);
   const bool clamp_vpd_n = FMT != FMT_F32 && (a.prep & MOD16_PREP_VPD_NIGHT_CLAMP) != 0;
@@ -409,7 +410,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
         const float probe = j == 0 ? nan_probe.x : nan_probe.y;
         const float td = j == 0 ? in.t_d.x : in.t_d.y, tn = j == 0 ? in.t_n.x : in.t_n.y;
         const float pa = j == 0 ? px.pa.x : px.pa.y;
-        if (OUT != 2 && (probe != probe || pa != pa || td < 0.0f || tn < 0.0f)) {
+        if (RULE && (probe != probe || pa != pa || td < 0.0f || tn < 0.0f)) {
           if (rule_in_regs) {
             flags |= j == 0 ? MASKED_X : MASKED_Y;
             continue;
@@ -442,6 +443,10 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       q_y = __float2ull_rn(fminf(mm.y, 1.0e16f));
       g_x = __ldg(a.group + (int64_t)blockIdx.y * a.t_chunk + i * PIPE_SUB);
       g_y = TWO ? __ldg(a.group + (int64_t)blockIdx.y * a.t_chunk + i * PIPE_SUB + 1) : g_x;
+    } else if (OUT == 4) {
+      res[0] = r.tot;       res[1] = r.day.pt;
+      res[2] = r.day.sat;   res[3] = r.day.unsat;
+      res[4] = r.night.sat; res[5] = r.night.unsat;
     } else if (OUT == 0) {
       res[0] = r.tot;
     } else if (OUT == 1) {
@@ -553,12 +558,14 @@ int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mod
   M16_PIPE(0, 0, 1); M16_PIPE(0, 0, 2); M16_PIPE(0, 0, 3);
   M16_PIPE(1, 0, 1); M16_PIPE(1, 0, 2); M16_PIPE(1, 0, 3);
   if constexpr (SEM == SEM_STATIC) { M16_PIPE(3, 0, 0); }
+  M16_PIPE(4, 0, 0);
 #undef M16_PIPE
   return MOD16_ERR_FLAGS;
 }
 
 inline bool pipe_has_variant(int out_mode, int extra, int fmt = 0) {
-  if (out_mode == 3) return extra == 0 && fmt == 0;   // annual sums: the plain tile layout
+  // annual sums, potential terms: the plain tile layout
+  if (out_mode == 3 || out_mode == 4) return extra == 0 && fmt == 0;
   return fmt == 0 ? (out_mode < 2 || extra < 2) : (out_mode < 2 && extra == 0);
 }
 

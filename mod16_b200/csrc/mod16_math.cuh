@@ -49,6 +49,10 @@ struct Drivers {  // one pixel-timestep, positional order of the reference signa
 template <typename R>
 struct Half {
   R canopy, soil, trans;
+  // MOD16_OUT_POTENTIAL [W m-2]: potential transpiration (:547-602, daytime; 0 at night) and
+  // the two terms of potential_soil_evaporation (:505-545 = :371, :373): evaporation from the
+  // saturated fraction and POTENTIAL evaporation from the unsaturated fraction
+  R pt, sat, unsat;
 };
 
 template <typename R> M16_HD R m_exp(R x);
@@ -183,6 +187,7 @@ M16_HD Half<R> half_day(bool daytime, R t, R vpd, R sw, R lw, R a_soil, R rc_in,
   R r_r = r_radiative<R>(rho, t);      // :298-299
 
   Half<R> o;
+  o.pt = daytime ? (R(1.26) * (s * a_can) * (R(1) - fw)) / (s + gamma) : R(0);  // :602
   // -- wet canopy evaporation
   if (SEM == SEM_STATIC) {
     R r_h = R(1) / (q.gl_sh * d.lai * fw);  // :305
@@ -235,6 +240,8 @@ M16_HD Half<R> half_day(bool daytime, R t, R vpd, R sw, R lw, R a_soil, R rc_in,
   R denom = s + gamma * (r_tot / r_as);                                       // :369
   R e_sat = (numer * fw) / denom;                                             // :371
   R e_unsat = (numer * (R(1) - fw)) / denom;                                  // :373
+  o.sat = e_sat;
+  o.unsat = e_unsat;
   R moist = m_pow<R>(rh, vpd / q.beta);                                       // :376 / :861
   if (SEM == SEM_STATIC) {
     o.soil = e_sat + e_unsat * moist;

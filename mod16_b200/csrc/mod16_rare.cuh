@@ -132,6 +132,10 @@ __device__ __forceinline__ void store_exact(const ForwardArgs<float>& a, int64_t
   if (OUT == 3) {
     const float tcm = 0.5f * (fast::celsius<float>(in.t_d) + fast::celsius<float>(in.t_n));
     annual_add(a, o / a.N, o % a.N, annual_fixed(r.tot, tcm));
+  } else if (OUT == 4) {
+    a.out[0][o] = r.tot;        a.out[1][o] = r.day.pt;
+    a.out[2][o] = r.day.sat;    a.out[3][o] = r.day.unsat;
+    a.out[4][o] = r.night.sat;  a.out[5][o] = r.night.unsat;
   } else if (OUT == 0) {
     a.out[0][o] = r.tot;
   } else if (OUT == 1) {
@@ -169,7 +173,7 @@ __device__ __noinline__ int rare_one(const ForwardArgs<float>& a, int64_t t, int
   const StepIn in = load_step(a, t, n);
   const int64_t o = t * a.N + n;
   bool g_pos = false;
-  if (OUT != 2) {
+  if (OUT != 2 && OUT != 4) {
     const PftConst pc = fast::make_pft_const(col, SEM);
     const int h = fast::nan_halves<SEM>(in, pc, a.has_rc != 0, g_pos);
     if (OUT == 0 ? h != 0 : h == 3) {

@@ -243,6 +243,10 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
                [mm] per pixel and group of time steps -- ``groups`` holds the group (year)
                index of every step; the reduction of the calibration's precipitation
                constraint, mod16/calibration.py:783-790, fused into the kernel)
+               | 'potential' (float32, (T, N) drivers: the total and the potential terms
+               [W m-2] -- total, potential transpiration (day, :547-602), evaporation of
+               the saturated / potential evaporation of the unsaturated soil fraction
+               (day), the same two at night (:450-545) -- from the same pass)
     gate     : 'global' (reference) | 'element' | 'open' | 'closed' | 'open_track' | 'fixup'
 
     drivers may hold ``rawio.RawDriver`` objects (storage formats: uint8 / int16 with scale,
@@ -430,10 +434,11 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
         for j in range(_abi.N_PFT):
             cp.table[i][j] = tab[i, j]
 
-    n_out = {'sum': 1, 'day_night': 2, 'components': 6, 'annual': 1}[out_mode]
+    n_out = {'sum': 1, 'day_night': 2, 'components': 6, 'annual': 1, 'potential': 6}[out_mode]
     flags = {'static': _abi.SEM_STATIC, 'instance': _abi.SEM_INSTANCE}[semantics]
     flags |= {'sum': _abi.OUT_SUM, 'day_night': _abi.OUT_DAY_NIGHT,
-              'components': _abi.OUT_COMPONENTS, 'annual': _abi.OUT_ANNUAL}[out_mode]
+              'components': _abi.OUT_COMPONENTS, 'annual': _abi.OUT_ANNUAL,
+              'potential': _abi.OUT_POTENTIAL}[out_mode]
     flags |= _abi.GATE_FLAGS[gate] | force
     if out_mode == 'annual':
         outs = list(out)                    # (n_groups, N) int64 accumulators, zeroed

@@ -82,6 +82,25 @@ class MOD16(ComponentMixin):
                            out_mode='sum', **kw)[0]
 
     @staticmethod
+    def _et_potential(params, *drivers, **kw):
+        '''
+        ``_et`` together with the potential terms the MOD16 product's PET / PLE layers are
+        built from, all from ONE pass over the drivers [W m-2]: returns the dict ``et`` (day +
+        night, as ``_et``), ``potential_transpiration`` (daytime, reference
+        ``MOD16.potential_transpiration``, mod16/__init__.py:547-602), ``evap_sat_day`` /
+        ``evap_unsat_day`` / ``evap_sat_night`` / ``evap_unsat_night`` (the two results of
+        ``MOD16.potential_soil_evaporation``, :450-545, with the static path's radiation
+        to the soil).  float32, (T, N) drivers.  ``params`` may be the pair ``(table, pft)``.
+        '''
+        if isinstance(params, tuple) and len(params) == 2:
+            kw.update(table=params[0], pft=params[1])
+            params = None
+        kw.setdefault('semantics', 'static')
+        out = run_forward(drivers, params=params, out_mode='potential', **kw)
+        return dict(zip(('et', 'potential_transpiration', 'evap_sat_day', 'evap_unsat_day',
+                         'evap_sat_night', 'evap_unsat_night'), out))
+
+    @staticmethod
     def _annual_et(params, years, *drivers, **kw):
         '''
         Annual evapotranspiration [mm] per pixel of ``_et(params, *drivers)`` -- the model-side

@@ -227,3 +227,56 @@ def test_nccl_world_of_one(cuda_lib):
         assert torch.equal(s0, s2) and torch.equal(c0, c2)
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('semantics', ['static', 'instance'])
+def test_potential_terms_from_the_same_pass(cuda_lib, semantics):
+    '''
+    MOD16_OUT_POTENTIAL: the total and the potential terms of
+    `MOD16.potential_transpiration` (:547-602) and `MOD16.potential_soil_evaporation`
+    (:450-545) as outputs of the fused kernel, against the reference's own functions
+    (restated in the oracle, golden-pinned in components.npz) on the same inputs.
+    '''
+    T, N = 18, 4800
+    d = synthetic.host_drivers(T, N, 181, dtype=np.float32)
+    rng = np.random.default_rng(182)
+    d['lai'][rng.random((T, N)) < 0.01] = np.nan           # the queue takes part
+    drv = [d[k] for k in NAMES]
+    d64 = dict((k, v.astype(np.float64) if isinstance(v, np.ndarray) else v) for k, v in d.items())
+    col = list(_table()[:, 7])
+    p = dict(zip(orc.PARAM_ORDER, col))
+    M = orc.InstanceModel
+    with np.errstate(all='ignore'):
+        rad_day = d64['sw_rad_day'] * (1 - d64['sw_albedo']) + d64['lw_net_day']
+        rad_night = d64['lw_net_night']
+        lo = 273.15 + (p['tmin_open'] if semantics == 'static' else p['tmin_close'])
+        ta = d64['temp_annual']
+        cond = (ta < 273.15 + 25) & ((ta > lo) if semantics == 'static' else (ta >= lo)) & \
+            ((d64['temp_day'] - d64['temp_night']) >= 5)
+        g = orc._ground_heat(rad_day, rad_night, d64['temp_day'], d64['temp_night'], cond)
+        rs = orc._soil_radiation(rad_day, rad_night, g[0], g[1], d64['fpar'])
+        kw = dict(vpd_open=p['vpd_open'], vpd_close=p['vpd_close'], rbl_min=p['rbl_min'],
+                  rbl_max=p['rbl_max'])
+        sat_d, unsat_d = M.potential_soil_evaporation(
+            d64['pressure'], d64['temp_day'], d64['vpd_day'], d64['fpar'], rs[0], **kw)
+        sat_n, unsat_n = M.potential_soil_evaporation(
+            d64['pressure'], d64['temp_night'], d64['vpd_night'], d64['fpar'], rs[1], **kw)
+        pt = M.potential_transpiration(d64['lw_net_day'], d64['sw_rad_day'], d64['sw_albedo'],
+                                       d64['pressure'], d64['temp_day'], d64['vpd_day'],
+                                       d64['fpar'])
+        if semantics == 'static':
+            tot = orc.static_et(col, *[d64[k] for k in NAMES])
+        else:
+            day, night = M(p).evapotranspiration(*[d64[k] for k in NAMES])
+            tot = day + night
+    got = MOD16._et_potential(col, *drv, semantics=semantics)
+    assert _kernel(cuda_lib) == (_abi.KERNEL_PIPE, 0)
+    scale = 1.0 if semantics == 'static' else parity.MASS_SCALE
+    parity.assert_parity(got['et'], tot, np.float32, scale, what='total')
+    ok = ~np.isnan(d['lai'])       # (LAI does not enter the potential terms: finite there too)
+    for name, want in (('potential_transpiration', pt), ('evap_sat_day', sat_d),
+                       ('evap_unsat_day', unsat_d), ('evap_sat_night', sat_n),
+                       ('evap_unsat_night', unsat_n)):
+        parity.assert_parity(got[name][ok], want[ok], np.float32, what=name)
+        parity.assert_parity(got[name][~ok], want[~ok], np.float32, what=name + ' (queued)')
+    assert np.isnan(got['et'][~ok]).all() == (semantics == 'static')
