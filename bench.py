@@ -952,7 +952,7 @@ def main():
         for wl in ('calibration', 'sobol'):
             for shard in (('draw', 'site') if (world > 1 and wl == 'calibration') else ('draw',)):
                 legs.append(lambda wl=wl, shard=shard: objective_bench(
-                    wl, dev=device, world=world, rank=rank, shard=shard, steps=3, warm=1,
+                    wl, dev=device, world=world, rank=rank, shard=shard, steps=3, warm=2,
                     cpu_draws=1 if world == 1 else 0))
         for leg in legs:
             res = leg()
