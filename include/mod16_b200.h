@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 8
+#define MOD16_ABI_VERSION 9
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -103,6 +103,12 @@ enum {
                                       POTENTIAL evaporation from the unsaturated fraction,
                                       day (potential_soil_evaporation, :450-545); out[4],
                                       out[5] the same at night */
+#define MOD16_OUT_COMPOSITE 0x50u  /* float32, streamable layouts: out[0] = day * day_weight[t] +
+                                      night * night_weight[t] -- the day-length weighted
+                                      composite of tests/verification/verify2.py:112-115,
+                                      `pred_day * updown * 8 * 3600 + pred_night * (24 -
+                                      updown) * 8 * 3600` [kg m-2 (8 days)-1 from the instance
+                                      path's kg m-2 s-1]; the weights are float32[T] */
 #define MOD16_OUT_MASK 0xF0u
 /* the static path's batch-global transpiration gate `if np.any(g_surf > 0)` (:343) */
 #define MOD16_GATE_GLOBAL 0x000u     /* call-exact: optimistic pass + device-side fix-up */
@@ -166,6 +172,10 @@ typedef struct mod16_out {
   const int32_t* group;
   int32_t n_groups;
   int32_t reserved;
+  /* MOD16_OUT_COMPOSITE: device float32[T], seconds of daylight / of night each time step
+     stands for (e.g. updown * 8 * 3600 and (24 - updown) * 8 * 3600) */
+  const float* day_weight;
+  const float* night_weight;
 } mod16_out_t;
 
 /*

@@ -69,6 +69,8 @@ struct ForwardArgs {
   R* out[6];
   const int* group;   // MOD16_OUT_ANNUAL: group (year) of every time step; out[0] = uint64 sums
   int n_groups;
+  const float* w_day;    // MOD16_OUT_COMPOSITE: float[T] weights of the day / night totals
+  const float* w_night;
   int* gate_flag;
   unsigned long long* redo_ws;  // [0] = count, [1 ..] = queued linear indices t * N + n
   long long redo_cap;           // entries the queue can hold (0: no queue)

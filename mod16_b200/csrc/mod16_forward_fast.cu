@@ -197,7 +197,8 @@ static int pipe_variant(const ForwardArgs<float>& a, uint32_t flags) {
   }
   const uint32_t om = flags & MOD16_OUT_MASK;
   const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1
-                       : (om == MOD16_OUT_ANNUAL ? 3 : (om == MOD16_OUT_POTENTIAL ? 4 : 2)));
+                       : (om == MOD16_OUT_ANNUAL ? 3 : (om == MOD16_OUT_POTENTIAL ? 4
+                       : (om == MOD16_OUT_COMPOSITE ? 5 : 2))));
   if (!pipe_has_variant(out_mode, extra)) return -1;
   return extra;
 }
@@ -238,7 +239,8 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
   dim3 grid((unsigned)bx, (unsigned)by);
   const uint32_t om = flags & MOD16_OUT_MASK;
   const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1
-                       : (om == MOD16_OUT_ANNUAL ? 3 : (om == MOD16_OUT_POTENTIAL ? 4 : 2)));
+                       : (om == MOD16_OUT_ANNUAL ? 3 : (om == MOD16_OUT_POTENTIAL ? 4
+                       : (om == MOD16_OUT_COMPOSITE ? 5 : 2))));
   const bool is_static = (flags & MOD16_SEM_MASK) == MOD16_SEM_STATIC;
   if (a.redo_cap > 0) M16_CUDA_CHECK(cudaMemsetAsync(a.redo_ws, 0, 8, st));
   if (out_mode == 3 && a.skip_if_flag) {
@@ -266,11 +268,13 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
       if (out_mode == 0) M16_REDO(SEM_STATIC, 0);
       else if (out_mode == 1) M16_REDO(SEM_STATIC, 1);
       else if (out_mode == 4) M16_REDO(SEM_STATIC, 4);
+      else if (out_mode == 5) M16_REDO(SEM_STATIC, 5);
       else M16_REDO(SEM_STATIC, 2);
     } else {
       if (out_mode == 0) M16_REDO(SEM_INSTANCE, 0);
       else if (out_mode == 1) M16_REDO(SEM_INSTANCE, 1);
       else if (out_mode == 4) M16_REDO(SEM_INSTANCE, 4);
+      else if (out_mode == 5) M16_REDO(SEM_INSTANCE, 5);
       else M16_REDO(SEM_INSTANCE, 2);
     }
 #undef M16_REDO
@@ -299,7 +303,8 @@ int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
   }
   // (no strided kernel for storage formats, nor for the annual sums)
   if (a.raw_fmt != 0 || (flags & MOD16_OUT_MASK) == MOD16_OUT_ANNUAL ||
-      (flags & MOD16_OUT_MASK) == MOD16_OUT_POTENTIAL)
+      (flags & MOD16_OUT_MASK) == MOD16_OUT_POTENTIAL ||
+      (flags & MOD16_OUT_MASK) == MOD16_OUT_COMPOSITE)
     return MOD16_ERR_LAYOUT;
   g_last_forward_kernel = MOD16_KERNEL_STRIDED;
   const int threads = 256;

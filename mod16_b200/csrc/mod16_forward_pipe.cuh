@@ -207,7 +207,7 @@ __device__ __forceinline__ int pipe_rule(const ForwardArgs<float>& a, int ts, fl
   c.vpd_off = vpd_off; c.inv_dvpd = inv_dvpd;
   bool g_pos;
   const int h = fast::nan_halves<SEM>(in, c, a.has_rc != 0, g_pos);
-  if (OUT == 2 || OUT == 4 || !((OUT == 0 || OUT == 3) ? h != 0 : h == 3)) return -1;
+  if (OUT == 2 || OUT == 4 || !((OUT == 0 || OUT == 3 || OUT == 5) ? h != 0 : h == 3)) return -1;
   if (OUT == 3) {
     annual_add(a, t, n, kAnnualNaN);
     return g_pos ? 1 : 0;
@@ -338,7 +338,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   int acc_g = -1;
   const float swn_scalar = a.drv[MOD16_D_SW_RAD_NIGHT].scalar;
   const int gate = a.gate;
-  constexpr int n_out = OUT == 3 ? 0 : (OUT == 0 ? 1 : (OUT == 1 ? 2 : 6));
+  constexpr int n_out = OUT == 3 ? 0 : ((OUT == 0 || OUT == 5) ? 1 : (OUT == 1 ? 2 : 6));
   constexpr bool RULE = OUT != 2 && OUT != 4;   // outputs a NaN total decides without the double code
   // this thread's pixel in a row (float32 rows; storage formats index per array)
   const uint32_t my0 = keep_u32(FMT < FMT_MODIS ? data0 + (uint32_t)tid * 4u : data0);
@@ -443,6 +443,12 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       q_y = __float2ull_rn(fminf(mm.y, 1.0e16f));
       g_x = __ldg(a.group + (int64_t)blockIdx.y * a.t_chunk + i * PIPE_SUB);
       g_y = TWO ? __ldg(a.group + (int64_t)blockIdx.y * a.t_chunk + i * PIPE_SUB + 1) : g_x;
+    } else if (OUT == 5) {   // day-length weighted composite (verify2.py:112-115)
+      const float* wd = a.w_day + (int64_t)blockIdx.y * a.t_chunk + i * PIPE_SUB;
+      const float* wn = a.w_night + (int64_t)blockIdx.y * a.t_chunk + i * PIPE_SUB;
+      const F2 w_d = F2{__ldg(wd), TWO ? __ldg(wd + 1) : 0.0f};
+      const F2 w_n = F2{__ldg(wn), TWO ? __ldg(wn + 1) : 0.0f};
+      res[0] = fast::vfma(r.tot_day, w_d, r.tot_night * w_n);
     } else if (OUT == 4) {
       res[0] = r.tot;       res[1] = r.day.pt;
       res[2] = r.day.sat;   res[3] = r.day.unsat;
@@ -558,14 +564,14 @@ int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mod
   M16_PIPE(0, 0, 1); M16_PIPE(0, 0, 2); M16_PIPE(0, 0, 3);
   M16_PIPE(1, 0, 1); M16_PIPE(1, 0, 2); M16_PIPE(1, 0, 3);
   if constexpr (SEM == SEM_STATIC) { M16_PIPE(3, 0, 0); }
-  M16_PIPE(4, 0, 0);
+  M16_PIPE(4, 0, 0); M16_PIPE(5, 0, 0);
 #undef M16_PIPE
   return MOD16_ERR_FLAGS;
 }
 
 inline bool pipe_has_variant(int out_mode, int extra, int fmt = 0) {
   // annual sums, potential terms: the plain tile layout
-  if (out_mode == 3 || out_mode == 4) return extra == 0 && fmt == 0;
+  if (out_mode >= 3) return extra == 0 && fmt == 0;
   return fmt == 0 ? (out_mode < 2 || extra < 2) : (out_mode < 2 && extra == 0);
 }
 

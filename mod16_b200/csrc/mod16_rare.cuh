@@ -132,6 +132,9 @@ __device__ __forceinline__ void store_exact(const ForwardArgs<float>& a, int64_t
   if (OUT == 3) {
     const float tcm = 0.5f * (fast::celsius<float>(in.t_d) + fast::celsius<float>(in.t_n));
     annual_add(a, o / a.N, o % a.N, annual_fixed(r.tot, tcm));
+  } else if (OUT == 5) {
+    const int64_t t = o / a.N;
+    a.out[0][o] = fmaf(r.tot_day, __ldg(a.w_day + t), r.tot_night * __ldg(a.w_night + t));
   } else if (OUT == 4) {
     a.out[0][o] = r.tot;        a.out[1][o] = r.day.pt;
     a.out[2][o] = r.day.sat;    a.out[3][o] = r.day.unsat;

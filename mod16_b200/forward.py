@@ -230,7 +230,7 @@ def _view_2d(shape):
 def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static',
                 out_mode='sum', gate='global', dtype=None, r_corr_list=None, device=None,
                 stream=None, force=0, as_torch=None, gate_flag=None, out=None,
-                workspace=None, prep=None, groups=None, n_groups=None):
+                workspace=None, prep=None, groups=None, n_groups=None, weights=None):
     '''
     Launches K1 once.
 
@@ -247,6 +247,9 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
                [W m-2] -- total, potential transpiration (day, :547-602), evaporation of
                the saturated / potential evaporation of the unsaturated soil fraction
                (day), the same two at night (:450-545) -- from the same pass)
+               | 'composite' (float32, (T, N) drivers: ``day * weights[0][t] + night *
+               weights[1][t]``, the day-length weighted composite of verify2.py:112-115;
+               ``weights`` = two (T,) arrays)
     gate     : 'global' (reference) | 'element' | 'open' | 'closed' | 'open_track' | 'fixup'
 
     drivers may hold ``rawio.RawDriver`` objects (storage formats: uint8 / int16 with scale,
@@ -303,8 +306,10 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
             return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
                                   semantics, out_mode, gate, r_corr_list, force, as_torch,
                                   gate_flag, out, workspace, full_shape, T, N, caller_stream,
-                                  prep if raw else None)
+                                  prep if raw else None, weights=weights)
         except _abi.LayoutError:
+            if out_mode in ('potential', 'composite'):
+                raise
             # a storage-format layout the fused kernel cannot stream: same arithmetic as
             # torch operations on the device first, then the plain float32 entry
             drivers = _plain_drivers(drivers, prep, dev, np_dtype)
@@ -364,7 +369,7 @@ def _plain_drivers(drivers, prep, dev, np_dtype):
 
 def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, semantics,
                    out_mode, gate, r_corr_list, force, as_torch, gate_flag, out, workspace,
-                   full_shape, T, N, caller_stream, prep=None, groups=None):
+                   full_shape, T, N, caller_stream, prep=None, groups=None, weights=None):
     'Body of run_forward; the current stream is `s`.  `prep` not None: the storage-format entry.'
     params = plist if plist else None
     st = _Staged(dev, np_dtype)
@@ -434,11 +439,12 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
         for j in range(_abi.N_PFT):
             cp.table[i][j] = tab[i, j]
 
-    n_out = {'sum': 1, 'day_night': 2, 'components': 6, 'annual': 1, 'potential': 6}[out_mode]
+    n_out = {'sum': 1, 'day_night': 2, 'components': 6, 'annual': 1, 'potential': 6,
+             'composite': 1}[out_mode]
     flags = {'static': _abi.SEM_STATIC, 'instance': _abi.SEM_INSTANCE}[semantics]
     flags |= {'sum': _abi.OUT_SUM, 'day_night': _abi.OUT_DAY_NIGHT,
               'components': _abi.OUT_COMPONENTS, 'annual': _abi.OUT_ANNUAL,
-              'potential': _abi.OUT_POTENTIAL}[out_mode]
+              'potential': _abi.OUT_POTENTIAL, 'composite': _abi.OUT_COMPOSITE}[out_mode]
     flags |= _abi.GATE_FLAGS[gate] | force
     if out_mode == 'annual':
         outs = list(out)                    # (n_groups, N) int64 accumulators, zeroed
@@ -456,6 +462,15 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
     if groups is not None:
         co.group, co.n_groups = groups[0].data_ptr(), groups[1]
         st.keep.append(groups[0])
+    if out_mode == 'composite':
+        if weights is None or len(weights) != 2:
+            raise TypeError('out_mode="composite" needs weights=(day_seconds, night_seconds)')
+        wt = [st.tensor(np.asarray(w.cpu() if isinstance(w, torch.Tensor) else w, np.float32),
+                        torch.float32).reshape(-1).contiguous() for w in weights]
+        if any(w.numel() != T for w in wt):
+            raise ValueError('composite weights must hold one value per time step')
+        st.keep.extend(wt)
+        co.day_weight, co.night_weight = wt[0].data_ptr(), wt[1].data_ptr()
     for k, o in enumerate(outs):
         co.out[k] = o.data_ptr()
     if gate_flag is None:

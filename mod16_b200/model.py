@@ -120,6 +120,21 @@ class MOD16(ComponentMixin):
         return run_forward(drivers, params=params, semantics='static', out_mode='annual',
                            groups=idx.astype(np.int32), n_groups=len(labels), **kw)[0]
 
+    def evapotranspiration_composite(self, updown, *drivers, days=8, **kw):
+        '''
+        The day-length weighted composite the verification scripts form from
+        ``evapotranspiration()`` (reference tests/verification/verify2.py:100-115):
+        ``pred_day * updown * days * 3600 + pred_night * (24 - updown) * days * 3600``
+        [kg m-2 per composite period], with ``updown`` the (T,) day length in hours, computed
+        in the same pass as the model (the day and night rates are never written).
+        float32, (T, N) drivers.
+        '''
+        u = np.asarray(updown, np.float64).reshape(-1)
+        w = ((u * days * 3600.0).astype(np.float32),
+             ((24.0 - u) * days * 3600.0).astype(np.float32))
+        return run_forward(drivers, params=self._vector(), semantics='instance',
+                           out_mode='composite', weights=w, **kw)[0]
+
     # -- instance interface ----------------------------------------------------------------
     def _vector(self):
         return [getattr(self, k) for k in self.required_parameters]

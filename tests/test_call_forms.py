@@ -280,3 +280,27 @@ def test_potential_terms_from_the_same_pass(cuda_lib, semantics):
         parity.assert_parity(got[name][ok], want[ok], np.float32, what=name)
         parity.assert_parity(got[name][~ok], want[~ok], np.float32, what=name + ' (queued)')
     assert np.isnan(got['et'][~ok]).all() == (semantics == 'static')
+
+
+def test_day_length_composite_from_the_same_pass(cuda_lib):
+    'MOD16_OUT_COMPOSITE against verify2.py:112-115 applied to the oracle\'s day / night rates.'
+    T, N = 23, 2400
+    d = synthetic.host_drivers(T, N, 191, dtype=np.float32)
+    rng = np.random.default_rng(192)
+    d['fpar'][rng.random((T, N)) < 0.01] = np.nan
+    drv = [d[k] for k in NAMES]
+    col = list(_table()[:, 4])
+    p = dict(zip(orc.PARAM_ORDER, col))
+    updown = rng.uniform(8.0, 16.0, T)
+    with np.errstate(all='ignore'):
+        day, night = orc.InstanceModel(p).evapotranspiration(*_d64(drv))
+        want = orc.daylength_composite(day, night, updown[:, None], days=8)
+    got = MOD16(p).evapotranspiration_composite(updown, *drv)
+    assert _kernel(cuda_lib) == (_abi.KERNEL_PIPE, 0)
+    # kg m-2 (8 days)-1: rates of ~1e-5 kg m-2 s-1 times ~3e5 s
+    parity.assert_parity(got, want, np.float32, parity.MASS_SCALE * 8 * 86400,
+                         what='8-day composite')
+    assert 0.005 < np.isnan(got).mean() < 0.02
+    with pytest.raises(_abi.LayoutError):       # (ragged N: no strided kernel for this mode)
+        MOD16(p).evapotranspiration_composite(updown, *[v[..., :1001] if isinstance(
+            v, np.ndarray) else v for v in drv])
