@@ -643,18 +643,11 @@ def end_to_end(args, device, world, rank, numa, drv, pft, table, T, N, np_dtype,
     from mod16_b200.streaming import StreamedForward
     names = [k for k in synthetic.DRIVER_NAMES
              if k not in synthetic.PER_PIXEL and k != 'sw_rad_night']
-    Te = min(args.e2e_T, T)
-    try:  # as many time steps as a third of the free host memory holds pinned
+    try:  # a third of the free host memory may be pinned at a time
         import psutil
         room = psutil.virtual_memory().available / 3.0 / max(world, 1)
-        Te = max(4, min(Te, int(room // (12 * N * np_dtype.itemsize))))
     except Exception:
-        Te = min(Te, 16)
-    tq = torch.tensor([Te], device=device, dtype=torch.int64)
-    if world > 1:
-        dist.all_reduce(tq, op=dist.ReduceOp.MIN)
-    Te = int(tq.item())
-    slab = max(1, min(8, Te // 4))
+        room = 16 * 12 * N * np_dtype.itemsize
     per_pixel = dict((k, drv[k].cpu().pin_memory()) for k in synthetic.PER_PIXEL)
     legs = {}
     layouts = ['float32'] + (['modis', 'packed'] if np_dtype == np.float32 else [])
@@ -664,6 +657,16 @@ def end_to_end(args, device, world, rank, numa, drv, pft, table, T, N, np_dtype,
             fmt.update(MODIS_NATIVE)
         if layout == 'packed':
             fmt.update(dict((k, (np.int16,) + v) for k, v in PACKED_MET.items()))
+        # as many time steps of the resident block as fit the pinned budget in this format
+        # (inputs + the float output): the whole year where the host has the memory
+        step_bytes = N * (sum(np.dtype(fmt[k][0]).itemsize if k in fmt else np_dtype.itemsize
+                              for k in names) + np_dtype.itemsize)
+        Te = max(4, min(args.e2e_T, T, int(room // step_bytes)))
+        tq = torch.tensor([Te], device=device, dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(tq, op=dist.ReduceOp.MIN)
+        Te = int(tq.item())
+        slab = max(1, min(8, Te // 4))
         host = dict(per_pixel)
         host['sw_rad_night'] = 0
         for k in names:
@@ -695,6 +698,7 @@ def end_to_end(args, device, world, rank, numa, drv, pft, table, T, N, np_dtype,
         ok = bool(np.isfinite(out_host[:1, :4096].numpy()).all())
         assert ok, 'implausible ET from the end-to-end leg'
         legs[layout] = {'value': world * reps * Te * N / dt, 'unit': 'pixel-timesteps/s',
+                        'steps_of_the_block': Te,
                         'h2d_bytes_per_step': runner.h2d_bytes // reps,
                         'd2h_bytes_per_step': runner.d2h_bytes // reps,
                         'h2d_bytes_per_unit': runner.h2d_bytes / reps / (Te * N)}
@@ -711,7 +715,7 @@ def end_to_end(args, device, world, rank, numa, drv, pft, table, T, N, np_dtype,
     e2e['sample'] = ('%d of the %d steps x %d pixels per GPU from pinned host memory through '
                      'mod16_b200.streaming.StreamedForward (slabs of %d steps, copies '
                      'overlapped with the kernel)%s' % (
-                         Te, T, N, slab,
+                         legs[head]['steps_of_the_block'], T, N, slab,
                          '' if numa is None else '; rank bound to NUMA node %d' % numa))
     return e2e
 
