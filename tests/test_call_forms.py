@@ -304,3 +304,39 @@ def test_day_length_composite_from_the_same_pass(cuda_lib):
     with pytest.raises(_abi.LayoutError):       # (ragged N: no strided kernel for this mode)
         MOD16(p).evapotranspiration_composite(updown, *[v[..., :1001] if isinstance(
             v, np.ndarray) else v for v in drv])
+
+
+@pytest.mark.parametrize('out_mode', ['sum', 'day_night', 'components'])
+def test_without_a_workspace_the_block_queues_and_its_own_sweep_take_over(cuda_lib, out_mode):
+    '''
+    The C ABI allows `workspace = NULL`: deferred elements then go to a 512-entry queue per
+    block, evaluated by the block after its loop; when that overflows, markers in the output
+    are found again by the block's own sweep.  10 % finite garbage (values the double code
+    must evaluate as the reference does) overflows every block's queue.
+    '''
+    dev = torch.device('cuda', 0)
+    T, N = 64, 4800
+    d = synthetic.host_drivers(T, N, 201, dtype=np.float32)
+    rng = np.random.default_rng(202)
+    bad = rng.random((T, N)) < 0.10
+    d['lai'][bad] = -9999.0            # finite fill: garbage in, the same garbage out
+    d['fpar'][rng.random((T, N)) < 0.02] = 2.55
+    drv = [d[k] for k in NAMES]
+    col = list(_table()[:, 7])
+    with np.errstate(all='ignore'):
+        if out_mode == 'components':
+            want = [c for half in orc.static_evapotranspiration(col, *_d64(drv), components=True)
+                    for c in half]
+        else:
+            day, night = orc.static_evapotranspiration(col, *_d64(drv))
+            want = [day + night] if out_mode == 'sum' else [day, night]
+    empty = torch.empty(0, dtype=torch.int64, device=dev)
+    got = run_forward(drv, params=col, out_mode=out_mode, dtype=np.float32, workspace=empty)
+    assert _kernel(cuda_lib)[0] == _abi.KERNEL_PIPE
+    for g, w in zip(got, want):
+        parity.assert_parity(g, w, np.float32, what='no workspace, ' + out_mode)
+    # and a tiny workspace (queue of 15 entries): the marker sweep kernel
+    tiny = torch.empty(16, dtype=torch.int64, device=dev)
+    got = run_forward(drv, params=col, out_mode=out_mode, dtype=np.float32, workspace=tiny)
+    for g, w in zip(got, want):
+        parity.assert_parity(g, w, np.float32, what='tiny workspace, ' + out_mode)
