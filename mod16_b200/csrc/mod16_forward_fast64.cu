@@ -41,6 +41,31 @@ __device__ __noinline__ bool exact64_one(const ForwardArgs<double>& a, const Dri
   return g_pos;
 }
 
+// The masked-driver rule (fast::nan_halves, see mod16_fast.cuh) for ONE element of the float64
+// entry: a NaN (or negative-temperature) driver that makes the total NaN whatever else the
+// element holds is answered without the op-for-op code -- masked pixels of a real tile are
+// masked at every step.  Returns true when the outputs were written (NaN totals).
+template <int SEM, int OUT>
+__device__ __noinline__ bool rule64_one(const ForwardArgs<double>& a, const Drivers<double>& d,
+                                        const Params<double>& q, int64_t o, bool& g_pos) {
+  if (OUT == 2) return false;
+  fast::StepIn f;
+  f.lw_d = (float)d.lw_d; f.lw_n = (float)d.lw_n; f.sw_d = (float)d.sw_d; f.sw_n = (float)d.sw_n;
+  f.alb = (float)d.alb; f.t_d = (float)d.t_d; f.t_n = (float)d.t_n; f.t_ann = 0.0f;
+  f.tmin = (float)d.tmin; f.vpd_d = (float)d.vpd_d; f.vpd_n = (float)d.vpd_n; f.p = (float)d.p;
+  f.fpar = (float)d.fpar; f.lai = (float)d.lai; f.rc_d = 0.0f; f.rc_n = 0.0f;
+  const double col[MOD16_N_PARAMS] = {q.tmin_close, q.tmin_open, q.vpd_open, q.vpd_close,
+                                      q.gl_sh,      q.gl_wv,     q.g_cuticular, q.csl,
+                                      q.rbl_min,    q.rbl_max,   q.beta};
+  const fast::PftConst pc = fast::make_pft_const(col, SEM);
+  const int h = fast::nan_halves<SEM>(f, pc, a.has_rc != 0, g_pos);
+  if (!(OUT == 0 ? h != 0 : h == 3)) return false;
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  a.out[0][o] = qnan;
+  if (OUT == 1) a.out[1][o] = qnan;
+  return true;
+}
+
 template <int SEM, int OUT>
 __global__ void __launch_bounds__(128)
 forward_fast64_kernel(const __grid_constant__ ForwardArgs<double> a) {
@@ -94,7 +119,9 @@ forward_fast64_kernel(const __grid_constant__ ForwardArgs<double> a) {
                                : fast::step_fast<double, SEM, false>(in, pc, px, a.gate, r, g_pos);
       const int64_t o = t * a.N + n;
       if (need) {
-        any_pos |= exact64_one<SEM, OUT>(a, d, q, o);
+        bool gp = false;
+        if (rule64_one<SEM, OUT>(a, d, q, o, gp)) any_pos |= gp;
+        else any_pos |= exact64_one<SEM, OUT>(a, d, q, o);
       } else {
         any_pos |= g_pos;
         store64<OUT>(a, o, r.day.canopy, r.day.soil, r.day.trans, r.night.canopy, r.night.soil,

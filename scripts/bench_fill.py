@@ -8,9 +8,10 @@ from mod16_b200 import MOD16, synthetic, utils
 from mod16_b200.forward import run_forward
 frac = float(sys.argv[1]) if len(sys.argv) > 1 else 0.3
 mode = sys.argv[2] if len(sys.argv) > 2 else 'masked'   # masked | negvpd | negvpd2 | filltemp | fill
-T, N = 64, 2400 * 2400
+dtype = np.float64 if (len(sys.argv) > 3 and sys.argv[3] == 'f64') else np.float32
+T, N = (16 if dtype == np.float64 else 64), 2400 * 2400
 dev = torch.device('cuda', 0)
-d = synthetic.device_drivers(T, N, 1, dev)
+d = synthetic.device_drivers(T, N, 1, dev, dtype=torch.float64 if dtype == np.float64 else torch.float32)
 if mode == 'masked':       # whole pixels masked (NaN fPAR / LAI at every step)
     mask = torch.rand(N, device=dev) < frac
     for k in ('fpar', 'lai'):
@@ -31,10 +32,10 @@ else:                      # unmasked fill values on whole pixels: double code, 
 table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51), MOD16.required_parameters, default_beta=250.0)
 pft = torch.from_numpy(synthetic.host_pft_map(N, 2)).to(dev)
 drv = [d[k] for k in synthetic.DRIVER_NAMES]
-out = torch.empty((T, N), device=dev)
+out = torch.empty((T, N), device=dev, dtype=torch.float64 if dtype == np.float64 else torch.float32)
 flag = torch.zeros(1, device=dev, dtype=torch.int32)
 f = lambda: run_forward(drv, pft=pft, table=table, semantics='static', out_mode='sum', gate='global',
-                        dtype=np.float32, device=dev, gate_flag=flag, out=[out])
+                        dtype=dtype, device=dev, gate_flag=flag, out=[out])
 for _ in range(2): f()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
