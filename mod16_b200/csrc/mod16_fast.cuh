@@ -338,6 +338,22 @@ template <class V> M16_HD V celsius(V t) {
 
 template <> M16_HD double celsius<double>(double t) { return t - 273.15; }   // (:216 ...)
 
+// The hot path subtracts the float 273.15f only: its Celsius temperature is kTcBias too high,
+// and every constant next to it absorbs the bias exactly (tc enters through fused
+// multiply-adds and one sum only), which saves the second subtraction of celsius().
+constexpr double kTcBias = 273.15 - (double)273.15f;
+template <class K> M16_HD double tc_bias();
+template <> M16_HD double tc_bias<float>() { return kTcBias; }
+template <> M16_HD double tc_bias<double>() { return 0.0; }
+template <class V> M16_HD V celsius_b(V t) { return t - 273.15f; }
+template <> M16_HD double celsius_b<double>(double t) { return t - 273.15; }
+
+// 2^-x next to e = 2^x: a second ex2 on the special-function unit (independent of the first:
+// no added latency), or the reciprocal of e in double (a libdevice exp2 costs four of those)
+M16_HD float vex2_neg(float x, float e) { (void)e; return vex2(-x); }
+M16_HD F2 vex2_neg(F2 x, F2 e) { (void)e; return vex2(-x); }
+M16_HD double vex2_neg(double x, double e) { (void)x; return d_rcp(e); }
+
 // q^-1.75 (:292): lg2 / ex2 on the special-function unit, or two square roots in double
 M16_HD float vpow_m175(float q) { return vex2(-1.75f * vlg2(q)); }
 M16_HD F2 vpow_m175(F2 q) { return vex2(-1.75f * vlg2(q)); }
@@ -405,9 +421,12 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
   typedef typename MaskOf<V>::type M;
   typedef typename ScalarOf<V>::type K;
   // saturation vapour pressure 610.8 exp(17.27 Tc / (Tc + 237.3)) and its reciprocal (:1365)
-  const V xe = (K(17.27 * 1.4426950408889634) * tc) * vrcp(tc + K(237.3));
+  // (tc carries tc_bias<K>(), see celsius_b)
+  const double tb = tc_bias<K>();
+  const V xe = vfma(tc, K(17.27 * 1.4426950408889634), K(-17.27 * 1.4426950408889634 * tb)) *
+               vrcp(tc + K(237.3 - tb));
   const V e = vex2(xe);                             // SVP / 610.8
-  const V ies = K(1.0 / 610.8) * vex2(-xe);   // 1 / SVP
+  const V ies = K(1.0 / 610.8) * vex2_neg(xe, e);   // 1 / SVP
   V rh = vfma(-vpd, ies, K(1.0));
   if (SEM == SEM_STATIC) rh = vmax(rh, splat<V>(K(0.0)));  // :280-281 (no upper clamp)
   else rh = vsat(rh);                                    // :671-673
@@ -422,14 +441,14 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
   const V omfw = K(1.0) - fw;
   // scaled slope S, psychrometric constant G and vapour-pressure term K (see kKappa)
   const V q = t * K(kKappa / kT0);
-  const V d2 = vfma(tc, K(kR), K(239.0 * kR));
+  const V d2 = vfma(tc, K(kR), K((239.0 - tb) * kR));
   const V dd = d2 * d2;
-  const V lam_n = vfma(tc, K(-2361.0 / kLam0), K(2.501e6 / kLam0));    // :121
+  const V lam_n = vfma(tc, K(-2361.0 / kLam0), K((2.501e6 + 2361.0 * tb) / kLam0));    // :121
   const V S = (e * lam_n) * q;                                                       // :1397
   const V G = (x.gp * q) * dd;                                                       // :1289
   const V Kv = (lam_n * dd) * vpd;
   // X = rho T (:409-412); B = X / r_r = 4 sigma T^4 / Cp (:298-299)
-  const V X = vfma(rh, vfma(tc, K(-0.252), K(2.0582)), x.pa);
+  const V X = vfma(rh, vfma(tc, K(-0.252), K(2.0582 + 0.252 * tb)), x.pa);
   const V q2 = q * q;
   const V B = q2 * q2;
   // 1 / r_corr = (P / 101300) (T / 293.15)^-1.75 (:292), or the supplied r_corr_list entry
@@ -604,8 +623,9 @@ M16_HD typename MaskOf<V>::type step_core(const StepInV<V>& in, V tc_d, V tc_n,
   const V a_nc = vfma(in.sw_n, oma, in.lw_n);            // :272 (night: sw_rad_night)
   // soil heat flux (:229-241)
   const V cond = vstep_ge_and(in.t_d - in.t_n, K(5.0), x.window);  // 1 inside the window, else 0
-  V g_d = cond * vfma(tc_d, K(4.73), K(-20.87));
-  V g_n = cond * vfma(tc_n, K(4.73), K(-20.87));
+  const double tb = tc_bias<K>();    // (tc_d, tc_n carry it, see celsius_b)
+  V g_d = cond * vfma(tc_d, K(4.73), K(-20.87 - 4.73 * tb));
+  V g_n = cond * vfma(tc_n, K(4.73), K(-20.87 - 4.73 * tb));
   const V lim_d = K(0.39) * a_d, lim_n = K(0.39) * a_n;
   // |G| > 0.39 |A| switches G to 0.39 A (:239); within kGuard of equality the decision is
   // the double code's.  A_day > 0 gates both limits below (:245-252).
@@ -646,7 +666,7 @@ M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<
                                           const PixConstV<V>& x, int gate, StepOutV<V>& o,
                                           typename MaskOf<V>::type& g_pos, V& gs_day,
                                           V& nan_probe) {
-  const V tc_d = celsius<V>(in.t_d), tc_n = celsius<V>(in.t_n);
+  const V tc_d = celsius_b<V>(in.t_d), tc_n = celsius_b<V>(in.t_n);
   const typename MaskOf<V>::type bad = mnot(mand(x.ok, in_domain<V>(in, tc_d, tc_n, nan_probe)));
   return mor(bad, step_core<V, SEM, HAS_RC>(in, tc_d, tc_n, c, x, gate, o, g_pos, gs_day));
 }

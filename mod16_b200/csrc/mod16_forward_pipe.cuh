@@ -396,7 +396,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     uint32_t flags = TWO ? flags0 : (flags0 | DONE_Y);
 
     // -- the domain of the fast formulas, tested while every input is still in a register
-    const F2 tc_d = fast::celsius<F2>(in.t_d), tc_n = fast::celsius<F2>(in.t_n);
+    const F2 tc_d = fast::celsius_b<F2>(in.t_d), tc_n = fast::celsius_b<F2>(in.t_n);
     F2 nan_probe;
     const M2 dom = fast::mand(px.ok, fast::in_domain<F2>(in, tc_d, tc_n, nan_probe));
     if (!(dom.x && dom.y)) {  // rare
@@ -437,7 +437,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     int g_x = -1, g_y = -1;
     if (OUT == 3) {
       const F2 tcm = 0.5f * (tc_d + tc_n);
-      const F2 lam = fast::vfma(tcm, -2361.0f, 2.501e6f);                      // :121
+      const F2 lam = fast::vfma(tcm, -2361.0f, (float)(2.501e6 + 2361.0 * fast::kTcBias));  // :121
       const F2 mm = (fast::vmax(r.tot, 0.0f) * (86400.0f * 4294967296.0f)) * fast::vrcp(lam);
       q_x = __float2ull_rn(fminf(mm.x, 1.0e16f));
       q_y = __float2ull_rn(fminf(mm.y, 1.0e16f));
