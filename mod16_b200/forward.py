@@ -299,16 +299,24 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
                                    '(T, N) drivers')
     with torch.cuda.device(dev), launch_stream(dev, stream) as (s, caller_stream):
         if out_mode == 'annual':
-            return _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate, as_torch,
-                               full_shape, T, N, caller_stream, prep if raw else None, groups,
-                               n_groups)
+            try:
+                return _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate,
+                                   as_torch, full_shape, T, N, caller_stream,
+                                   prep if raw else None, groups, n_groups)
+            except _abi.LayoutError:
+                if not raw:
+                    raise
+                drivers = _plain_drivers(drivers, prep, dev, np_dtype)
+                return _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate,
+                                   as_torch, full_shape, T, N, caller_stream, None, groups,
+                                   n_groups)
         try:
             return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
                                   semantics, out_mode, gate, r_corr_list, force, as_torch,
                                   gate_flag, out, workspace, full_shape, T, N, caller_stream,
                                   prep if raw else None, weights=weights)
         except _abi.LayoutError:
-            if out_mode in ('potential', 'composite'):
+            if not raw:          # plain float32 drivers: the mode itself needs a streamable layout
                 raise
             # a storage-format layout the fused kernel cannot stream: same arithmetic as
             # torch operations on the device first, then the plain float32 entry
@@ -316,7 +324,7 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
             return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
                                   semantics, out_mode, gate, r_corr_list, force, as_torch,
                                   gate_flag, out, workspace, full_shape, T, N, caller_stream,
-                                  None)
+                                  None, weights=weights)
 
 
 def _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate, as_torch, full_shape,

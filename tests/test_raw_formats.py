@@ -192,3 +192,26 @@ def test_streamed_forward_with_stored_slabs(cuda_lib):
     vec = [table[i][pft].reshape(1, N) for i in range(11)]
     (rd, rn), _ = _reference(stored, (), vec, gate='open')
     parity.assert_parity(out_host.numpy(), rd + rn, np.float32, what='streamed stored slabs')
+
+
+@pytest.mark.gpu
+def test_stored_drivers_with_the_other_output_modes(cuda_lib):
+    'Annual sums and potential terms from stored drivers: converted on the device, then fused.'
+    T, N = 20, 2400
+    rng = np.random.default_rng(12)
+    d = synthetic.host_drivers(T, N, 97, dtype=np.float32)
+    stored = _stored(d, 'modis', rng, fills=False)
+    drv = [stored[k] for k in NAMES]
+    col = list(_table()[:, 7])
+    (rd, rn), phys = _reference(stored, (), col)
+    years = np.repeat([0, 1], T // 2)
+    with np.errstate(all='ignore'):
+        want = orc.annual_mass_sums(rd + rn, years, orc.lhv(0.5 * (phys[5] + phys[6])))
+    got = MOD16._annual_et(col, years, *drv)
+    assert np.all(np.abs(got - want) <= 1e-5 * np.maximum(np.abs(want), 1.0))
+    pot = MOD16._et_potential(col, *drv)
+    parity.assert_parity(pot['et'], rd + rn, np.float32, what='total from stored drivers')
+    with np.errstate(all='ignore'):
+        pt = orc.InstanceModel.potential_transpiration(phys[0], phys[2], phys[4], phys[11], phys[5],
+                                                       phys[9], phys[12])
+    parity.assert_parity(pot['potential_transpiration'], pt, np.float32, what='PT')
