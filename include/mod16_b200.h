@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 9
+#define MOD16_ABI_VERSION 10
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -203,6 +203,12 @@ typedef struct mod16_out {
 #define MOD16_T_U8 2
 #define MOD16_PREP_VPD_NIGHT_CLAMP 0x1u /* vpd_night < 0 -> 0 (a NaN stays NaN) */
 #define MOD16_PREP_ELEVATION 0x2u       /* drv[MOD16_D_PRESSURE] holds elevation in metres */
+#define MOD16_PREP_VPD_FROM_QV 0x4u     /* drv[MOD16_D_VPD_DAY / _NIGHT] hold the 10 m water
+                                           vapour mixing ratio QV10M, `ps` the surface
+                                           pressure: VPD = MOD16.vpd(qv10m, ps, temp)
+                                           = 610.7 exp(17.38 Tc / (239 + Tc)) - qv ps /
+                                           (0.622 + 0.379 qv) (mod16/__init__.py:605-644,
+                                           mod16/calibration.py:393-400); float32 arrays */
 
 typedef struct mod16_raw_driver {
   const void* ptr;   /* device array of `dtype`, or NULL: use `scalar` (a physical value) */
@@ -219,6 +225,7 @@ typedef struct mod16_raw_drivers {
   mod16_raw_driver_t drv[MOD16_N_DRIVERS];
   uint32_t prep;     /* MOD16_PREP_* */
   uint32_t reserved;
+  mod16_raw_driver_t ps[2]; /* MOD16_PREP_VPD_FROM_QV: surface pressure, day and night */
 } mod16_raw_drivers_t;
 
 int mod16_abi_version(void);

@@ -19,13 +19,13 @@ GATE_OPEN_TRACK, GATE_FIXUP = 0x400, 0x500
 FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
 KERNEL_PIPE, KERNEL_STRIDED, KERNEL_EXACT, KERNEL_FAST64 = 1, 2, 3, 4  # last_forward_kernel & 0xff
 T_F32, T_I16, T_U8 = 0, 1, 2                            # mod16_raw_driver_t.dtype
-PREP_VPD_NIGHT_CLAMP, PREP_ELEVATION = 0x1, 0x2
+PREP_VPD_NIGHT_CLAMP, PREP_ELEVATION, PREP_VPD_FROM_QV = 0x1, 0x2, 0x4
 ERR_LAYOUT = -7
 ANNUAL_OVERFLOW = 0x40000000
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                         'libmod16_b200.so')
 
@@ -50,7 +50,7 @@ class RawDriver(ctypes.Structure):
 
 class RawDrivers(ctypes.Structure):
     _fields_ = [('drv', RawDriver * N_DRIVERS), ('prep', ctypes.c_uint32),
-                ('reserved', ctypes.c_uint32)]
+                ('reserved', ctypes.c_uint32), ('ps', RawDriver * 2)]
 
 
 class Params(ctypes.Structure):

@@ -57,6 +57,7 @@ struct ForwardArgs {
   RawInfo raw[MOD16_N_DRIVERS];
   int raw_fmt;       // 0: every driver float (the plain entries); else see mod16_forward_pipe.cuh
   uint32_t prep;     // MOD16_PREP_*
+  Arr<R> ps[2];      // MOD16_PREP_VPD_FROM_QV: surface pressure, day / night
   Arr<R> rc[2];
   int has_rc;
   // parameters

@@ -137,6 +137,7 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
   a.t_chunk = 1;
   a.raw_fmt = 0;
   a.prep = 0;
+  for (int k = 0; k < 2; ++k) { a.ps[k].ptr = nullptr; a.ps[k].ts = a.ps[k].ns = 0; a.ps[k].scalar = R(0); }
   for (int k = 0; k < MOD16_N_DRIVERS; ++k) {
     a.raw[k].dtype = MOD16_T_F32; a.raw[k].has_fill = 0;
     a.raw[k].scale = 1.0f; a.raw[k].offset = 0.0f; a.raw[k].fill = 0;
@@ -318,7 +319,18 @@ int mod16_forward_raw_f32(const mod16_raw_drivers_t* drivers, const mod16_params
     }
   }
   a.prep = drivers->prep;
-  if (a.prep & ~(MOD16_PREP_VPD_NIGHT_CLAMP | MOD16_PREP_ELEVATION)) return MOD16_ERR_FLAGS;
+  if (a.prep & ~(MOD16_PREP_VPD_NIGHT_CLAMP | MOD16_PREP_ELEVATION | MOD16_PREP_VPD_FROM_QV))
+    return MOD16_ERR_FLAGS;
+  if (a.prep & MOD16_PREP_VPD_FROM_QV) {
+    if (any_int) return MOD16_ERR_LAYOUT;   // (float32 arrays only)
+    for (int k = 0; k < 2; ++k) {
+      const mod16_raw_driver_t& r = drivers->ps[k];
+      if (r.dtype != MOD16_T_F32 || r.t_stride < 0 || r.n_stride < 0) return MOD16_ERR_LAYOUT;
+      mod16_driver_t d;
+      d.ptr = r.ptr; d.t_stride = r.t_stride; d.n_stride = r.n_stride; d.scalar = r.scalar;
+      mod16::fill_arr<float>(a.ps[k], d);
+    }
+  }
   a.raw_fmt = !any_int ? mod16::FMT_F32_PREP : (met_int ? mod16::FMT_PACKED : mod16::FMT_MODIS);
   cudaStream_t st = (cudaStream_t)stream;
   return mod16::run_with_gate<float>(a, flags, st, [&](mod16::ForwardArgs<float>& x) {

@@ -172,6 +172,12 @@ static int pipe_variant(const ForwardArgs<float>& a, uint32_t flags) {
     }
     const uint32_t om = flags & MOD16_OUT_MASK;
     if (om != MOD16_OUT_SUM && om != MOD16_OUT_DAY_NIGHT) return -1;
+    if (a.prep & MOD16_PREP_VPD_FROM_QV) {   // + the two surface-pressure arrays
+      if (a.raw_fmt != FMT_F32_PREP || !dense_tn(a.ps[0], a.T, a.N) ||
+          !dense_tn(a.ps[1], a.T, a.N))
+        return -1;
+      return 4;
+    }
     return 0;
   }
   static const int per_step[] = {
@@ -225,6 +231,13 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
   if (extra & 2) {
     add(MOD16_D_TEMP_ANNUAL);
     add(MOD16_D_PRESSURE);
+  }
+  if (extra & 4) {
+    for (int h = 0; h < 2; ++h) {
+      src.ptr[n_arr] = (const char*)a.ps[h].ptr;
+      src.ts[n_arr] = a.ps[h].ts * 4;
+      ++n_arr;
+    }
   }
   const int64_t bx = (a.N + PIPE_TILE - 1) / PIPE_TILE;
   if (bx > 2147483647LL) return MOD16_ERR_SHAPE;

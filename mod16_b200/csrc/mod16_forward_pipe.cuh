@@ -26,6 +26,9 @@
 //   EXTRA 2: + temp_annual and pressure varying in time -- the (T x N) annual means of
 //            mod16/calibration.py:556-560; the per-pixel terms are then rebuilt per step
 //   EXTRA 3: all fourteen
+//   EXTRA 4: + surface pressure day / night; the two VPD slots hold the water vapour mixing
+//            ratio QV10M and VPD = MOD16.vpd(qv10m, ps, temp) (mod16/__init__.py:605-644) is
+//            formed on the fly -- the loaders' other way to the VPD (calibration.py:393-400)
 // Parameters come from the BPLUT (one column, or gathered by land cover) or from per-pixel
 // arrays -- the `params_dict[key][pft_map].reshape((1, N))` form of the reference's own
 // callers (notebooks/MOD16_Forward_Run_example.ipynb) --: they are time-invariant, so the
@@ -61,7 +64,7 @@ constexpr int PIPE_QCAP = 512;             // deferred exact re-evaluations per 
 constexpr uint32_t PIPE_ROWB = PIPE_TILE * sizeof(float);  // bytes per array row
 
 __host__ __device__ constexpr int pipe_n_arr(int extra) {
-  return 11 + ((extra & 1) ? 1 : 0) + ((extra & 2) ? 2 : 0);
+  return 11 + ((extra & 1) ? 1 : 0) + ((extra & 2) ? 2 : 0) + ((extra & 4) ? 2 : 0);
 }
 // Storage formats of the streamed arrays (FMT): 0 float32, no loader conversions (the plain
 // entries); 1 float32 + the `prep` conversions; 2 MODIS (sw_albedo int16, fpar / lai uint8);
@@ -237,6 +240,8 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   constexpr int NST = pipe_n_stages(EXTRA, FMT);
   constexpr bool SWN = (EXTRA & 1) != 0;   // sw_rad_night streamed
   constexpr bool PXT = (EXTRA & 2) != 0;   // temp_annual / pressure streamed
+  constexpr bool QV = (EXTRA & 4) != 0;    // VPD from QV10M and surface pressure
+  static_assert(!QV || EXTRA == 4, "VPD from QV10M: the eleven arrays + two pressures");
   constexpr uint32_t SUBB = pipe_eoff(FMT, NARR) * PIPE_TILE;   // bytes per sub-step
   constexpr uint32_t STAGEB = PIPE_SUB * SUBB;                  // bytes per stage
   // [stage][sub-step][array][PIPE_TILE]
@@ -376,6 +381,15 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
         in.vpd_n = M16_RAW(8, MOD16_D_VPD_NIGHT);  in.fpar = M16_RAW(9, MOD16_D_FPAR);
         in.lai = M16_RAW(10, MOD16_D_LAI);
 #undef M16_RAW
+      }
+      if (QV) {   // MOD16.vpd (:639-644): 610.7 exp(17.38 Tc / (239 + Tc)) - qv ps / (0.622 + 0.379 qv)
+        const F2 ps_d = M16_IN(11), ps_n = M16_IN(12);
+        const F2 td = fast::celsius<F2>(in.t_d), tn = fast::celsius<F2>(in.t_n);
+        const float k2 = (float)(17.38 * 1.4426950408889634);
+        const F2 es_d = 610.7f * fast::vex2((k2 * td) * fast::vrcp(td + 239.0f));
+        const F2 es_n = 610.7f * fast::vex2((k2 * tn) * fast::vrcp(tn + 239.0f));
+        in.vpd_d = es_d - (in.vpd_d * ps_d) * fast::vrcp(fast::vfma(in.vpd_d, 0.379f, 0.622f));
+        in.vpd_n = es_n - (in.vpd_n * ps_n) * fast::vrcp(fast::vfma(in.vpd_n, 0.379f, 0.622f));
       }
       if (FMT != FMT_F32 && clamp_vpd_n) {   // where(vpd_night < 0, 0, vpd_night): NaN stays
         in.vpd_n.x = in.vpd_n.x < 0.0f ? 0.0f : in.vpd_n.x;
@@ -563,6 +577,7 @@ int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mod
   M16_PIPE(2, 0, 0); M16_PIPE(2, 1, 0);
   M16_PIPE(0, 0, 1); M16_PIPE(0, 0, 2); M16_PIPE(0, 0, 3);
   M16_PIPE(1, 0, 1); M16_PIPE(1, 0, 2); M16_PIPE(1, 0, 3);
+  M16_PIPE(0, 4, 1); M16_PIPE(1, 4, 1);
   if constexpr (SEM == SEM_STATIC) { M16_PIPE(3, 0, 0); }
   M16_PIPE(4, 0, 0); M16_PIPE(5, 0, 0);
 #undef M16_PIPE
@@ -572,6 +587,7 @@ int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mod
 inline bool pipe_has_variant(int out_mode, int extra, int fmt = 0) {
   // annual sums, potential terms: the plain tile layout
   if (out_mode >= 3) return extra == 0 && fmt == 0;
+  if (extra == 4) return fmt == 1 && out_mode < 2;   // VPD from QV10M: float32 + conversions
   return fmt == 0 ? (out_mode < 2 || extra < 2) : (out_mode < 2 && extra == 0);
 }
 

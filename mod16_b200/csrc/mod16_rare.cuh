@@ -83,6 +83,12 @@ __device__ __forceinline__ float drv_at(const ForwardArgs<float>& a, int k, int6
     else if (r.dtype == MOD16_T_U8) v = dequant((int)__ldg((const unsigned char*)d.ptr + i), r);
     else v = __ldg(d.ptr + i);
   }
+  if ((k == MOD16_D_VPD_DAY || k == MOD16_D_VPD_NIGHT) && (a.prep & MOD16_PREP_VPD_FROM_QV)) {
+    // MOD16.vpd(qv10m, pressure, tmean) (:605-644), in double for the op-for-op pass
+    const int h = k == MOD16_D_VPD_DAY ? 0 : 1;
+    const double temp = (double)a.drv[h == 0 ? MOD16_D_TEMP_DAY : MOD16_D_TEMP_NIGHT].at(t, n);
+    v = (float)vpd_from_qv<double>((double)v, (double)a.ps[h].at(t, n), temp);
+  }
   if (k == MOD16_D_VPD_NIGHT && (a.prep & MOD16_PREP_VPD_NIGHT_CLAMP)) v = v < 0.0f ? 0.0f : v;
   if (k == MOD16_D_PRESSURE && (a.prep & MOD16_PREP_ELEVATION)) v = pressure_from_elevation(v);
   return v;

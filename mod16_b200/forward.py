@@ -230,7 +230,8 @@ def _view_2d(shape):
 def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static',
                 out_mode='sum', gate='global', dtype=None, r_corr_list=None, device=None,
                 stream=None, force=0, as_torch=None, gate_flag=None, out=None,
-                workspace=None, prep=None, groups=None, n_groups=None, weights=None):
+                workspace=None, prep=None, groups=None, n_groups=None, weights=None,
+                surface_pressure=None):
     '''
     Launches K1 once.
 
@@ -255,7 +256,10 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
     drivers may hold ``rawio.RawDriver`` objects (storage formats: uint8 / int16 with scale,
     offset and fill value); ``prep`` names loader conversions applied on the device:
     'vpd_night_clamp' (calibration.py:401), 'elevation' (the ``pressure`` driver holds
-    elevation in metres, calibration.py:405-408).  Both select the float32 path.
+    elevation in metres, calibration.py:405-408).  ``surface_pressure=(ps_day, ps_night)``:
+    the ``vpd_day`` / ``vpd_night`` drivers hold the water vapour mixing ratio QV10M and the
+    kernel forms ``VPD = MOD16.vpd(qv10m, ps, temp)`` itself (mod16/__init__.py:605-644, the
+    loaders' other way to the VPD, calibration.py:393-400).  All select the float32 path.
 
     out      : optional list of preallocated CUDA tensors ((T, N), contiguous) to write into
     workspace : optional int64 CUDA tensor, scratch of the float32 path (default: a cached
@@ -279,10 +283,15 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
         as_torch = any((isinstance(v, torch.Tensor) and v.device.type == 'cuda') or
                        (isinstance(v, RawDriver) and v.is_cuda()) for v in everything)
     prep = prep_word(prep)
+    if surface_pressure is not None:
+        if len(surface_pressure) != 2:
+            raise TypeError('surface_pressure = (ps_day, ps_night)')
+        prep |= _abi.PREP_VPD_FROM_QV
+        surface_pressure = [_arrayish(v) for v in surface_pressure]
     raw = prep != 0 or any(isinstance(v, RawDriver) for v in drivers)
     if raw and (np_dtype != np.dtype('float32') or r_corr_list is not None or force):
         # storage formats belong to the float32 kernels: other call forms see plain arrays
-        drivers, prep, raw = _plain_drivers(drivers, prep, dev, np_dtype), 0, False
+        drivers, prep, raw = _plain_drivers(drivers, prep, dev, np_dtype, surface_pressure), 0, False
 
     shapes = [_shape(v) for v in everything]
     if pft is not None:
@@ -302,11 +311,11 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
             try:
                 return _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate,
                                    as_torch, full_shape, T, N, caller_stream,
-                                   prep if raw else None, groups, n_groups)
+                                   prep if raw else None, groups, n_groups, surface_pressure)
             except _abi.LayoutError:
                 if not raw:
                     raise
-                drivers = _plain_drivers(drivers, prep, dev, np_dtype)
+                drivers = _plain_drivers(drivers, prep, dev, np_dtype, surface_pressure)
                 return _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate,
                                    as_torch, full_shape, T, N, caller_stream, None, groups,
                                    n_groups)
@@ -314,13 +323,13 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
             return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
                                   semantics, out_mode, gate, r_corr_list, force, as_torch,
                                   gate_flag, out, workspace, full_shape, T, N, caller_stream,
-                                  prep if raw else None, weights=weights)
+                                  prep if raw else None, weights=weights, ps=surface_pressure)
         except _abi.LayoutError:
             if not raw:          # plain float32 drivers: the mode itself needs a streamable layout
                 raise
             # a storage-format layout the fused kernel cannot stream: same arithmetic as
             # torch operations on the device first, then the plain float32 entry
-            drivers = _plain_drivers(drivers, prep, dev, np_dtype)
+            drivers = _plain_drivers(drivers, prep, dev, np_dtype, surface_pressure)
             return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
                                   semantics, out_mode, gate, r_corr_list, force, as_torch,
                                   gate_flag, out, workspace, full_shape, T, N, caller_stream,
@@ -328,7 +337,7 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
 
 
 def _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate, as_torch, full_shape,
-                T, N, caller_stream, prep, groups, n_groups):
+                T, N, caller_stream, prep, groups, n_groups, ps=None):
     '''
     out_mode='annual': integer accumulators on the device (2^-32 mm, order-independent), the
     double-precision queue sized for an eighth of the call (no per-step output exists that
@@ -345,7 +354,7 @@ def _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate, as_torc
     flag = torch.zeros(1, device=dev, dtype=torch.int32)
     _run_on_stream(lib, s, dev, np_dtype, drivers, [], plist, pft, table, 'static', 'annual',
                    gate, None, 0, True, flag, [acc], ws, full_shape, T, N, caller_stream, prep,
-                   groups=(g, G))
+                   groups=(g, G), ps=ps)
     if int(flag.item()) & _abi.ANNUAL_OVERFLOW:
         raise _abi.Mod16Error(
             'out_mode="annual": more than an eighth of the elements need the double-precision '
@@ -357,10 +366,18 @@ def _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate, as_torc
     return [out if as_torch else out.cpu().numpy()]
 
 
-def _plain_drivers(drivers, prep, dev, np_dtype):
+def _plain_drivers(drivers, prep, dev, np_dtype, ps=None):
     'Storage-format drivers and loader conversions as plain device tensors of `np_dtype`.'
     t_dtype = _TORCH_DT[np_dtype]
     out = []
+    if prep & _abi.PREP_VPD_FROM_QV:          # MOD16.vpd (:639-644), in double
+        drivers = list(drivers)
+        for h, (k_vpd, k_t) in enumerate(((9, 5), (10, 6))):
+            qv, ps, temp = (torch.as_tensor(v.physical() if isinstance(v, RawDriver) else v)
+                            .to(dev).double() for v in (drivers[k_vpd], ps[h], drivers[k_t]))
+            tc = temp - 273.15
+            drivers[k_vpd] = (610.7 * torch.exp((17.38 * tc) / (239 + tc)) -
+                              (qv * ps) / (0.622 + (0.379 * qv))).to(t_dtype)
     for k, v in enumerate(drivers):
         clamp = k == 10 and (prep & _abi.PREP_VPD_NIGHT_CLAMP)
         if isinstance(v, RawDriver):
@@ -377,7 +394,8 @@ def _plain_drivers(drivers, prep, dev, np_dtype):
 
 def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, semantics,
                    out_mode, gate, r_corr_list, force, as_torch, gate_flag, out, workspace,
-                   full_shape, T, N, caller_stream, prep=None, groups=None, weights=None):
+                   full_shape, T, N, caller_stream, prep=None, groups=None, weights=None,
+                   ps=None):
     'Body of run_forward; the current stream is `s`.  `prep` not None: the storage-format entry.'
     params = plist if plist else None
     st = _Staged(dev, np_dtype)
@@ -405,6 +423,11 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
                     slot.has_fill, slot.fill = 1, int(v.fill)
             else:
                 st.fill(slot, v, T, N, len(full_shape))
+        if prep & _abi.PREP_VPD_FROM_QV:
+            for h in range(2):
+                slot = cd.ps[h]
+                slot.dtype, slot.has_fill, slot.scale, slot.offset, slot.fill = _abi.T_F32, 0, 1.0, 0.0, 0
+                st.fill(slot, ps[h], T, N, len(full_shape))
     else:
         cd = _abi.Drivers()
         for k, v in enumerate(drivers):

@@ -215,3 +215,45 @@ def test_stored_drivers_with_the_other_output_modes(cuda_lib):
         pt = orc.InstanceModel.potential_transpiration(phys[0], phys[2], phys[4], phys[11], phys[5],
                                                        phys[9], phys[12])
     parity.assert_parity(pot['potential_transpiration'], pt, np.float32, what='PT')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N', [4800, 1003])
+def test_vpd_from_mixing_ratio_and_surface_pressure(cuda_lib, N):
+    '''
+    `MOD16.vpd(qv10m, ps, temp)` (mod16/__init__.py:605-644; calibration.py:393-400) formed
+    inside K1 from QV10M and surface pressure, against the oracle's `vpd_from_qv` in double
+    followed by `_et` (N = 1003: the same through the conversion on the device).
+    '''
+    T = 17
+    rng = np.random.default_rng(13)
+    d = synthetic.host_drivers(T, N, 98, dtype=np.float32)
+    ps_d = rng.uniform(7.0e4, 1.02e5, (T, N)).astype(np.float32)
+    ps_n = (ps_d * rng.uniform(0.995, 1.005, (T, N))).astype(np.float32)
+    # mixing ratios that give the synthetic VPDs back: qv = 0.622 avp / (ps - 0.379 avp)
+    def qv_of(vpd, temp, ps):
+        tc = temp.astype(np.float64) - 273.15
+        avp = 610.7 * np.exp(17.38 * tc / (239 + tc)) - vpd
+        return (0.622 * avp / (ps - 0.379 * avp)).astype(np.float32)
+    qv_d, qv_n = qv_of(d['vpd_day'], d['temp_day'], ps_d), qv_of(d['vpd_night'], d['temp_night'], ps_n)
+    drv = [d[k] for k in NAMES]
+    drv[9], drv[10] = qv_d, qv_n
+    d64 = _d64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in [d[k] for k in NAMES]]
+    vd = orc.vpd_from_qv(qv_d.astype(np.float64), ps_d.astype(np.float64), d64[5])
+    vn = orc.vpd_from_qv(qv_n.astype(np.float64), ps_n.astype(np.float64), d64[6])
+    vn = np.where(vn < 0, 0, vn)                                   # calibration.py:401
+    ref_in = list(d64)
+    ref_in[9], ref_in[10] = vd, vn
+    col = list(_table()[:, 7])
+    with np.errstate(all='ignore'):
+        rd, rn = orc.static_evapotranspiration(col, *ref_in)
+    got = MOD16._et(col, *drv, surface_pressure=(ps_d, ps_n), prep=('vpd_night_clamp',))
+    k = cuda_lib.mod16_last_forward_kernel()
+    if N % 4 == 0:
+        assert (k & 0xff, (k >> 8) & 0xf, k >> 12) == (_abi.KERNEL_PIPE, 4, 1)
+    # the VPD is a difference of two O(1e3) Pa numbers formed in float32: 1e-2 Pa of noise
+    m = parity.mismatch(got, rd + rn, np.float32)
+    assert m['nan_mismatch'] == 0 and m['max_abs'] < 5e-3 and m['n_fail'] <= 2e-4 * m['n'], m
+    gd, gn = run_forward(drv, params=col, out_mode='day_night', surface_pressure=(ps_d, ps_n),
+                         prep=('vpd_night_clamp',))
+    assert np.abs(gd - rd).max() < 5e-3 and np.abs(gn - rn).max() < 5e-3
