@@ -373,11 +373,11 @@ def _plain_drivers(drivers, prep, dev, np_dtype, ps=None):
     if prep & _abi.PREP_VPD_FROM_QV:          # MOD16.vpd (:639-644), in double
         drivers = list(drivers)
         for h, (k_vpd, k_t) in enumerate(((9, 5), (10, 6))):
-            qv, ps, temp = (torch.as_tensor(v.physical() if isinstance(v, RawDriver) else v)
-                            .to(dev).double() for v in (drivers[k_vpd], ps[h], drivers[k_t]))
+            qv, p_sfc, temp = (torch.as_tensor(v.physical() if isinstance(v, RawDriver) else v)
+                               .to(dev).double() for v in (drivers[k_vpd], ps[h], drivers[k_t]))
             tc = temp - 273.15
             drivers[k_vpd] = (610.7 * torch.exp((17.38 * tc) / (239 + tc)) -
-                              (qv * ps) / (0.622 + (0.379 * qv))).to(t_dtype)
+                              (qv * p_sfc) / (0.622 + (0.379 * qv))).to(t_dtype)
     for k, v in enumerate(drivers):
         clamp = k == 10 and (prep & _abi.PREP_VPD_NIGHT_CLAMP)
         if isinstance(v, RawDriver):
