@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 10
+#define MOD16_ABI_VERSION 11
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -109,6 +109,12 @@ enum {
                                       `pred_day * updown * 8 * 3600 + pred_night * (24 -
                                       updown) * 8 * 3600` [kg m-2 (8 days)-1 from the instance
                                       path's kg m-2 s-1]; the weights are float32[T] */
+#define MOD16_OUT_SUM_I16 0x60u    /* float32, streamable layouts: out[0] is int16 (T, N),
+                                      round(total / out_scale) saturated to +-32767; a NaN
+                                      total is -32768 (the way the MOD16 product stores its
+                                      layers: scaled integers with a fill value).  Needs
+                                      gate_flag; queue overflow is reported like
+                                      MOD16_OUT_ANNUAL (MOD16_ANNUAL_OVERFLOW) */
 #define MOD16_OUT_MASK 0xF0u
 /* the static path's batch-global transpiration gate `if np.any(g_surf > 0)` (:343) */
 #define MOD16_GATE_GLOBAL 0x000u     /* call-exact: optimistic pass + device-side fix-up */
@@ -176,6 +182,7 @@ typedef struct mod16_out {
      stands for (e.g. updown * 8 * 3600 and (24 - updown) * 8 * 3600) */
   const float* day_weight;
   const float* night_weight;
+  double out_scale;   /* MOD16_OUT_SUM_I16: physical value of one count (e.g. 0.1 W m-2) */
 } mod16_out_t;
 
 /*

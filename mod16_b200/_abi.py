@@ -13,7 +13,7 @@ N_DRIVERS = 14
 # flag words (mirror include/mod16_b200.h)
 SEM_STATIC, SEM_INSTANCE = 0x0, 0x1
 OUT_SUM, OUT_DAY_NIGHT, OUT_COMPONENTS, OUT_ANNUAL, OUT_POTENTIAL = 0x00, 0x10, 0x20, 0x30, 0x40
-OUT_COMPOSITE = 0x50
+OUT_COMPOSITE, OUT_SUM_I16 = 0x50, 0x60
 GATE_GLOBAL, GATE_ELEMENT, GATE_OPEN, GATE_CLOSED = 0x000, 0x100, 0x200, 0x300
 GATE_OPEN_TRACK, GATE_FIXUP = 0x400, 0x500
 FORCE_GENERIC, FORCE_MIRROR = 0x1000, 0x2000
@@ -25,7 +25,7 @@ ANNUAL_OVERFLOW = 0x40000000
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                         'libmod16_b200.so')
 
@@ -65,7 +65,7 @@ class Out(ctypes.Structure):
                 ('workspace', ctypes.c_void_p), ('workspace_bytes', ctypes.c_int64),
                 ('group', ctypes.c_void_p), ('n_groups', ctypes.c_int32),
                 ('reserved', ctypes.c_int32), ('day_weight', ctypes.c_void_p),
-                ('night_weight', ctypes.c_void_p)]
+                ('night_weight', ctypes.c_void_p), ('out_scale', ctypes.c_double)]
 
 
 class Aggregate(ctypes.Structure):

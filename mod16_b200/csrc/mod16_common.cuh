@@ -72,6 +72,7 @@ struct ForwardArgs {
   int n_groups;
   const float* w_day;    // MOD16_OUT_COMPOSITE: float[T] weights of the day / night totals
   const float* w_night;
+  float out_inv_scale;   // MOD16_OUT_SUM_I16: counts per physical unit
   int* gate_flag;
   unsigned long long* redo_ws;  // [0] = count, [1 ..] = queued linear indices t * N + n
   long long redo_cap;           // entries the queue can hold (0: no queue)

@@ -71,10 +71,15 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
                  gm = flags & MOD16_GATE_MASK;
   if (sem > MOD16_SEM_INSTANCE) return MOD16_ERR_FLAGS;
   if (om != MOD16_OUT_SUM && om != MOD16_OUT_DAY_NIGHT && om != MOD16_OUT_COMPONENTS &&
-      om != MOD16_OUT_ANNUAL && om != MOD16_OUT_POTENTIAL && om != MOD16_OUT_COMPOSITE)
+      om != MOD16_OUT_ANNUAL && om != MOD16_OUT_POTENTIAL && om != MOD16_OUT_COMPOSITE &&
+      om != MOD16_OUT_SUM_I16)
     return MOD16_ERR_FLAGS;
-  if ((om == MOD16_OUT_POTENTIAL || om == MOD16_OUT_COMPOSITE) && sizeof(R) != sizeof(float))
+  if ((om == MOD16_OUT_POTENTIAL || om == MOD16_OUT_COMPOSITE || om == MOD16_OUT_SUM_I16) &&
+      sizeof(R) != sizeof(float))
     return MOD16_ERR_FLAGS;
+  if (om == MOD16_OUT_SUM_I16 && (!(out->out_scale > 0.0) || !out->gate_flag))
+    return MOD16_ERR_FLAGS;
+  a.out_inv_scale = om == MOD16_OUT_SUM_I16 ? (float)(1.0 / out->out_scale) : 0.0f;
   if (om == MOD16_OUT_COMPOSITE && T > 0 && (!out->day_weight || !out->night_weight))
     return MOD16_ERR_NULL;
   a.w_day = out->day_weight;
@@ -111,7 +116,8 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
     if (n_arr && (a.par_stride[k] < 0 || a.par_stride[k] > 1)) return MOD16_ERR_SHAPE;
     for (int c = 0; c < MOD16_N_PFT; ++c) a.table[k][c] = par->table[k][c];
   }
-  const int n_out = (om == MOD16_OUT_SUM || om == MOD16_OUT_ANNUAL || om == MOD16_OUT_COMPOSITE) ? 1
+  const int n_out = (om == MOD16_OUT_SUM || om == MOD16_OUT_ANNUAL || om == MOD16_OUT_COMPOSITE ||
+                     om == MOD16_OUT_SUM_I16) ? 1
                     : (om == MOD16_OUT_DAY_NIGHT ? 2 : 6);
   for (int k = 0; k < 6; ++k) {
     a.out[k] = k < n_out ? (R*)out->out[k] : nullptr;

@@ -204,7 +204,7 @@ static int pipe_variant(const ForwardArgs<float>& a, uint32_t flags) {
   const uint32_t om = flags & MOD16_OUT_MASK;
   const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1
                        : (om == MOD16_OUT_ANNUAL ? 3 : (om == MOD16_OUT_POTENTIAL ? 4
-                       : (om == MOD16_OUT_COMPOSITE ? 5 : 2))));
+                       : (om == MOD16_OUT_COMPOSITE ? 5 : (om == MOD16_OUT_SUM_I16 ? 6 : 2)))));
   if (!pipe_has_variant(out_mode, extra)) return -1;
   return extra;
 }
@@ -253,7 +253,7 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
   const uint32_t om = flags & MOD16_OUT_MASK;
   const int out_mode = om == MOD16_OUT_SUM ? 0 : (om == MOD16_OUT_DAY_NIGHT ? 1
                        : (om == MOD16_OUT_ANNUAL ? 3 : (om == MOD16_OUT_POTENTIAL ? 4
-                       : (om == MOD16_OUT_COMPOSITE ? 5 : 2))));
+                       : (om == MOD16_OUT_COMPOSITE ? 5 : (om == MOD16_OUT_SUM_I16 ? 6 : 2)))));
   const bool is_static = (flags & MOD16_SEM_MASK) == MOD16_SEM_STATIC;
   if (a.redo_cap > 0) M16_CUDA_CHECK(cudaMemsetAsync(a.redo_ws, 0, 8, st));
   if (out_mode == 3 && a.skip_if_flag) {
@@ -276,6 +276,10 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
   } while (0)
     if (is_static && out_mode == 3) {   // (no marker sweep: nothing per step to mark)
       redo_queue_kernel<SEM_STATIC, 3><<<148 * 4, 128, 0, st>>>(a);
+      M16_CUDA_CHECK(cudaGetLastError());
+    } else if (out_mode == 6) {
+      if (is_static) redo_queue_kernel<SEM_STATIC, 6><<<148 * 4, 128, 0, st>>>(a);
+      else redo_queue_kernel<SEM_INSTANCE, 6><<<148 * 4, 128, 0, st>>>(a);
       M16_CUDA_CHECK(cudaGetLastError());
     } else if (is_static) {
       if (out_mode == 0) M16_REDO(SEM_STATIC, 0);
@@ -317,7 +321,8 @@ int launch_fast_f32(ForwardArgs<float>& a, uint32_t flags, cudaStream_t st) {
   // (no strided kernel for storage formats, nor for the annual sums)
   if (a.raw_fmt != 0 || (flags & MOD16_OUT_MASK) == MOD16_OUT_ANNUAL ||
       (flags & MOD16_OUT_MASK) == MOD16_OUT_POTENTIAL ||
-      (flags & MOD16_OUT_MASK) == MOD16_OUT_COMPOSITE)
+      (flags & MOD16_OUT_MASK) == MOD16_OUT_COMPOSITE ||
+      (flags & MOD16_OUT_MASK) == MOD16_OUT_SUM_I16)
     return MOD16_ERR_LAYOUT;
   g_last_forward_kernel = MOD16_KERNEL_STRIDED;
   const int threads = 256;

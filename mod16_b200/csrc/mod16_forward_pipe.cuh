@@ -176,7 +176,7 @@ __device__ __forceinline__ bool pipe_defer(const ForwardArgs<float>& a, int ts, 
     if (queued) redo_q[slot] = (uint32_t)ts << 10 | (uint32_t)tid;
   }
   if (queued) return false;
-  if (OUT == 3) {
+  if (OUT == 3 || OUT == 6) {
     // the annual sums have no per-step output to carry a marker: with a workspace the element
     // goes to the block's own queue; when that is full too the call reports it (bit 30 of
     // the gate word: the sums are incomplete, see MOD16_OUT_ANNUAL in the header)
@@ -210,9 +210,15 @@ __device__ __forceinline__ int pipe_rule(const ForwardArgs<float>& a, int ts, fl
   c.vpd_off = vpd_off; c.inv_dvpd = inv_dvpd;
   bool g_pos;
   const int h = fast::nan_halves<SEM>(in, c, a.has_rc != 0, g_pos);
-  if (OUT == 2 || OUT == 4 || !((OUT == 0 || OUT == 3 || OUT == 5) ? h != 0 : h == 3)) return -1;
+  if (OUT == 2 || OUT == 4 ||
+      !((OUT == 0 || OUT == 3 || OUT == 5 || OUT == 6) ? h != 0 : h == 3))
+    return -1;
   if (OUT == 3) {
     annual_add(a, t, n, kAnnualNaN);
+    return g_pos ? 1 : 0;
+  }
+  if (OUT == 6) {
+    ((short*)a.out[0])[t * a.N + n] = (short)-32768;
     return g_pos ? 1 : 0;
   }
   const float qnan = __int_as_float(0x7fc00000);
@@ -337,13 +343,15 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     }
   }
   // the masked-driver rule is decided from registers for the static total of a sane column
-  const bool rule_in_regs = (OUT == 0 || OUT == 3) && SEM == SEM_STATIC && c1.ok != 0.0f;
+  const bool rule_in_regs = (OUT == 0 || OUT == 3 || OUT == 6) && SEM == SEM_STATIC &&
+                            c1.ok != 0.0f;
   // MOD16_OUT_ANNUAL: this pixel's running sum of the current group (year), 2^-32 mm
   unsigned long long acc_run = 0ULL;
   int acc_g = -1;
   const float swn_scalar = a.drv[MOD16_D_SW_RAD_NIGHT].scalar;
   const int gate = a.gate;
-  constexpr int n_out = OUT == 3 ? 0 : ((OUT == 0 || OUT == 5) ? 1 : (OUT == 1 ? 2 : 6));
+  constexpr int n_out = (OUT == 3 || OUT == 6) ? 0 : ((OUT == 0 || OUT == 5) ? 1 : (OUT == 1 ? 2 : 6));
+  constexpr bool NOMARK = OUT == 3 || OUT == 6;   // no float per-step output to carry a marker
   constexpr bool RULE = OUT != 2 && OUT != 4;   // outputs a NaN total decides without the double code
   // this thread's pixel in a row (float32 rows; storage formats index per array)
   const uint32_t my0 = keep_u32(FMT < FMT_MODIS ? data0 + (uint32_t)tid * 4u : data0);
@@ -463,6 +471,8 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
       const F2 w_d = F2{__ldg(wd), TWO ? __ldg(wd + 1) : 0.0f};
       const F2 w_n = F2{__ldg(wn), TWO ? __ldg(wn + 1) : 0.0f};
       res[0] = fast::vfma(r.tot_day, w_d, r.tot_night * w_n);
+    } else if (OUT == 6) {
+      res[0] = r.tot * a.out_inv_scale;
     } else if (OUT == 4) {
       res[0] = r.tot;       res[1] = r.day.pt;
       res[2] = r.day.sat;   res[3] = r.day.unsat;
@@ -478,6 +488,14 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     if (OUT == 3 && flags == 0u && !(late.x || late.y) && g_x == acc_g && g_y == acc_g) {
       gs_max = fmaxf(gs_max, fmaxf(gs.x, gs.y));
       acc_run += q_x + q_y;
+    } else if (OUT == 6 && flags == 0u && !(late.x || late.y)) {
+      gs_max = fmaxf(gs_max, fmaxf(gs.x, gs.y));
+      short* o16 = (short*)a.out[0] + off;   // (in the domain: finite)
+      int q0, q1;
+      asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(q0) : "f"(fmaxf(res[0].x, -32767.0f)));
+      asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(q1) : "f"(fmaxf(res[0].y, -32767.0f)));
+      o16[0] = (short)q0;
+      if (TWO) o16[t_stride] = (short)q1;
     } else if (OUT != 3 && flags == 0u && !(late.x || late.y)) {
       gs_max = fmaxf(gs_max, fmaxf(gs.x, gs.y));
 #pragma unroll
@@ -493,6 +511,7 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
         if (flags & (j == 0 ? MASKED_X : MASKED_Y)) {
           // (g_surf > 0 from Tmin, VPD, T, P of the hot path; NaN > 0 is false)
           if (OUT == 3) q_j = kAnnualNaN;
+          else if (OUT == 6) ((short*)a.out[0])[off + j * t_stride] = (short)-32768;
           else st_stream1(a.out[0] + off + j * t_stride, __int_as_float(0x7fc00000));
           any_pos |= j == 0 ? g_pos.x : g_pos.y;
         } else if (j == 0 ? late.x : late.y) {
@@ -500,6 +519,8 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
           continue;
         } else {
           any_pos |= j == 0 ? g_pos.x : g_pos.y;
+          if (OUT == 6)
+            ((short*)a.out[0])[off + j * t_stride] = to_i16(j == 0 ? res[0].x : res[0].y, 1.0f);
 #pragma unroll
           for (int k = 0; k < n_out; ++k)
             st_stream1(a.out[k] + off + j * t_stride, j == 0 ? res[k].x : res[k].y);
@@ -528,14 +549,14 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     atomicAdd((unsigned long long*)a.out[0] + (int64_t)acc_g * a.N + tile0 + tid, acc_run);
   // the block-local deferred pass: consumers only (named barrier 1), one element each; when
   // the block's queue overflowed, every thread also looks for markers in its own column
-  if (a.redo_cap == 0 || OUT == 3) {
+  if (a.redo_cap == 0 || NOMARK) {
     asm volatile("bar.sync 1, %0;" ::"n"(PIPE_CONSUMERS) : "memory");
     const int total = redo_n < PIPE_QCAP ? redo_n : PIPE_QCAP;
     for (int e = tid; e < total; e += PIPE_CONSUMERS) {
       const uint32_t q = redo_q[e];
       any_pos |= fix_exact_one<SEM, OUT>(a, t0 + (int64_t)(q >> 10), tile0 + (q & 1023u));
     }
-    if (OUT != 3 && redo_n > PIPE_QCAP && live) {
+    if (!NOMARK && redo_n > PIPE_QCAP && live) {
       for (int ts = 0; ts < nsteps; ++ts) {
         const int64_t o = (t0 + ts) * a.N + tile0 + tid;
         if (__float_as_int(((volatile float*)a.out[0])[o]) == REDO_MARK)
@@ -579,7 +600,7 @@ int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mod
   M16_PIPE(1, 0, 1); M16_PIPE(1, 0, 2); M16_PIPE(1, 0, 3);
   M16_PIPE(0, 4, 1); M16_PIPE(1, 4, 1);
   if constexpr (SEM == SEM_STATIC) { M16_PIPE(3, 0, 0); }
-  M16_PIPE(4, 0, 0); M16_PIPE(5, 0, 0);
+  M16_PIPE(4, 0, 0); M16_PIPE(5, 0, 0); M16_PIPE(6, 0, 0);
 #undef M16_PIPE
   return MOD16_ERR_FLAGS;
 }

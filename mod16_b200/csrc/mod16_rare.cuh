@@ -132,12 +132,22 @@ __device__ __forceinline__ void annual_add(const ForwardArgs<float>& a, int64_t 
     atomicAdd((unsigned long long*)a.out[0] + (int64_t)g * a.N + n, q);
 }
 
+// MOD16_OUT_SUM_I16: round(v / scale) saturated to +-32767; NaN -> -32768
+__device__ __forceinline__ short to_i16(float v, float inv_scale) {
+  if (v != v) return (short)-32768;
+  int q;
+  asm("cvt.rni.sat.s16.f32 %0, %1;" : "=r"(q) : "f"(fmaxf(v * inv_scale, -32767.0f)));
+  return (short)q;
+}
+
 template <int OUT>
 __device__ __forceinline__ void store_exact(const ForwardArgs<float>& a, int64_t o,
                                             const fast::StepOut& r, const StepIn& in) {
   if (OUT == 3) {
     const float tcm = 0.5f * (fast::celsius<float>(in.t_d) + fast::celsius<float>(in.t_n));
     annual_add(a, o / a.N, o % a.N, annual_fixed(r.tot, tcm));
+  } else if (OUT == 6) {
+    ((short*)a.out[0])[o] = to_i16(r.tot, a.out_inv_scale);
   } else if (OUT == 5) {
     const int64_t t = o / a.N;
     a.out[0][o] = fmaf(r.tot_day, __ldg(a.w_day + t), r.tot_night * __ldg(a.w_night + t));

@@ -231,7 +231,7 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
                 out_mode='sum', gate='global', dtype=None, r_corr_list=None, device=None,
                 stream=None, force=0, as_torch=None, gate_flag=None, out=None,
                 workspace=None, prep=None, groups=None, n_groups=None, weights=None,
-                surface_pressure=None):
+                surface_pressure=None, out_scale=None):
     '''
     Launches K1 once.
 
@@ -251,6 +251,9 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
                | 'composite' (float32, (T, N) drivers: ``day * weights[0][t] + night *
                weights[1][t]``, the day-length weighted composite of verify2.py:112-115;
                ``weights`` = two (T,) arrays)
+               | 'sum_i16' (float32, (T, N) drivers: the total as int16 counts of
+               ``out_scale``, -32768 where it is NaN -- the way the MOD16 product stores its
+               layers; returns a ``rawio.RawDriver`` whose ``physical()`` gives the floats)
     gate     : 'global' (reference) | 'element' | 'open' | 'closed' | 'open_track' | 'fixup'
 
     drivers may hold ``rawio.RawDriver`` objects (storage formats: uint8 / int16 with scale,
@@ -323,7 +326,8 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
             return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
                                   semantics, out_mode, gate, r_corr_list, force, as_torch,
                                   gate_flag, out, workspace, full_shape, T, N, caller_stream,
-                                  prep if raw else None, weights=weights, ps=surface_pressure)
+                                  prep if raw else None, weights=weights, ps=surface_pressure,
+                                  out_scale=out_scale)
         except _abi.LayoutError:
             if not raw:          # plain float32 drivers: the mode itself needs a streamable layout
                 raise
@@ -333,7 +337,7 @@ def run_forward(drivers, *, params=None, pft=None, table=None, semantics='static
             return _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table,
                                   semantics, out_mode, gate, r_corr_list, force, as_torch,
                                   gate_flag, out, workspace, full_shape, T, N, caller_stream,
-                                  None, weights=weights)
+                                  None, weights=weights, out_scale=out_scale)
 
 
 def _run_annual(lib, s, dev, np_dtype, drivers, plist, pft, table, gate, as_torch, full_shape,
@@ -395,7 +399,7 @@ def _plain_drivers(drivers, prep, dev, np_dtype, ps=None):
 def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, semantics,
                    out_mode, gate, r_corr_list, force, as_torch, gate_flag, out, workspace,
                    full_shape, T, N, caller_stream, prep=None, groups=None, weights=None,
-                   ps=None):
+                   ps=None, out_scale=None):
     'Body of run_forward; the current stream is `s`.  `prep` not None: the storage-format entry.'
     params = plist if plist else None
     st = _Staged(dev, np_dtype)
@@ -471,14 +475,20 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
             cp.table[i][j] = tab[i, j]
 
     n_out = {'sum': 1, 'day_night': 2, 'components': 6, 'annual': 1, 'potential': 6,
-             'composite': 1}[out_mode]
+             'composite': 1, 'sum_i16': 1}[out_mode]
     flags = {'static': _abi.SEM_STATIC, 'instance': _abi.SEM_INSTANCE}[semantics]
     flags |= {'sum': _abi.OUT_SUM, 'day_night': _abi.OUT_DAY_NIGHT,
               'components': _abi.OUT_COMPONENTS, 'annual': _abi.OUT_ANNUAL,
-              'potential': _abi.OUT_POTENTIAL, 'composite': _abi.OUT_COMPOSITE}[out_mode]
+              'potential': _abi.OUT_POTENTIAL, 'composite': _abi.OUT_COMPOSITE,
+              'sum_i16': _abi.OUT_SUM_I16}[out_mode]
     flags |= _abi.GATE_FLAGS[gate] | force
     if out_mode == 'annual':
         outs = list(out)                    # (n_groups, N) int64 accumulators, zeroed
+    elif out_mode == 'sum_i16':
+        if not out_scale or out_scale <= 0:
+            raise ValueError('out_mode="sum_i16" needs out_scale > 0')
+        outs = list(out) if out is not None else [
+            torch.empty((T, N), device=dev, dtype=torch.int16)]
     elif out is not None:
         outs = list(out)
         if len(outs) != n_out or any(
@@ -493,6 +503,10 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
     if groups is not None:
         co.group, co.n_groups = groups[0].data_ptr(), groups[1]
         st.keep.append(groups[0])
+    if out_mode == 'sum_i16':
+        co.out_scale = float(out_scale)
+        # (no float output to carry overflow markers: a generous queue, like 'annual')
+        workspace = torch.empty(max(1 << 20, T * N // 8 + 1024), device=dev, dtype=torch.int64)
     if out_mode == 'composite':
         if weights is None or len(weights) != 2:
             raise TypeError('out_mode="composite" needs weights=(day_seconds, night_seconds)')
@@ -521,6 +535,13 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
                   ctypes.c_void_p(handle)))
     if out_mode == 'annual':
         return outs
+    if out_mode == 'sum_i16':
+        if int(gate_flag.item()) & _abi.ANNUAL_OVERFLOW:
+            raise _abi.Mod16Error('out_mode="sum_i16": more than an eighth of the elements need '
+                                  'the double-precision pass; mask fill values first')
+        o = outs[0].reshape(full_shape)
+        hand_over((o,), caller_stream)
+        return [RawDriver(o if as_torch else o.cpu().numpy(), float(out_scale), 0.0, -32768)]
     outs = [o.reshape(full_shape) for o in outs]
     if as_torch:
         # Staged copies were allocated and used on `s` alone: the caching allocator's stream

@@ -340,3 +340,39 @@ def test_without_a_workspace_the_block_queues_and_its_own_sweep_take_over(cuda_l
     got = run_forward(drv, params=col, out_mode=out_mode, dtype=np.float32, workspace=tiny)
     for g, w in zip(got, want):
         parity.assert_parity(g, w, np.float32, what='tiny workspace, ' + out_mode)
+
+
+@pytest.mark.parametrize('semantics', ['static', 'instance'])
+def test_scaled_int16_output(cuda_lib, semantics):
+    'MOD16_OUT_SUM_I16: the total as the product stores it -- int16 counts, -32768 for NaN.'
+    T, N = 21, 4800
+    d = synthetic.host_drivers(T, N, 211, dtype=np.float32)
+    rng = np.random.default_rng(212)
+    d['lai'][rng.random((T, N)) < 0.01] = np.nan
+    d['fpar'][rng.random((T, N)) < 0.005] = -1.0          # finite garbage: the double code decides
+    drv = [d[k] for k in NAMES]
+    col = list(_table()[:, 7])
+    with np.errstate(all='ignore'):
+        if semantics == 'static':
+            want = orc.static_et(col, *_d64(drv))
+            scale = 0.1                                    # W m-2 per count
+        else:
+            day, night = orc.InstanceModel(dict(zip(orc.PARAM_ORDER, col))).evapotranspiration(
+                *_d64(drv))
+            want = day + night
+            scale = 1e-8                                   # kg m-2 s-1 per count
+    got = run_forward(drv, params=col, semantics=semantics, out_mode='sum_i16', out_scale=scale)[0]
+    assert _kernel(cuda_lib)[0] == _abi.KERNEL_PIPE
+    raw = got.raw
+    assert raw.dtype == np.int16 and raw.shape == (T, N)
+    assert np.array_equal(raw == -32768, np.isnan(want))
+    ok = ~np.isnan(want)
+    counts = np.clip(want[ok] / scale, -32767, 32767)
+    # half a count of rounding + the float32 tolerance of the total itself
+    tol = 0.5 + np.maximum(1e-5 * np.abs(want[ok]), 1e-3 * (1.0 if semantics == 'static'
+                                                            else parity.MASS_SCALE)) / scale
+    assert np.all(np.abs(raw[ok] - counts) <= tol + 1e-6)
+    assert np.allclose(got.physical()[ok], want[ok], atol=0.51 * scale + 1e-3 * (
+        1.0 if semantics == 'static' else parity.MASS_SCALE), rtol=1e-5)
+    with pytest.raises(ValueError):
+        run_forward(drv, params=col, out_mode='sum_i16')
