@@ -13,10 +13,12 @@
 
 namespace mod16 {
 
-int launch_pipe_static(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode, int extra,
-                       int fmt, dim3 grid, cudaStream_t st);
-int launch_pipe_instance(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode,
-                         int extra, int fmt, dim3 grid, cudaStream_t st);
+#define M16_DECL(name)                                                                  \
+  int name(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode, int extra, int fmt, \
+           dim3 grid, cudaStream_t st);
+M16_DECL(launch_pipe_static) M16_DECL(launch_pipe_static_b)
+M16_DECL(launch_pipe_instance) M16_DECL(launch_pipe_instance_b)
+#undef M16_DECL
 
 template <int SEM, int OUT>
 __global__ void __launch_bounds__(256, 4)
@@ -263,8 +265,10 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
                                                  (int64_t)a.n_groups * a.N, a.gate_flag);
     M16_CUDA_CHECK(cudaGetLastError());
   }
-  const int rc = is_static ? launch_pipe_static(a, src, out_mode, extra, fmt, grid, st)
-                           : launch_pipe_instance(a, src, out_mode, extra, fmt, grid, st);
+  const bool part_b = fmt != 0 || out_mode >= 3;
+  const int rc = is_static
+      ? (part_b ? launch_pipe_static_b : launch_pipe_static)(a, src, out_mode, extra, fmt, grid, st)
+      : (part_b ? launch_pipe_instance_b : launch_pipe_instance)(a, src, out_mode, extra, fmt, grid, st);
   if (rc != MOD16_OK) return rc;
   if (a.redo_cap > 0) {
 #define M16_REDO(S, O)                                                                  \

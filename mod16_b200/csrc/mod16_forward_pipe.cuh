@@ -582,25 +582,33 @@ static int launch_pipe_inst(const ForwardArgs<float>& a, const PipeSrc& src, dim
   return MOD16_OK;
 }
 
-// Instantiated per semantics in mod16_forward_pipe_{static,instance}.cu (parallel builds).
+// Instantiated per semantics and part in mod16_forward_pipe_{static,instance}[_b].cu (parallel
+// builds).
 // EXTRA 2 / 3 (time-varying annual temperature / pressure) exist for the summed and the
 // day / night outputs; `separate=True` with such drivers takes the strided kernel.
 // Storage formats (FMT > 0) exist for the summed and the day / night outputs of the eleven
 // per-step arrays.
-template <int SEM>
+// PART splits the instantiations over two translation units per semantics (build time):
+// 0 = the float32 layouts with the three classic output modes, 1 = storage formats, loader
+// conversions and the epilogue output modes.  Returns MOD16_ERR_FLAGS for a variant of the
+// other part.
+template <int SEM, int PART>
 int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode, int extra,
                     int fmt, dim3 grid, cudaStream_t st) {
 #define M16_PIPE(O, E, F) \
   if (out_mode == O && extra == E && fmt == F) \
     return launch_pipe_inst<SEM, O, E, F>(a, src, grid, st)
-  M16_PIPE(0, 0, 0); M16_PIPE(0, 1, 0); M16_PIPE(0, 2, 0); M16_PIPE(0, 3, 0);
-  M16_PIPE(1, 0, 0); M16_PIPE(1, 1, 0); M16_PIPE(1, 2, 0); M16_PIPE(1, 3, 0);
-  M16_PIPE(2, 0, 0); M16_PIPE(2, 1, 0);
-  M16_PIPE(0, 0, 1); M16_PIPE(0, 0, 2); M16_PIPE(0, 0, 3);
-  M16_PIPE(1, 0, 1); M16_PIPE(1, 0, 2); M16_PIPE(1, 0, 3);
-  M16_PIPE(0, 4, 1); M16_PIPE(1, 4, 1);
-  if constexpr (SEM == SEM_STATIC) { M16_PIPE(3, 0, 0); }
-  M16_PIPE(4, 0, 0); M16_PIPE(5, 0, 0); M16_PIPE(6, 0, 0);
+  if constexpr (PART == 0) {
+    M16_PIPE(0, 0, 0); M16_PIPE(0, 1, 0); M16_PIPE(0, 2, 0); M16_PIPE(0, 3, 0);
+    M16_PIPE(1, 0, 0); M16_PIPE(1, 1, 0); M16_PIPE(1, 2, 0); M16_PIPE(1, 3, 0);
+    M16_PIPE(2, 0, 0); M16_PIPE(2, 1, 0);
+  } else {
+    M16_PIPE(0, 0, 1); M16_PIPE(0, 0, 2); M16_PIPE(0, 0, 3);
+    M16_PIPE(1, 0, 1); M16_PIPE(1, 0, 2); M16_PIPE(1, 0, 3);
+    M16_PIPE(0, 4, 1); M16_PIPE(1, 4, 1);
+    if constexpr (SEM == SEM_STATIC) { M16_PIPE(3, 0, 0); }
+    M16_PIPE(4, 0, 0); M16_PIPE(5, 0, 0); M16_PIPE(6, 0, 0);
+  }
 #undef M16_PIPE
   return MOD16_ERR_FLAGS;
 }

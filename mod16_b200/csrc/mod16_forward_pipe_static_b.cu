@@ -1,0 +1,10 @@
+// forward_pipe_kernel, static semantics (`_evapotranspiration` / `_et`): instantiations, part 1
+// (storage formats, loader conversions, epilogue output modes).
+#include "mod16_forward_pipe.cuh"
+
+namespace mod16 {
+int launch_pipe_static_b(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode, int extra,
+                               int fmt, dim3 grid, cudaStream_t st) {
+  return launch_pipe_sem<SEM_STATIC, 1>(a, src, out_mode, extra, fmt, grid, st);
+}
+}  // namespace mod16
