@@ -646,11 +646,26 @@ def end_to_end(args, device, world, rank, numa, drv, pft, table, T, N, np_dtype,
     from mod16_b200.streaming import StreamedForward
     names = [k for k in synthetic.DRIVER_NAMES
              if k not in synthetic.PER_PIXEL and k != 'sw_rad_night']
-    try:  # a third of the free host memory may be pinned at a time
+    def drop_pinned():
+        # pinned blocks go back to torch's host cache, not to the system: without this the
+        # three legs' buffers add up (and, times the ranks, exhaust the host)
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        if hasattr(torch._C, '_host_emptyCache'):
+            torch._C._host_emptyCache()
+
+    try:  # a third of the free host memory may be pinned at a time, over all ranks
         import psutil
         room = psutil.virtual_memory().available / 3.0 / max(world, 1)
+        if not hasattr(torch._C, '_host_emptyCache'):
+            room /= 3.0        # (the legs' buffers cannot be returned: share the budget)
     except Exception:
         room = 16 * 12 * N * np_dtype.itemsize
+    tr = torch.tensor([room], device=device, dtype=torch.float64)
+    if world > 1:             # (every rank measured at a different moment: agree on the least)
+        dist.all_reduce(tr, op=dist.ReduceOp.MIN)
+    room = float(tr.item())
     per_pixel = dict((k, drv[k].cpu().pin_memory()) for k in synthetic.PER_PIXEL)
     legs = {}
     layouts = ['float32'] + (['modis', 'packed'] if np_dtype == np.float32 else [])
@@ -707,6 +722,7 @@ def end_to_end(args, device, world, rank, numa, drv, pft, table, T, N, np_dtype,
                         'h2d_bytes_per_unit': runner.h2d_bytes / reps / (Te * N)}
         del host, out_host, runner
         torch.cuda.empty_cache()
+        drop_pinned()
     head = 'packed' if 'packed' in legs else 'float32'
     e2e = dict(legs[head])
     e2e['input_format'] = {
