@@ -135,6 +135,11 @@ M16_HD F2 vrcp(F2 a) { return F2{s_rcp(a.x), s_rcp(a.y)}; }
 M16_HD F2 vex2(F2 a) { return F2{s_ex2(a.x), s_ex2(a.y)}; }
 M16_HD F2 vlg2(F2 a) { return F2{s_lg2(a.x), s_lg2(a.y)}; }
 M16_HD F2 vsat(F2 a) { return F2{s_sat(a.x), s_sat(a.y)}; }
+// sat(a b + c): two scalar FFMA.SAT instead of one packed FMA and two saturating adds
+M16_HD float vsat_fma(float a, float b, float c) { return s_sat(fmaf(a, b, c)); }
+M16_HD F2 vsat_fma(F2 a, F2 b, F2 c) {
+  return F2{s_sat(fmaf(a.x, b.x, c.x)), s_sat(fmaf(a.y, b.y, c.y))};
+}
 M16_HD F2 vabs(F2 a) { return F2{fabsf(a.x), fabsf(a.y)}; }
 M16_HD F2 vmax(F2 a, F2 b) { return F2{fmaxf(a.x, b.x), fmaxf(a.y, b.y)}; }
 M16_HD F2 vmin(F2 a, F2 b) { return F2{fminf(a.x, b.x), fminf(a.y, b.y)}; }
@@ -194,6 +199,7 @@ M16_HD double vrcp(double a) { return d_rcp(a); }
 M16_HD double vex2(double a) { return exp2(a); }
 M16_HD double vlg2(double a) { return log2(a); }
 M16_HD double vsat(double a) { return a != a ? 0.0 : (a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a)); }
+M16_HD double vsat_fma(double a, double b, double c) { return vsat(fma(a, b, c)); }
 M16_HD double vabs(double a) { return fabs(a); }
 M16_HD double vmax(double a, double b) { return fmax(a, b); }
 M16_HD double vmin(double a, double b) { return fmin(a, b); }
@@ -427,9 +433,9 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
                vrcp(tc + K(237.3 - tb));
   const V e = vex2(xe);                             // SVP / 610.8
   const V ies = K(1.0 / 610.8) * vex2_neg(xe, e);   // 1 / SVP
-  V rh = vfma(-vpd, ies, K(1.0));
-  if (SEM == SEM_STATIC) rh = vmax(rh, splat<V>(K(0.0)));  // :280-281 (no upper clamp)
-  else rh = vsat(rh);                                    // :671-673
+  V rh;
+  if (SEM == SEM_STATIC) rh = vmax(vfma(-vpd, ies, K(1.0)), splat<V>(K(0.0)));  // :280-281 (no upper clamp)
+  else rh = vsat_fma(-vpd, ies, splat<V>(K(1.0)));                              // :671-673
   // discontinuities in rh: the f_wet jump at 0.7 (:282), guarded for |rh - 0.7| < 4e-6, and
   // rh -> 0+, where rh^(vpd/beta) is ill-conditioned (:376), guarded for 0 < rh < 2e-3
   // (rh == 0 exactly -- the clamp -- is NOT guarded: |0 - 1e-3| * 0.1 == kGuard).
@@ -459,7 +465,7 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
   } else {
     inv_rc = x.ip * vpow_m175(q);
   }
-  const V m_v = vsat(vfma(-vpd, c.inv_dvpd, c.vpd_off));  // reversed ramp on VPD (:326)
+  const V m_v = vsat_fma(-vpd, c.inv_dvpd, c.vpd_off);  // reversed ramp on VPD (:326)
   const V Kf = Kv * fpar;
   const V SA = S * a_can;
   V il = splat<V>(K(0.0));
@@ -488,7 +494,7 @@ M16_HD HalfV<V> half_fast(V t, V tc, V vpd, V a_can, V a_soil, V rc, V tmin, V f
   if (DAY || SEM == SEM_INSTANCE) {
     V gs = splat<V>(K(0.0));
     if (DAY) {
-      const V m_t = vsat(vfma(tmin, c.inv_dtmin, c.tmin_bias));                 // :325
+      const V m_t = vsat_fma(tmin, c.inv_dtmin, c.tmin_bias);                 // :325
       gs = ((c.csl * m_t) * m_v) * inv_rc;                                      // :327-328
     }
     g_pos = vgt(gs, splat<V>(K(0.0)));
