@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MOD16_ABI_VERSION 11
+#define MOD16_ABI_VERSION 12
 
 #define MOD16_N_PARAMS 11  /* MOD16.required_parameters, mod16/__init__.py:152-155 */
 #define MOD16_N_PFT 13     /* BPLUT arrays are indexed by PFT code 0..12, mod16/utils.py:104 */
@@ -141,7 +141,11 @@ typedef struct mod16_drivers {
   mod16_driver_t drv[MOD16_N_DRIVERS];
   mod16_driver_t r_corr[2]; /* optional `r_corr_list` (day, night), :291-294 */
   int32_t has_r_corr;
-  int32_t reserved;
+  /* mod16_forward_f64 only: bit k set = drv[k].ptr is a FLOAT32 array (strides in float32
+     elements), widened exactly inside the kernel.  The reference's stock call -- float32
+     drivers from the archive with the float64 BPLUT, which numpy promotes to float64 -- then
+     needs no float64 copies of the drivers.  0 for every other entry. */
+  uint32_t f32_mask;
 } mod16_drivers_t;
 
 /*

@@ -25,7 +25,7 @@ ANNUAL_OVERFLOW = 0x40000000
 GATE_FLAGS = {'global': GATE_GLOBAL, 'element': GATE_ELEMENT, 'open': GATE_OPEN,
               'closed': GATE_CLOSED, 'open_track': GATE_OPEN_TRACK, 'fixup': GATE_FIXUP}
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib',
                         'libmod16_b200.so')
 
@@ -37,7 +37,7 @@ class Driver(ctypes.Structure):
 
 class Drivers(ctypes.Structure):
     _fields_ = [('drv', Driver * N_DRIVERS), ('r_corr', Driver * 2),
-                ('has_r_corr', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('has_r_corr', ctypes.c_int32), ('f32_mask', ctypes.c_uint32)]
 
 
 class RawDriver(ctypes.Structure):

@@ -29,7 +29,10 @@ struct Arr {
   const R* ptr;      // NULL: scalar
   int64_t ts, ns;    // element strides over time / pixels (0 broadcasts)
   R scalar;
+  int is_f32;        // (R = double only) ptr holds float32 elements: widened on load
   __device__ __forceinline__ R at(int64_t t, int64_t n) const {
+    if (sizeof(R) == 8 && is_f32)
+      return ptr ? (R)__ldg(reinterpret_cast<const float*>(ptr) + t * ts + n * ns) : scalar;
     return ptr ? __ldg(ptr + t * ts + n * ns) : scalar;
   }
 };
@@ -40,6 +43,7 @@ inline void fill_arr(Arr<R>& dst, const mod16_driver_t& src) {
   dst.ts = src.ptr ? src.t_stride : 0;
   dst.ns = src.ptr ? src.n_stride : 0;
   dst.scalar = (R)src.scalar;
+  dst.is_f32 = 0;
 }
 
 // Storage format of one driver of mod16_forward_raw_f32 (float32 path only).

@@ -94,7 +94,9 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
   for (int k = 0; k < MOD16_N_DRIVERS; ++k) {
     if (drv->drv[k].t_stride < 0 || drv->drv[k].n_stride < 0) return MOD16_ERR_SHAPE;
     fill_arr<R>(a.drv[k], drv->drv[k]);
+    if (sizeof(R) == 8 && (drv->f32_mask >> k & 1u) && drv->drv[k].ptr) a.drv[k].is_f32 = 1;
   }
+  if (sizeof(R) != 8 && drv->f32_mask != 0) return MOD16_ERR_FLAGS;
   a.has_rc = drv->has_r_corr ? 1 : 0;
   for (int k = 0; k < 2; ++k) {
     if (a.has_rc) {
@@ -102,6 +104,7 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
       fill_arr<R>(a.rc[k], drv->r_corr[k]);
     } else {
       a.rc[k].ptr = nullptr; a.rc[k].ts = a.rc[k].ns = 0; a.rc[k].scalar = R(0);
+      a.rc[k].is_f32 = 0;
     }
   }
   int n_arr = 0;
@@ -143,7 +146,9 @@ int build_forward_args(const mod16_drivers_t* drv, const mod16_params_t* par,
   a.t_chunk = 1;
   a.raw_fmt = 0;
   a.prep = 0;
-  for (int k = 0; k < 2; ++k) { a.ps[k].ptr = nullptr; a.ps[k].ts = a.ps[k].ns = 0; a.ps[k].scalar = R(0); }
+  for (int k = 0; k < 2; ++k) {
+    a.ps[k].ptr = nullptr; a.ps[k].ts = a.ps[k].ns = 0; a.ps[k].scalar = R(0); a.ps[k].is_f32 = 0;
+  }
   for (int k = 0; k < MOD16_N_DRIVERS; ++k) {
     a.raw[k].dtype = MOD16_T_F32; a.raw[k].has_fill = 0;
     a.raw[k].scale = 1.0f; a.raw[k].offset = 0.0f; a.raw[k].fill = 0;
@@ -301,7 +306,7 @@ int mod16_forward_raw_f32(const mod16_raw_drivers_t* drivers, const mod16_params
     plain.drv[k].scalar = r.scalar;
   }
   plain.has_r_corr = 0;
-  plain.reserved = 0;
+  plain.f32_mask = 0;
   for (int k = 0; k < 2; ++k) {
     plain.r_corr[k].ptr = nullptr; plain.r_corr[k].t_stride = plain.r_corr[k].n_stride = 0;
     plain.r_corr[k].scalar = 0.0;

@@ -409,7 +409,9 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
     big = [k for k, v in enumerate(drivers) if hostcopy.worthwhile(v)]
     if big:
         for k, t in zip(big, hostcopy.upload([drivers[k] for k in big], dev, s)):
-            if t.dtype != st.t_dtype:
+            # (a float32 array headed for the float64 entry stays float32: widened in the kernel)
+            if t.dtype != st.t_dtype and not (t.dtype == torch.float32 and
+                                              st.t_dtype == torch.float64 and prep is None):
                 t = t.to(st.t_dtype)
             drivers[k] = t
             st.keep.append(t)
@@ -434,8 +436,16 @@ def _run_on_stream(lib, s, dev, np_dtype, drivers, extra, plist, pft, table, sem
                 st.fill(slot, ps[h], T, N, len(full_shape))
     else:
         cd = _abi.Drivers()
+        mask = 0
         for k, v in enumerate(drivers):
-            st.fill(cd.drv[k], v, T, N, len(full_shape))
+            # float64 entry: a float32 driver stays float32 (widened exactly in the kernel) --
+            # the reference's stock call is float32 drivers + the float64 BPLUT
+            is32 = (np_dtype == np.dtype('float64') and not _is_scalar(v) and
+                    str(getattr(v, 'dtype', '')).replace('torch.', '') == 'float32')
+            st.fill(cd.drv[k], v, T, N, len(full_shape), keep_dtype=is32)
+            if is32 and cd.drv[k].ptr:
+                mask |= 1 << k
+        cd.f32_mask = mask
         cd.has_r_corr = 1 if r_corr_list is not None else 0
         for k, v in enumerate(extra[:2]):
             st.fill(cd.r_corr[k], v, T, N, len(full_shape))

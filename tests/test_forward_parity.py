@@ -477,3 +477,41 @@ def test_land_cover_codes_outside_the_table(cuda_lib, dtype):
     parity.assert_parity(got[:, ok], ref, dtype, what='codes inside the table')
     with pytest.raises(IndexError):
         [table[i][pft] for i in range(11)]
+
+
+@pytest.mark.gpu
+def test_stock_promotion_float32_drivers_with_float64_parameters(cuda_lib):
+    '''
+    The reference's stock call: float32 drivers from the archive + the float64 BPLUT, which
+    numpy promotes to float64.  The float64 entry reads the float32 arrays as they are
+    (`mod16_drivers_t.f32_mask`); results equal the call on float64 copies bit for bit.
+    '''
+    T, N = 9, 2052
+    d = synthetic.host_drivers(T, N, 181, dtype=np.float32, nan_frac=0.01, fill_frac=0.005)
+    drv = [d[k] for k in NAMES]
+    table = utils.bplut_table(utils.restore_bplut(utils.BPLUT_C51), MOD16.required_parameters,
+                              default_beta=250.0)
+    pft = synthetic.host_pft_map(N, 182)
+    vec = [table[i][pft].reshape(1, N) for i in range(11)]          # float64
+    got = MOD16._et(vec, *drv)                                      # promotes: float64
+    assert got.dtype == np.float64
+    assert cuda_lib.mod16_last_forward_kernel() & 0xff == _abi.KERNEL_FAST64
+    d64 = [v.astype(np.float64) if isinstance(v, np.ndarray) else v for v in drv]
+    same = MOD16._et(vec, *d64)
+    assert np.array_equal(got, same, equal_nan=True)
+    with np.errstate(all='ignore'):
+        ref = orc.static_et(vec, *d64)
+    parity.assert_parity(got, ref, np.float64, what='stock promotion')
+    # device tensors of mixed precision, instance semantics, the op-for-op kernel as well
+    dev = torch.device('cuda', 0)
+    mixed = [torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v for v in drv]
+    mixed[4] = mixed[4].double()
+    col = dict(zip(orc.PARAM_ORDER, table[:, 4]))
+    day, night = MOD16(col).evapotranspiration(*mixed, dtype=np.float64)
+    with np.errstate(all='ignore'):
+        rd, rn = orc.InstanceModel(col).evapotranspiration(*d64)
+    parity.assert_parity(day.cpu().numpy(), rd, np.float64, parity.MASS_SCALE, what='mixed day')
+    parity.assert_parity(night.cpu().numpy(), rn, np.float64, parity.MASS_SCALE, what='mixed night')
+    from mod16_b200.forward import run_forward
+    mirror = run_forward(drv, params=vec, dtype=np.float64, force=_abi.FORCE_MIRROR)[0]
+    parity.assert_parity(mirror, ref, np.float64, what='op-for-op kernel on float32 arrays')
