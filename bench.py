@@ -832,7 +832,12 @@ def secondary_lines(args, device, world, rank, drv_list, drv, pft, table, out):
 
 
 def f64_kernel_name():
-    return 'forward_fast64_kernel'
+    'The float64 kernel the LAST launch of this process used (mod16_last_forward_kernel()).'
+    from mod16_b200 import _abi
+    k = _abi.load().mod16_last_forward_kernel()
+    if k & 0xff == _abi.KERNEL_EXACT:
+        return 'forward_strided_kernel'
+    return 'forward_canon64_kernel' if (k >> 8) & 1 else 'forward_fast64_kernel'
 
 
 def main():
@@ -1011,7 +1016,7 @@ def main():
                          'kernel': {'pipe': 'forward_pipe_kernel',
                                     'generic': 'forward_strided_fast_kernel',
                                     'mirror': 'forward_strided_kernel<float>'}[args.kernel]
-                                   if np_dtype == np.float32 else f64_kernel_name(),
+                                   if np_dtype == np.float32 else kname,
                          'kernel_ms': kernel_ms, 'bytes_per_unit': bytes_per_unit},
             'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
             'clocks': clocks, 'cpu_baseline': cpu,

@@ -251,6 +251,10 @@ int mod16_last_cuda_error(void);
 #define MOD16_KERNEL_STRIDED 2
 #define MOD16_KERNEL_EXACT 3
 #define MOD16_KERNEL_FAST64 4  /* float64 entry: rearranged algebra in double */
+/* (MOD16_KERNEL_FAST64: bit 8 of the value is set when the launch took the canonical-layout
+   kernel -- every time-varying source a (T, N) array of one width and one time stride, which
+   is what the reference's loaders produce -- and clear for the general kernel, which accepts
+   any broadcast layout and arrays of both widths.  Same results, bit for bit.) */
 int mod16_last_forward_kernel(void);
 const char* mod16_error_string(int code);
 

@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 '''Writes profiles/<tag>_launches_summary.txt and profiles/<tag>_<kernel>_full.txt from the ncu
 outputs of scripts/gpu_check.sh / gpu_ncu.sh under gpurun_out/.
-usage: make_profile_summary.py <tag> <launches.csv|-> <report.ncu-rep> <units per launch> "<command>"'''
+usage: make_profile_summary.py <tag> <launches.csv|-> <report.ncu-rep> <units per launch> "<command>" [bytes per unit]
+(bytes per unit: 48 for the float32 sum, the default; 96 for the float64 entry on float64 drivers)'''
 import collections, csv, io, subprocess, sys
 tag, launches, rep, units, cmd = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4]), sys.argv[5]
+bpu = float(sys.argv[6]) if len(sys.argv) > 6 else 48.0
 if launches != '-':
     rows = list(csv.reader(l for l in open(launches) if l.startswith('"')))
     hdr = rows[0]; ik = hdr.index('Kernel Name'); iv = hdr.index('Metric Value'); ig = hdr.index('Grid Size')
@@ -38,7 +40,7 @@ kname = r[hdr.index('Kernel Name')]
 short = kname.split('<')[0].split('(')[0].split('::')[-1].replace('void ', '')
 with open('profiles/%s_%s_full.txt' % (tag, short), 'w') as f:
     f.write('ncu --set full --clock-control none --import-source on: %s\n' % cmd)
-    f.write('kernel: %s\n%.4g pixel-timesteps per launch (algorithmic bytes %.4g GB at 48 B each)\n\n' % (kname, units, units * 48 / 1e9))
+    f.write('kernel: %s\n%.4g pixel-timesteps per launch (algorithmic bytes %.4g GB at %g B each)\n\n' % (kname, units, units * bpu / 1e9, bpu))
     vals = {}
     for k in keys:
         if k in hdr:
