@@ -31,6 +31,7 @@
 // Citations are file:line under /root/reference/mod16/__init__.py.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 #include "mod16_math.cuh"
 
 namespace mod16 {
@@ -196,8 +197,85 @@ inline double d_rcp(double a) { return 1.0 / a; }
 inline double d_rsqrt(double a) { return 1.0 / sqrt(a); }
 #endif
 M16_HD double vrcp(double a) { return d_rcp(a); }
+
+// ---- exp2 / log2 of the float64 entry, for the arguments the fast algebra produces ----------
+// Inside the fast domain exp2 sees the saturation-pressure exponent (|x| < 10) and the
+// exponent of rh^(vpd/beta), which is <= 0 and may be -inf (rh clamped to exactly 0, :280-281);
+// log2 sees rh in [2e-5, ~3e3] or exactly 0 (0 < rh < 2e-5 is guarded, see guard_rh0).  Lanes
+// outside the domain are flagged and their values discarded, so nothing else has to be right.
+// Restricted to that, both are branch-free, the polynomials are evaluated pairwise (Estrin:
+// a dependent chain of 5 instead of 12 -- the kernel is latency-bound) and
+// the coefficients are compile-time constants.  They are 2-3 ulp functions, not libm's
+// < 1 ulp: measured maximum relative error 4.8e-16 (exp2, against long double) and 5.8e-16
+// (log2) over those ranges; tests/test_hostmath.py holds both below 1e-15, where the float64
+// entry promises 1e-10.  -DM16_F64_LIBM keeps the library functions (A/B builds).
+#if M16_DEV
+__device__ __forceinline__ int d_hi(double a) { return __double2hiint(a); }
+__device__ __forceinline__ int d_lo(double a) { return __double2loint(a); }
+__device__ __forceinline__ double d_make(int hi, int lo) { return __hiloint2double(hi, lo); }
+#else
+inline int d_hi(double a) { int64_t b; memcpy(&b, &a, 8); return (int)(b >> 32); }
+inline int d_lo(double a) { int64_t b; memcpy(&b, &a, 8); return (int)(b & 0xffffffffLL); }
+inline double d_make(int hi, int lo) {
+  const int64_t b = ((int64_t)hi << 32) | (int64_t)(uint32_t)lo;
+  double a; memcpy(&a, &b, 8); return a;
+}
+#endif
+constexpr double kLn2 = 0.6931471805599453094;
+constexpr double ex2_c(int k) {        // ln2^k / k!
+  double c = 1.0;
+  for (int i = 1; i <= k; ++i) c = c * kLn2 / (double)i;
+  return c;
+}
+// 2^x for x <= ~1000 (results below 2^-1021, -inf included, are returned as 0)
+M16_HD double d_exp2(double x) {
+  const double xc = fmax(x, -1021.0);
+  const double big = 6755399441055744.0;          // 1.5 * 2^52: rint(xc) in the low word
+  const double t = xc + big;
+  const double f = xc - (t - big);                // exact, |f| <= 1/2
+  constexpr double c0 = ex2_c(0), c1 = ex2_c(1), c2 = ex2_c(2), c3 = ex2_c(3), c4 = ex2_c(4),
+                   c5 = ex2_c(5), c6 = ex2_c(6), c7 = ex2_c(7), c8 = ex2_c(8), c9 = ex2_c(9),
+                   c10 = ex2_c(10), c11 = ex2_c(11), c12 = ex2_c(12);
+  const double f2 = f * f, f4 = f2 * f2, f8 = f4 * f4;
+  const double p01 = fma(f, c1, c0), p23 = fma(f, c3, c2), p45 = fma(f, c5, c4);
+  const double p67 = fma(f, c7, c6), p89 = fma(f, c9, c8), pab = fma(f, c11, c10);
+  const double q0 = fma(p23, f2, p01), q1 = fma(p67, f2, p45), q2 = fma(pab, f2, p89);
+  const double r0 = fma(q1, f4, q0), r1 = fma(f4, c12, q2);
+  const double p = fma(r1, f8, r0);               // 2^f in [0.707, 1.415]
+  // * 2^n, n = rint(xc) in the low word of t (two's complement): normal for n >= -1021
+  const double r = d_make((int)((unsigned)d_hi(p) + ((unsigned)d_lo(t) << 20)), d_lo(p));
+  return x < -1021.0 ? 0.0 : r;
+}
+constexpr double lg2_c(int k) { return (2.0 / kLn2) / (double)(2 * k + 1); }
+// log2(r) for normal positive r; log2(0) = -inf
+M16_HD double d_log2(double r) {
+  int hi = d_hi(r);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;            // mantissa in [1, 2)
+  const bool up = hi > 0x3ff6a09e;                // > sqrt(2) (top word): halve, e + 1
+  hi -= up ? 0x00100000 : 0;
+  e += up ? 1 : 0;
+  const double m = d_make(hi, d_lo(r));           // [0.7071, 1.4143)
+  const double s = (m - 1.0) * d_rcp(m + 1.0);    // |s| < 0.1716; m - 1 is exact
+  const double z = s * s, z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+  // atanh series: log2(m) = s (2 / ln2) (1 + z/3 + z^2/5 + ...), terms to z^10 (2e-17)
+  constexpr double l0 = lg2_c(0), l1 = lg2_c(1), l2 = lg2_c(2), l3 = lg2_c(3), l4 = lg2_c(4),
+                   l5 = lg2_c(5), l6 = lg2_c(6), l7 = lg2_c(7), l8 = lg2_c(8), l9 = lg2_c(9),
+                   l10 = lg2_c(10);
+  const double p01 = fma(z, l1, l0), p23 = fma(z, l3, l2), p45 = fma(z, l5, l4);
+  const double p67 = fma(z, l7, l6), p89 = fma(z, l9, l8);
+  const double q0 = fma(p23, z2, p01), q1 = fma(p67, z2, p45), q2 = fma(z2, l10, p89);
+  const double pl = fma(q2, z8, fma(q1, z4, q0));
+  const double v = fma(s, pl, (double)e);
+  return r == 0.0 ? d_make((int)0xfff00000u, 0) : v;     // -inf
+}
+#ifdef M16_F64_LIBM
 M16_HD double vex2(double a) { return exp2(a); }
 M16_HD double vlg2(double a) { return log2(a); }
+#else
+M16_HD double vex2(double a) { return d_exp2(a); }
+M16_HD double vlg2(double a) { return d_log2(a); }
+#endif
 M16_HD double vsat(double a) { return a != a ? 0.0 : (a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a)); }
 M16_HD double vsat_fma(double a, double b, double c) { return vsat(fma(a, b, c)); }
 M16_HD double vabs(double a) { return fabs(a); }

@@ -128,3 +128,14 @@ def nan_halves(params, drivers, semantics='static'):
     fn(ctypes.c_int({'static': 0, 'instance': 1}[semantics]), p(drv), p(par), ctypes.c_int64(n),
        p(h), p(g))
     return h.reshape(shape), g.reshape(shape).astype(bool)
+
+
+def exp2_log2(x):
+    '''d_exp2(x), d_log2(x) of csrc/mod16_fast.cuh (the float64 entry's own functions).'''
+    x = np.ascontiguousarray(x, np.float64).ravel()
+    ex, lg = np.empty_like(x), np.empty_like(x)
+    fn = lib().hm_exp2_log2
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    fn(x.ctypes.data, x.size, ex.ctypes.data, lg.ctypes.data)
+    return ex, lg

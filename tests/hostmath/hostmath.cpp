@@ -223,6 +223,13 @@ void hm_fast_f64(int sem, int gate, const double* drv, const double* par, const 
                  int has_rc, int64_t n, double* out, uint8_t* gpos) {
   run_fast64(sem, gate, drv, par, rc, has_rc, n, out, gpos);
 }
+// the float64 entry's own exp2 / log2 (mod16_fast.cuh: d_exp2, d_log2), element by element
+void hm_exp2_log2(const double* x, int64_t n, double* ex, double* lg) {
+  for (int64_t i = 0; i < n; ++i) {
+    ex[i] = mod16::fast::d_exp2(x[i]);
+    lg[i] = mod16::fast::d_log2(x[i]);
+  }
+}
 void hm_nan_halves(int sem, const float* drv, const double* par, int64_t n, uint8_t* h,
                    uint8_t* gpos) {
   run_nan_halves(sem, drv, par, n, h, gpos);

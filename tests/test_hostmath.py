@@ -298,3 +298,43 @@ def test_float64_fast_path_equals_the_op_for_op_code_on_a_plain_element():
         for c in range(3):
             assert abs(a[h][c] - b[h][c]) <= 1e-12 * max(abs(b[h][c]), 1.0)
     assert not a['guarded'].any()
+
+
+def test_float64_exp2_log2_against_libm():
+    '''
+    The float64 entry evaluates exp2 / log2 with its own restricted-range functions
+    (csrc/mod16_fast.cuh: d_exp2, d_log2).  Over the arguments the fast algebra can produce
+    they are 2-3 ulp functions (measured maxima against libm: 4.7e-16 for exp2, 5.8e-16 for
+    log2; held below 1e-15 here) -- five orders inside the 1e-10 the entry promises -- and
+    the special values the algebra relies on are exact: log2(0) = -inf (rh clamped to 0,
+    mod16/__init__.py:280-281), exp2(-inf) = 0, exp2(0) = 1, log2(1) = 0.
+    '''
+    rng = np.random.default_rng(77)
+    # exp2: the saturation-pressure exponent (|x| < 10) and the exponent of rh^(vpd / beta),
+    # which is <= 0 and reaches far below the underflow threshold
+    x = np.concatenate([rng.uniform(-10.0, 10.0, 200000), -rng.exponential(30.0, 200000),
+                        rng.uniform(-1021.0, -900.0, 20000), np.arange(-1021.0, 11.0),
+                        np.arange(-1021.0, 10.0) + 0.5, np.arange(-1020.0, 10.0) - 0.5])
+    ex, _ = hostmath.exp2_log2(x)
+    want = np.exp2(x)
+    rel = np.abs(ex - want) / want
+    assert rel.max() < 1e-15, rel.max()
+    # log2: rh in [2e-5, 3e3] (0 < rh < 2e-5 is guarded, negative VPD reaches ~3e3), dense
+    # around 1 and around sqrt(2) / 2, sqrt(2) where the reduction switches
+    r = np.concatenate([np.exp(rng.uniform(np.log(2e-5), np.log(3e3), 300000)),
+                        1.0 + rng.uniform(-1e-3, 1e-3, 50000), 1.0 + rng.uniform(-1e-9, 1e-9, 5000),
+                        np.sqrt(2.0) * (1.0 + rng.uniform(-1e-6, 1e-6, 5000)),
+                        np.sqrt(0.5) * (1.0 + rng.uniform(-1e-6, 1e-6, 5000)),
+                        2.0 ** np.arange(-15, 12), np.nextafter(1.0, 0.0) * np.ones(1),
+                        np.nextafter(1.0, 2.0) * np.ones(1)])
+    _, lg = hostmath.exp2_log2(r)
+    want = np.log2(r)
+    # relative where log2 is away from 0, absolute (in units of |r - 1|) next to r = 1
+    err = np.abs(lg - want) / np.maximum(np.abs(want), 1e-300)
+    assert err[want != 0].max() < 1e-15, err[want != 0].max()
+    # special values
+    ex, lg = hostmath.exp2_log2(np.array([0.0, -np.inf, -1021.0, -1021.5, -5000.0, 1.0]))
+    assert ex[0] == 1.0 and ex[1] == 0.0 and ex[2] == 2.0 ** -1021 and ex[3] == 0.0 and ex[4] == 0.0
+    assert lg[0] == -np.inf and lg[5] == 0.0
+    _, lg = hostmath.exp2_log2(2.0 ** np.arange(-14, 12))
+    assert np.array_equal(lg, np.arange(-14.0, 12.0))
