@@ -831,6 +831,13 @@ def secondary_lines(args, device, world, rank, drv_list, drv, pft, table, out):
     return lines
 
 
+def _named(name, line):
+    'A secondary line with a `name` key like the others (None stays None: non-zero ranks).'
+    if isinstance(line, dict) and 'name' not in line:
+        line = dict([('name', name)] + list(line.items()))
+    return line
+
+
 def f64_kernel_name():
     'The float64 kernel the LAST launch of this process used (mod16_last_forward_kernel()).'
     from mod16_b200 import _abi
@@ -992,9 +999,10 @@ def main():
         legs = [lambda: global_year(g_args, device, world, rank, 2, 1)]
         for wl in ('calibration', 'sobol'):
             for shard in (('draw', 'site') if (world > 1 and wl == 'calibration') else ('draw',)):
-                legs.append(lambda wl=wl, shard=shard: objective_bench(
-                    wl, dev=device, world=world, rank=rank, shard=shard, steps=3, warm=2,
-                    cpu_draws=1 if world == 1 else 0))
+                legs.append(lambda wl=wl, shard=shard: _named(
+                    'objective batch (K2), %s workload, sharded by %s' % (wl, shard),
+                    objective_bench(wl, dev=device, world=world, rank=rank, shard=shard,
+                                    steps=3, warm=2, cpu_draws=1 if world == 1 else 0)))
         for leg in legs:
             res = leg()
             torch.cuda.empty_cache()
