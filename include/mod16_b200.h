@@ -285,12 +285,14 @@ int mod16_forward_f64(const mod16_drivers_t* drivers, const mod16_params_t* para
  * NSE = 1 - sse / sum((obs - mean(obs))^2) with unit weights.
  *
  * The static path's batch-global transpiration gate `if np.any(g_surf > 0)` (:343) is
- * evaluated PER DRAW over the elements that enter its sums, as one reference call per draw
- * on the NaN-filtered drivers would (mod16/calibration.py:887-891 removes the rows without an
- * observation before the model sees them) (MOD16_GATE_GLOBAL); MOD16_GATE_OPEN /
+ * evaluated PER DRAW over EVERY element of the (T, N) block, with or without an observation or
+ * weight, as one reference call per draw does: `_et` sees whatever drivers it is handed, and
+ * missing observations are masked afterwards in the score (mod16/calibration.py:224-227; the
+ * default calibration run leaves them in place, :355-370, the k-fold branch :895-901 and
+ * mod16/sensitivity.py:179-186 remove those rows first) (MOD16_GATE_GLOBAL); MOD16_GATE_OPEN /
  * MOD16_GATE_CLOSED fix it.  Elements whose drivers make the prediction NaN for every draw
- * (masked pixels) count like missing observations.  r_corr_list is not supported.  All
- * reductions are deterministic (no floating-point atomics).
+ * (masked pixels) enter no sum, like missing observations.  r_corr_list is not supported.
+ * All reductions are deterministic (no floating-point atomics).
  */
 typedef struct mod16_objective {
   const double* draws;     /* device (D, 11) row-major, order of required_parameters */
@@ -298,7 +300,8 @@ typedef struct mod16_objective {
   mod16_driver_t weights;  /* residual weights; ptr NULL: the scalar (1.0 = unweighted) */
   double* sse;             /* device (D,), overwritten */
   double* count;           /* device (D,), overwritten */
-  int32_t* gate;           /* device (D,) or NULL: 1 where any g_surf > 0 for the draw */
+  int32_t* gate;           /* device (D,) or NULL: 1 where any g_surf > 0 for the draw
+                              (over every element, see above) */
   void* workspace;         /* device scratch, 256-byte aligned */
   int64_t workspace_bytes; /* >= mod16_objective_workspace_bytes(T, N, D, f32) */
   double* raw;             /* device (D, 5) or NULL: the un-gated statistics sse_open, n_open,

@@ -118,7 +118,9 @@ obj_classify_kernel(const __grid_constant__ ObjArgs<float> a) {
       c = obj::make_elem_rec(in, (float)ob, (float)w, r) ? 1 : 2;
       if (c == 2) {
         // masked (NaN) drivers: the prediction is NaN for every draw, so the pair is not
-        // valid for any of them -- same as a missing observation
+        // valid for any of them -- same as a missing observation.  (Elements dropped here
+        // still belong to each draw's `_et` call and so to its gate, :343: the exact
+        // kernel's passes over ALL elements evaluate their g_surf, see objective_exact_kernel.)
         fast::PftConstV<float> sane;
         sane.tmin_bias = -26.5f; sane.inv_dtmin = 0.1f; sane.vpd_off = 3.0f;
         sane.inv_dvpd = 1e-3f; sane.csl = 0.0f; sane.ok = 1.0f;
@@ -395,9 +397,20 @@ objective_exact_kernel(const __grid_constant__ ObjArgs<R> a, const int mode) {
       Drivers<double> dr;
       double ob, w;
       load_element<R>(a, e, dr, ob, w);
-      if (!(ob == ob) || !(w == w)) continue;
       Half<double> day, night;
       bool g_pos;
+      if (!(ob == ob) || !(w == w)) {
+        // No valid pair -- but the element is part of the draw's `_et` call, so its g_surf
+        // takes part in the batch-global gate `np.any(g_surf > 0)` (:343) like any other.
+        // Only the passes over ALL elements see it (mode 1 walks the compacted list of
+        // valid elements; a draw no valid element opens is redone by mode 2, see the
+        // reduce kernel), and only a thread that has not seen an open gate yet needs it.
+        if (SEM == SEM_STATIC && mode != 1 && a.gate_mode == 0 && acc[4] == 0.0) {
+          pixel_step<double, SEM>(dr, q, false, GATE_OPEN, day, night, g_pos);
+          if (g_pos) acc[4] = 1.0;
+        }
+        continue;
+      }
       pixel_step<double, SEM>(dr, q, false, GATE_OPEN, day, night, g_pos);
       const double tn = half_total<double, SEM>(night);
       const double x_o = ((half_total<double, SEM>(day) + tn) - ob) * w;   // :193
@@ -470,8 +483,13 @@ objective_reduce_kernel(const __grid_constant__ ObjArgs<float> a, const int is_s
     sse_o += p[0]; n_o += p[1]; sse_c += p[2]; n_c += p[3];
     any = any || p[4] > 0.0;
   }
-  // the fast kernel did not accumulate the sums this draw's gate selects: exact kernel
-  if (use_fast && fast_mode == 0 && is_static && a.gate_mode == 0 && !any) bad = true;
+  // No valid element opened this draw's gate.  Two reasons to hand it to the exact kernel's
+  // pass over ALL elements (mode 2): in MODE 0 the fast kernel did not accumulate the sums a
+  // closed gate selects; and in every mode the elements dropped at classification (missing
+  // observation or weight, masked drivers) are part of the draw's `_et` call and may still
+  // open its gate (:343) -- only that pass sees them.  Such draws are rare (csl == 0, or a
+  // Tmin ramp above every Tmin), so the pass costs nothing measurable.
+  if (use_fast && is_static && a.gate_mode == 0 && !any) bad = true;
   double sse, cnt;
   int gate;
   finish_draw(a.gate_mode, is_static != 0, sse_o, n_o, sse_c, n_c, any, sse, cnt, gate,

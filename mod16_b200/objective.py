@@ -52,12 +52,17 @@ class ObjectiveBackend(object):
     semantics : 'static' (``_et``, W m-2) or 'instance' (day + night of
         ``evapotranspiration()``, kg m-2 s-1)
     gate : 'global' -- each draw gets the batch-global transpiration gate of ITS call, as in
-        the reference (:343) --, 'open' or 'closed'.  The gate of a draw is taken over the
-        elements that enter its sums, i.e. those with an observation and a weight: both
-        reference callers drop the elements without an observation BEFORE the model sees
-        them (mod16/calibration.py:895-900 ``d.copy()[~np.isnan(tower_obs)]``,
-        mod16/sensitivity.py:179-186 ``drivers = [d[mask] for d in drivers]``), so their
-        ``np.any(g_surf > 0)`` never covers such elements either.
+        the reference (:343) --, 'open' or 'closed'.  The gate of a draw is taken over EVERY
+        element handed in, with or without an observation or weight: the reference evaluates
+        ``np.any(g_surf > 0)`` inside ``_et`` on whatever drivers it is given and masks the
+        missing observations afterwards, in the score (calibration.py:224-227).  Its default
+        calibration run hands ``_et`` the drivers with NaN observations in place
+        (``_load_data``, calibration.py:355-370: validation days are set to NaN, nothing is
+        removed); the k-fold branch (calibration.py:895-901) and the sensitivity loader
+        (sensitivity.py:179-186) remove those elements first, in which case there is nothing
+        to tell apart.  Elements without a valid pair cost nothing on the fast path: only a
+        draw that no valid element opens (csl == 0, a Tmin ramp above every Tmin) is
+        re-evaluated over all of them.
     dtype : np.float32 (fast path) or np.float64; default follows numpy promotion
     '''
 

@@ -223,6 +223,60 @@ def test_objective_batch_per_draw_gate(cuda_lib, dtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('mask', ['observation', 'weight'])
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_objective_batch_gate_sees_elements_without_an_observation(cuda_lib, dtype, mask):
+    '''
+    `np.any(g_surf > 0)` (mod16/__init__.py:343) runs over every element of the draw's `_et`
+    call; the observation mask is applied afterwards, in the score (calibration.py:224-227).
+    So an element WITHOUT a valid observation (or weight) still opens the gate.  Constructed
+    case: two draws whose Tmin ramp opens on the five warmest-Tmin elements only, and exactly
+    those five have no observation (second configuration: a valid observation but no weight).
+    Every valid element then has g_surf == 0, yet the reference keeps its cuticular
+    transpiration: its score is the open gate's, which differs from the closed gate's.
+    '''
+    from mod16_b200.objective import ObjectiveBackend, finish_raw
+    T, N, D = 9, 257, 24
+    drv, d64, draws, obs, w = _problem(T, N, D, 61, dtype=dtype, fixed=False, obs_nan=0.2)
+    obs, w = obs.copy(), w.copy()
+    tmin_c = np.asarray(d64[NAMES.index('tmin')], np.float64) - 273.15
+    order = np.argsort(tmin_c, axis=None)
+    top = np.unravel_index(order[-5:], tmin_c.shape)
+    thr = 0.5 * (tmin_c.flat[order[-6]] + tmin_c.flat[order[-5]])
+    assert tmin_c.flat[order[-5]] - tmin_c.flat[order[-6]] > 1e-3      # a clean threshold
+    k_a, k_b, k_closed = 4, 9, 13
+    for k in (k_a, k_b):
+        draws[k, 0], draws[k, 1] = thr, thr + 10.0      # tmin_close, tmin_open [deg C]
+        draws[k, 2], draws[k, 3] = 650.0, 1.0e5         # vpd_open, vpd_close: never closes
+        assert draws[k, 7] > 0                          # csl
+    draws[k_closed, 7] = 0.0                            # csl = 0: closed on every element
+    if mask == 'observation':
+        obs[top] = np.nan
+        assert np.isfinite(w[top]).all()
+    else:
+        obs[top] = 100.0                                # valid: the weight alone drops them
+        w[top] = np.nan
+    ref = {}
+    for gate in ('global', 'open', 'closed'):
+        ref[gate] = _reference_stats(d64, draws, obs, w, gate=gate)
+    for k in (k_a, k_b):
+        # the case discriminates: open and closed gates give different scores, and the
+        # reference's (global) gate is the open one
+        assert ref['global'][0][k] == ref['open'][0][k]
+        assert abs(ref['open'][0][k] - ref['closed'][0][k]) > 1e-3 * ref['open'][0][k]
+    assert ref['global'][0][k_closed] == ref['closed'][0][k_closed]
+    backend = ObjectiveBackend(drv, obs, w, dtype=dtype)
+    sse, cnt, g = backend(draws, return_gate=True)
+    _check(sse, cnt, ref['global'][0], ref['global'][1], ref['global'][2], dtype)
+    assert g[k_a] and g[k_b] and not g[k_closed]
+    # the un-gated statistics (the site-sharded form) carry the same gate
+    s2, c2, g2 = finish_raw(backend(draws, raw=True))
+    _check(s2.cpu().numpy(), c2.cpu().numpy(), ref['global'][0], ref['global'][1],
+           ref['global'][2], dtype)
+    assert np.array_equal(g2.cpu().numpy().astype(bool), np.asarray(g, bool))
+
+
+@pytest.mark.gpu
 def test_objective_batch_degenerate_draws_and_small_batches(cuda_lib):
     from mod16_b200.objective import objective_batch
     T, N, D = 11, 200, 48
@@ -298,8 +352,9 @@ def test_raw_statistics_and_site_sharding_on_one_gpu(cuda_lib, dtype):
     sse, cnt, gate = whole(draws, return_gate=True)
     raw = whole(draws, raw=True)
     s2, c2, g2 = finish_raw(raw)
-    # (a draw whose gate is closed takes the double kernel in the plain call and the float
-    # kernel's closed sums in the raw call: equal to float32 rounding, not bit for bit)
+    # (a draw no valid element opens is redone by the double kernel's pass over all elements
+    # in both calls -- only that pass sees the elements without an observation, which are
+    # part of the gate; the tolerance is kept for the other draws of the float32 raw call)
     assert np.allclose(s2.cpu().numpy(), sse, rtol=1e-6 if dtype == np.float32 else 0, atol=0)
     assert np.array_equal(c2.cpu().numpy(), cnt)
     assert np.array_equal(g2.cpu().numpy(), gate) and not gate[3]
