@@ -376,3 +376,48 @@ def test_scaled_int16_output(cuda_lib, semantics):
         1.0 if semantics == 'static' else parity.MASS_SCALE), rtol=1e-5)
     with pytest.raises(ValueError):
         run_forward(drv, params=col, out_mode='sum_i16')
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_a_stream_that_is_not_the_current_one(cuda_lib, dtype):
+    '''
+    `stream=` with numpy inputs: the staging copies, the launch and the read-back of one call
+    must all be ordered on THAT stream (they ran on the current stream
+    while the kernel ran on the given one, so the kernel could start before its inputs had
+    landed and the read-back could overtake it).  The current stream is kept busy while the
+    call is made on a side stream; results must equal the default-stream call bit for bit --
+    as numpy arrays, as device tensors, and with the stream given as a raw handle.
+    '''
+    dev = torch.device('cuda', 0)
+    T, N = 12, 300000                      # ~170 MB of pageable host arrays to stage
+    d = synthetic.host_drivers(T, N, 71, dtype=dtype, nan_frac=0.001, fill_frac=0.001)
+    drv = [d[k] for k in NAMES]
+    table, pft = _table(), synthetic.host_pft_map(N, 72)
+    kw = dict(pft=pft, table=table, dtype=dtype, gate='global')
+    want = run_forward(drv, **kw)[0]
+    view = np.int32 if np.dtype(dtype) == np.float32 else np.int64
+
+    def busy():
+        'Queues ~100 ms of work on the current stream.'
+        a = torch.randn(4096, 4096, device=dev)
+        for _ in range(40):
+            a = a @ a
+            a = a / a.abs().max()
+        return a
+
+    side = torch.cuda.Stream(device=dev)
+    for handle in (side, side.cuda_stream):
+        keep = busy()
+        got = run_forward(drv, stream=handle, **kw)[0]          # numpy in, numpy out
+        assert np.array_equal(got.view(view), want.view(view))
+        keep = busy()
+        t = run_forward(drv, stream=handle, as_torch=True, **kw)[0]
+        side.synchronize()                                      # the caller's contract
+        assert np.array_equal(t.cpu().numpy().view(view), want.view(view))
+        del keep
+    torch.cuda.synchronize()
+    # and the reference-facing call (keyword passed through MOD16._et_by_pft)
+    keep = busy()
+    got = MOD16._et_by_pft(table, pft, *drv, dtype=dtype, stream=side)
+    assert np.array_equal(got.view(view), want.view(view))
+    del keep
