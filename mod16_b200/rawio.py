@@ -3,7 +3,7 @@ Drivers in their storage formats.
 
 The reference's loaders convert the archive's integer products to floating point on the host
 before they call the model -- ``fpar /= 100``, ``lai /= 10`` (mod16/calibration.py:422-423,
-mod16/sensitivity.py:172-173: MOD15 stores fPAR in percent and LAI in tenths, one byte each),
+mod16/sensitivity.py:167-168: MOD15 stores fPAR in percent and LAI in tenths, one byte each),
 ``vpd_night = np.where(vpd_night < 0, 0, vpd_night)`` (calibration.py:401), ``pressure =
 MOD16.air_pressure(elevation)`` (calibration.py:405-408) -- and hand over 48 bytes per
 pixel-timestep.  ``RawDriver`` passes the stored integers instead; the fused kernel applies
