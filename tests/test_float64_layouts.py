@@ -10,7 +10,9 @@ dispatch between them (bit 8 of mod16_last_forward_kernel(): canonical-layout ke
   the instance semantics of this algebra are pinned to the oracle in test_forward_parity.py);
 * a pixel range of a wider array stays canonical, a (T, 1) broadcast driver does not;
 * a scalar driver that is not a float32 value keeps float32 arrays off the all-float32 kernel;
-* `r_corr_list` (two more sources) on both kernels.
+* `r_corr_list` (two more sources) on both kernels;
+* both kernels on elements placed 1e-13 ... 1e-7 on either side of every switch of the model
+  (tests/switch_cases.py), against the oracle.
 '''
 import os
 
@@ -155,3 +157,41 @@ def test_r_corr_list_on_both_kernels(cuda_lib):
     with np.errstate(all='ignore'):
         ref = orc.static_et(vec, *_d64(d32), r_corr_list=rc)
     parity.assert_parity(got[0], ref, np.float64, what='r_corr_list, float32 drivers')
+
+
+@pytest.mark.parametrize('semantics', ['static', 'instance'])
+def test_float64_kernels_at_the_discontinuities(cuda_lib, semantics):
+    '''
+    tests/switch_cases.py: elements 1e-13 ... 1e-7 on both sides of every switch of the model
+    (rh = 0.7, rh -> 0+, rh >= 1, |G| = 0.39 |A|, A_day = 0, the night soil-radiation
+    condition, the 5 K day-night switch, the annual-temperature window, the ramp ends).  The
+    host build of the same algebra is held to the oracle in tests/test_hostmath.py; here the
+    CUDA kernels are -- the canonical-layout kernel and the general one, whose reciprocals
+    are the hardware-seeded ones -- on the same elements laid out as a (T, N) block, so that
+    the time loop and the input ring take part.  Per-element gate, all six components.
+    '''
+    import switch_cases
+    drv, groups, grp, off = switch_cases.build(semantics)
+    T = 40
+    N = drv[0].size // T
+    assert T * N == drv[0].size
+    blk = [np.ascontiguousarray(v.reshape(T, N)) for v in drv]
+    day, night, scale = switch_cases.reference(semantics, blk)
+    kw = dict(params=switch_cases.BPLUT7, semantics=semantics, out_mode='components',
+              gate='element', dtype=np.float64)
+    canon = run_forward(blk, **kw)
+    assert _kernel(cuda_lib) == (_abi.KERNEL_FAST64, CANON)
+    with _general_kernel():
+        general = run_forward(blk, **kw)
+        assert _kernel(cuda_lib) == (_abi.KERNEL_FAST64, 0)
+    assert _same_bits(canon, general)
+    for c in range(3):
+        parity.assert_parity(canon[c], day[c], np.float64, scale, what='day %d' % c)
+        parity.assert_parity(canon[3 + c], night[c], np.float64, scale, what='night %d' % c)
+    # and the summed outputs of the same block (float64 arrays only: float32 cannot hold
+    # offsets of 1e-13)
+    tot = (day[0] + day[1] + day[2]) + (night[0] + night[1] + night[2])
+    kw['out_mode'] = 'sum' if semantics == 'static' else 'day_night'
+    got = run_forward(blk, **kw)
+    got = got[0] if semantics == 'static' else got[0] + got[1]
+    parity.assert_parity(got, tot, np.float64, scale, what='total')

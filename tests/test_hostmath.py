@@ -338,3 +338,31 @@ def test_float64_exp2_log2_against_libm():
     assert lg[0] == -np.inf and lg[5] == 0.0
     _, lg = hostmath.exp2_log2(2.0 ** np.arange(-14, 12))
     assert np.array_equal(lg, np.arange(-14.0, 12.0))
+
+
+@pytest.mark.parametrize('semantics', ['static', 'instance'])
+def test_float64_fast_path_at_the_discontinuities(semantics):
+    '''
+    Elements placed on both sides of every switch of the model, 1e-13 ... 1e-7 away
+    (tests/switch_cases.py lists them).  The float64 fast path -- its guards, and since round
+    2 its own exp2 / log2 -- must stay within 1e-10 of the oracle on all of them.
+    '''
+    import switch_cases
+    drv, groups, grp, off = switch_cases.build(semantics)
+    r = hostmath.forward(BPLUT7, drv, semantics, 'element', dtype=np.float64, fast=True)
+    day, night, scale = switch_cases.reference(semantics, drv)
+    assert np.isfinite(day[0] + day[1] + day[2]).mean() > 0.95     # a test of values, not NaNs
+    for c in range(3):
+        parity.assert_parity(r['day'][c], day[c], np.float64, scale, what='day %d' % c)
+        parity.assert_parity(r['night'][c], night[c], np.float64, scale, what='night %d' % c)
+    tot = (day[0] + day[1] + day[2]) + (night[0] + night[1] + night[2])
+    parity.assert_parity(r['tot'], tot, np.float64, scale, what='total')
+    # the guards are narrow: close to a guarded switch most elements take the op-for-op
+    # detour, 1e-8 away none does; exact comparisons and continuous ramps need none
+    g = r['guarded'].reshape(-1)
+    near, far = np.abs(off) <= 3e-10, np.abs(off) >= 1e-8
+    for name in ('rh07', 'g_day', 'g_night', 'a_zero'):
+        m = grp == groups.index(name)
+        assert g[m & near].mean() > 0.4 and g[m & far].mean() < 0.05, name
+    for name in ('rh1', 'soil_n', 'dt5', 'tann_hi', 'tann_lo', 'tmin_lo', 'tmin_hi', 'vpd_lo'):
+        assert g[grp == groups.index(name)].mean() == 0.0, name
