@@ -118,7 +118,14 @@ enum {
 #define MOD16_OUT_MASK 0xF0u
 /* the static path's batch-global transpiration gate `if np.any(g_surf > 0)` (:343) */
 #define MOD16_GATE_GLOBAL 0x000u     /* call-exact: optimistic pass + device-side fix-up */
-#define MOD16_GATE_ELEMENT 0x100u    /* predicate per element (a loop of scalar calls) */
+#define MOD16_GATE_ELEMENT 0x100u    /* predicate per element (a loop of scalar calls).  With it
+                                        g_surf = 0+ is a switch of each element (the cuticular
+                                        transpiration appears): the fast paths hand elements
+                                        within rounding of a zero of the Tmin / VPD ramps to
+                                        the op-for-op code.  float32, static path: runs on the
+                                        strided kernel (MOD16_KERNEL_STRIDED), and
+                                        mod16_forward_raw_f32 answers MOD16_ERR_LAYOUT
+                                        (convert, then mod16_forward_f32) */
 #define MOD16_GATE_OPEN 0x200u       /* always compute transpiration */
 #define MOD16_GATE_CLOSED 0x300u     /* transpiration = 0 */
 #define MOD16_GATE_OPEN_TRACK 0x400u /* GATE_OPEN, and OR the predicate into *gate_flag */

@@ -488,6 +488,11 @@ constexpr float kGuard = 1.0e-4f;
 template <class S> M16_HD S guard_width();
 template <> M16_HD float guard_width<float>() { return kGuard; }
 template <> M16_HD double guard_width<double>() { return 1.0e-9; }
+// Relative width of the guard around a ramp's zero (per-element gate only, ramp_zero_need): the
+// ramp's two terms are rounded coefficients times inputs, ~3 roundings of their common size
+template <class K> M16_HD K ramp_guard();
+template <> M16_HD float ramp_guard<float>() { return 1.0e-6f; }
+template <> M16_HD double ramp_guard<double>() { return 1.0e-12; }
 template <class S> M16_HD S guard_rh0();
 template <> M16_HD float guard_rh0<float>() { return 1.0e-3f; }
 template <> M16_HD double guard_rh0<double>() { return 1.0e-5; }
@@ -745,14 +750,38 @@ M16_HD typename MaskOf<V>::type step_core(const StepInV<V>& in, V tc_d, V tc_n,
   o.tot = o.tot_day + o.tot_night;
   return need;
 }
+// Evaluated per element, the gate (:343) makes g_surf = 0+ a switch of its own: the cuticular
+// transpiration appears as soon as both ramps (:325-326) are positive.  Their one-FMA forms
+// are differences of numbers of the size of tmin_bias / vpd_off, so within rounding of a
+// ramp's zero the sign -- and with it the element's gate -- is the double code's to decide.
+// (Under a batch-global gate an element's own outputs are continuous at these points; only
+// its vote in any(g_surf > 0) is not: DESIGN.md 3.1.)
+// A function of the raw inputs, called BEFORE the step's arithmetic: a branch inside
+// step_core splits its basic block, changes which products are fused with their sums, and
+// the kernels that have the guard then differ from the one that has not by an ulp.
+template <class V, int SEM>
+M16_HD typename MaskOf<V>::type ramp_zero_need(const StepInV<V>& in, const PftConstV<V>& c,
+                                               int gate) {
+  typedef typename ScalarOf<V>::type K;
+  if (SEM != SEM_STATIC || gate != GATE_ELEMENT) return mask_splat<V>(false);
+  const V ut = vfma(in.tmin, c.inv_dtmin, c.tmin_bias);
+  const V uv = vfma(-in.vpd_d, c.inv_dvpd, c.vpd_off);
+  return mor(vlt(vabs(ut), ramp_guard<K>() * vabs(c.tmin_bias)),
+             vlt(vabs(uv), ramp_guard<K>() * vabs(c.vpd_off)));
+}
+
+// (The pipelined kernel calls step_core itself and has no ramp-zero guard: at its register
+// limit the extra live values cost ten instructions per pair of steps on every path.  Static
+// launches with the per-element gate take the strided kernel, see pipe_variant.)
 template <class V, int SEM, bool HAS_RC>
 M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,
                                           const PixConstV<V>& x, int gate, StepOutV<V>& o,
                                           typename MaskOf<V>::type& g_pos, V& gs_day,
                                           V& nan_probe) {
+  const typename MaskOf<V>::type rz = ramp_zero_need<V, SEM>(in, c, gate);
   const V tc_d = celsius_b<V>(in.t_d), tc_n = celsius_b<V>(in.t_n);
   const typename MaskOf<V>::type bad = mnot(mand(x.ok, in_domain<V>(in, tc_d, tc_n, nan_probe)));
-  return mor(bad, step_core<V, SEM, HAS_RC>(in, tc_d, tc_n, c, x, gate, o, g_pos, gs_day));
+  return mor(mor(bad, rz), step_core<V, SEM, HAS_RC>(in, tc_d, tc_n, c, x, gate, o, g_pos, gs_day));
 }
 template <class V, int SEM, bool HAS_RC>
 M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,

@@ -155,6 +155,9 @@ static bool dense_tn(const Arr<float>& d, int64_t T, int64_t N, int esize = 4) {
 // Returns the EXTRA variant (mod16_forward_pipe.cuh), or -1.
 static int pipe_variant(const ForwardArgs<float>& a, uint32_t flags) {
   if (a.N % 4 != 0 || a.has_rc) return -1;
+  // the per-element gate of the static path needs the guard at the zeros of the Tmin / VPD
+  // ramps (fast::ramp_zero_need in step_fast), which the pipelined kernel is built without
+  if ((flags & MOD16_SEM_MASK) == MOD16_SEM_STATIC && a.gate == GATE_ELEMENT) return -1;
   if (a.raw_fmt != 0) {  // storage formats: the eleven per-step arrays in the format's types
     static const int order[] = {
         MOD16_D_LW_NET_DAY, MOD16_D_LW_NET_NIGHT, MOD16_D_SW_RAD_DAY, MOD16_D_SW_ALBEDO,

@@ -11,11 +11,13 @@ NAMES = list(synthetic.DRIVER_NAMES)
 BPLUT7 = [-8., 8.8, 650., 4400., .02, .02, 1e-5, .0055, 60., 95., 250.]
 
 
-def build(semantics):
+def build(semantics, dtype=np.float64):
     '''
     Returns (drivers as fourteen (1, n) float64 arrays, group names, group index per element,
     offset per element).  Offsets are 1e-13 ... 1e-7 on both sides (below 1e-13 the
-    reference's own rounding picks the side).  Groups: the f_wet jump at rh = 0.7 (:282),
+    reference's own rounding picks the side); with ``dtype=np.float32`` they are 1e-8 ... 1e-3
+    and every array is rounded to float32 afterwards -- the smallest offsets then fall within
+    rounding of the switch, which is where the float32 path must hand over to its double code.  Groups: the f_wet jump at rh = 0.7 (:282),
     rh -> 0+ and rh == 0 (:281), rh == 1 and rh > 1 (negative VPD), |G| = 0.39 |A| on both
     half-days (:240), A_day = 0, the night condition of the soil radiation (:248-252; the day
     condition :245-247 cannot be reached once |G| <= 0.39 |A|), the 5 K day-night switch and
@@ -23,7 +25,10 @@ def build(semantics):
     ramps (:325-326) and of the r_tot ramp (:357-361).  Parameters: BPLUT7 for every element.
     '''
     rng = np.random.default_rng(2024)
-    eps = np.array([1e-13, 1e-12, 1e-11, 1e-10, 3e-10, 1e-9, 3e-9, 1e-8, 1e-7])
+    if np.dtype(dtype) == np.float64:
+        eps = np.array([1e-13, 1e-12, 1e-11, 1e-10, 3e-10, 1e-9, 3e-9, 1e-8, 1e-7])
+    else:
+        eps = np.array([1e-8, 1e-7, 3e-7, 1e-6, 4e-6, 1e-5, 3e-5, 1e-4, 1e-3])
     offs = np.concatenate([eps, -eps])
     per = 40                                            # elements per (group, offset)
     groups = ['rh07', 'rh0', 'rh1', 'g_day', 'g_night', 'a_zero', 'soil_n', 'dt5', 'tann_hi',
@@ -89,13 +94,17 @@ def build(semantics):
         m = sel(name)
         d['vpd_day'][m] = base * (1.0 + off[m])
         d['vpd_night'][m] = base * (1.0 - off[m])
-    drv = [d[k].reshape(1, n) for k in NAMES]
+    drv = [d[k].reshape(1, n).astype(dtype) for k in NAMES]
     return drv, groups, grp, off
 
 
 def reference(semantics, drv):
-    'Oracle components (day, night) of `drv` with the per-element gate, and the mass scale.'
+    '''
+    Oracle components (day, night) of `drv` with the per-element gate, and the mass scale;
+    float32 drivers are evaluated on their float64 values.
+    '''
     import parity
+    drv = [np.asarray(v, np.float64) for v in drv]
     p = dict(zip(orc.PARAM_ORDER, BPLUT7))
     with np.errstate(all='ignore'):
         if semantics == 'static':

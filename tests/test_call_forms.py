@@ -421,3 +421,53 @@ def test_a_stream_that_is_not_the_current_one(cuda_lib, dtype):
     got = MOD16._et_by_pft(table, pft, *drv, dtype=dtype, stream=side)
     assert np.array_equal(got.view(view), want.view(view))
     del keep
+
+
+@pytest.mark.parametrize('semantics', ['static', 'instance'])
+def test_float32_kernels_at_the_discontinuities(cuda_lib, semantics):
+    '''
+    tests/switch_cases.py in float32: elements 1e-8 ... 1e-3 on both sides of every switch of
+    the model, rounded to float32, laid out as a (T, N) block.
+
+    * Per-element gate: with it the zeros of the Tmin and VPD ramps are switches too (g_surf
+      = 0+ turns the cuticular transpiration on, mod16/__init__.py:343-348).  The static path
+      then runs on the strided kernel, whose guards cover them (the pipelined kernel is built
+      without that guard); the instance path has no gate and stays on the pipeline.
+    * Batch-global gate (the reference's `_et`): the pipelined kernel, every component.
+    All against the float64 oracle on the same float32 inputs, 1e-5 relative / 1e-3 W m-2.
+    '''
+    import switch_cases
+    drv, groups, grp, off = switch_cases.build(semantics, np.float32)
+    T = 40
+    N = drv[0].size // T                  # 252: a multiple of 4, streamable
+    blk = [np.ascontiguousarray(v.reshape(T, N)) for v in drv]
+    day, night, scale = switch_cases.reference(semantics, blk)
+    kw = dict(params=switch_cases.BPLUT7, semantics=semantics, dtype=np.float32)
+    # all six components (with time-varying annual temperature and pressure that output is
+    # the strided kernel's in any case)
+    got = run_forward(blk, gate='element', out_mode='components', **kw)
+    assert _kernel(cuda_lib)[0] == _abi.KERNEL_STRIDED
+    for c in range(3):
+        parity.assert_parity(got[c], day[c], np.float32, scale, what='element gate, day %d' % c)
+        parity.assert_parity(got[3 + c], night[c], np.float32, scale,
+                             what='element gate, night %d' % c)
+    # day / night totals: a layout the pipeline streams -- and takes, except for the static
+    # path under the per-element gate
+    td, tn = day[0] + day[1] + day[2], night[0] + night[1] + night[2]
+    got = run_forward(blk, gate='element', out_mode='day_night', **kw)
+    assert _kernel(cuda_lib)[0] == (_abi.KERNEL_STRIDED if semantics == 'static'
+                                    else _abi.KERNEL_PIPE)
+    parity.assert_parity(got[0], td, np.float32, scale, what='element gate, day total')
+    parity.assert_parity(got[1], tn, np.float32, scale, what='element gate, night total')
+    if semantics == 'static':
+        # the reference's own gate: open for the whole block (some element transpires)
+        with np.errstate(all='ignore'):
+            gday, gnight = orc.static_evapotranspiration(
+                switch_cases.BPLUT7, *[np.asarray(v, np.float64) for v in blk], gate='global',
+                components=True)
+        got = run_forward(blk, gate='global', out_mode='day_night', **kw)
+        assert _kernel(cuda_lib)[0] == _abi.KERNEL_PIPE
+        parity.assert_parity(got[0], gday[0] + gday[1] + gday[2], np.float32, scale,
+                             what='global gate, day total')
+        parity.assert_parity(got[1], gnight[0] + gnight[1] + gnight[2], np.float32, scale,
+                             what='global gate, night total')

@@ -364,5 +364,38 @@ def test_float64_fast_path_at_the_discontinuities(semantics):
     for name in ('rh07', 'g_day', 'g_night', 'a_zero'):
         m = grp == groups.index(name)
         assert g[m & near].mean() > 0.4 and g[m & far].mean() < 0.05, name
-    for name in ('rh1', 'soil_n', 'dt5', 'tann_hi', 'tann_lo', 'tmin_lo', 'tmin_hi', 'vpd_lo'):
+    for name in ('rh1', 'soil_n', 'dt5', 'tann_hi', 'tann_lo', 'tmin_hi', 'vpd_lo'):
         assert g[grp == groups.index(name)].mean() == 0.0, name
+    # the zero of a ramp (Tmin at tmin_close, VPD at vpd_close): under the per-element gate of
+    # the static path g_surf = 0+ switches the cuticular transpiration on, so it is guarded
+    # (1e-12 of the ramp's terms in double); the instance path has no gate and needs none
+    for name in ('tmin_lo', 'vpd_hi'):
+        m = grp == groups.index(name)
+        if semantics == 'static':
+            # (the VPD ramp's guard ends at |off| = 1e-12 exactly: asserted one decade inside)
+            assert g[m & (np.abs(off) <= 1e-13)].all() and not g[m & (np.abs(off) >= 1e-9)].any(), name
+        elif name == 'tmin_lo':
+            assert not g[m].any(), name
+
+
+@pytest.mark.parametrize('fast', [True, 'pair'])
+@pytest.mark.parametrize('semantics', ['static', 'instance'])
+def test_float32_fast_path_at_the_discontinuities(semantics, fast):
+    '''
+    The same switches for the float32 kernels' math (scalar and packed-pair instantiations),
+    offsets 1e-8 ... 1e-3 rounded to float32: 1e-5 relative / 1e-3 W m-2 against the float64
+    oracle on the same float32 inputs, components and totals.
+    '''
+    import switch_cases
+    drv, groups, grp, off = switch_cases.build(semantics, np.float32)
+    r = hostmath.forward(BPLUT7, drv, semantics, 'element', dtype=np.float32, fast=fast)
+    day, night, scale = switch_cases.reference(semantics, drv)
+    for c in range(3):
+        parity.assert_parity(r['day'][c], day[c], np.float32, scale, what='day %d' % c)
+        parity.assert_parity(r['night'][c], night[c], np.float32, scale, what='night %d' % c)
+    td, tn = day[0] + day[1] + day[2], night[0] + night[1] + night[2]
+    parity.assert_parity(r['tot_day'], td, np.float32, scale, what='day total')
+    parity.assert_parity(r['tot_night'], tn, np.float32, scale, what='night total')
+    g = r['guarded'].reshape(-1)
+    print('guarded fraction at the discontinuities, float32 (%s, %s): %.3f' % (
+        semantics, fast, g.mean()))
