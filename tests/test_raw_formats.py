@@ -257,3 +257,35 @@ def test_vpd_from_mixing_ratio_and_surface_pressure(cuda_lib, N):
     gd, gn = run_forward(drv, params=col, out_mode='day_night', surface_pressure=(ps_d, ps_n),
                          prep=('vpd_night_clamp',))
     assert np.abs(gd - rd).max() < 5e-3 and np.abs(gn - rn).max() < 5e-3
+
+
+@pytest.mark.gpu
+def test_per_element_gate_with_stored_drivers_and_pipeline_only_outputs(cuda_lib):
+    '''
+    The per-element gate of the static float32 path runs on the strided kernel (it guards the
+    zeros of the Tmin / VPD ramps), which has no storage formats and none of
+    the epilogue outputs:
+    * stored drivers in a streamable layout are converted on the device and evaluated by the
+      plain entry -- same values as the oracle's per-element gate on the stored values;
+    * an epilogue output (here the potential terms) answers MOD16_ERR_LAYOUT;
+    * the same calls with the batch-global gate stay on the fused pipeline.
+    '''
+    T, N = 6, 1024
+    rng = np.random.default_rng(19)
+    d = synthetic.host_drivers(T, N, 95, dtype=np.float32)
+    stored = _stored(d, 'packed', rng)
+    drv = [stored[k] for k in NAMES]
+    col = list(_table()[:, 5])
+    (rd, rn), _ = _reference(stored, (), col, gate='element')
+    got = run_forward(drv, params=col, gate='element')[0]
+    k = cuda_lib.mod16_last_forward_kernel()
+    assert k & 0xff == _abi.KERNEL_STRIDED and k >> 12 == 0
+    parity.assert_parity(got, rd + rn, np.float32, what='stored drivers, per-element gate')
+    run_forward(drv, params=col, gate='global')
+    k = cuda_lib.mod16_last_forward_kernel()
+    assert k & 0xff == _abi.KERNEL_PIPE and k >> 12 == 3            # fused, PACKED format
+    plain = [d[n] for n in NAMES]
+    with pytest.raises(_abi.LayoutError):
+        run_forward(plain, params=col, gate='element', out_mode='potential')
+    six = run_forward(plain, params=col, gate='global', out_mode='potential')
+    assert cuda_lib.mod16_last_forward_kernel() & 0xff == _abi.KERNEL_PIPE and len(six) == 6
