@@ -442,3 +442,40 @@ def test_calibration_config_at_full_size(cuda_lib):
     assert np.array_equal(c3, cnt[pick]) and np.all(np.abs(r_big - r_small) <= tol)
     rm = np.sqrt(sse / cnt)
     assert 10.0 < rm.min() < rm.max() < 1000.0  # plausible RMSD range, W m-2
+
+
+@pytest.mark.parametrize('pair', [False, True])
+def test_factorised_math_at_the_discontinuities(pair):
+    '''
+    K2's own arithmetic on the elements of tests/switch_cases.py (float32, 1e-8 ... 1e-3 on
+    both sides of every switch of the model).  Draw 0 is the parameter column the elements
+    were placed for, so the draw-dependent bound of the annual-temperature window (an exact
+    float comparison, mod16_objective.cuh: tann_lo) and the ends of the draw's ramps fall ON
+    elements; the other draws move them.  Every element that keeps a fast record must match
+    the oracle for every draw -- gate open and gate closed -- and the elements within rounding
+    of a draw-independent switch must have lost theirs.
+    '''
+    import switch_cases
+    drv, groups, grp, off = switch_cases.build('static', np.float32)
+    d64 = [np.asarray(v, np.float64) for v in drv]
+    col = np.array(switch_cases.BPLUT7)
+    draws = np.vstack([col[None, :], synthetic.host_param_draws(7, 321, bplut_column=col)])
+    r = hostmath.objective(draws, drv, pair=pair)
+    assert r['draw_ok'].all()
+    m = r['fast']
+    for i, x in enumerate(draws):
+        with np.errstate(all='ignore'):
+            day, night = orc.static_evapotranspiration(list(x), *d64, gate='open')
+            closed = orc.static_et(list(x), *d64, gate='closed')
+        parity.assert_parity(r['tot'][i][m], (day + night)[m], np.float32,
+                             what='K2 pred at the switches, draw %d' % i)
+        parity.assert_parity((r['tot'][i] - r['tr'][i])[m], closed[m], np.float32,
+                             what='K2 gate-closed pred at the switches, draw %d' % i)
+    # the draw-independent switches: within rounding -> no fast record; far away -> kept
+    fast = m.reshape(-1)
+    near, far = np.abs(off) <= 1e-7, np.abs(off) >= 1e-4
+    for name in ('rh07', 'g_day', 'g_night', 'a_zero'):
+        k = grp == groups.index(name)
+        assert fast[k & near].mean() < 0.5 and fast[k & far].mean() > 0.9, (
+            name, fast[k & near].mean(), fast[k & far].mean())
+    print('fast records kept at the switches: %.3f' % fast.mean())
