@@ -134,8 +134,7 @@ def test_r_corr_list_on_both_kernels(cuda_lib):
     T, N = 7, 900
     d = synthetic.host_drivers(T, N, 341, dtype=np.float64)
     drv = [d[k] for k in NAMES]
-    rc = [np.ascontiguousarray(np.broadcast_to(
-              orc.r_correction(d['pressure'], d[t]) * f, (T, N)))
+    rc = [np.broadcast_to(orc.r_correction(d['pressure'], d[t]) * f, (T, N)).copy()
           for t, f in (('temp_day', 1.1), ('temp_night', 0.9))]
     table, pft = _table(), synthetic.host_pft_map(N, 342)
     vec = [table[i][pft].reshape(1, N) for i in range(11)]
