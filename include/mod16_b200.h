@@ -122,13 +122,13 @@ enum {
                                         g_surf = 0+ is a switch of each element (the cuticular
                                         transpiration appears): the fast paths hand elements
                                         within rounding of a zero of the Tmin / VPD ramps to
-                                        the op-for-op code.  float32, static path: runs on the
-                                        strided kernel (MOD16_KERNEL_STRIDED); what only the
-                                        pipelined kernel offers is then not available and
-                                        answers MOD16_ERR_LAYOUT -- mod16_forward_raw_f32
-                                        (convert, then mod16_forward_f32) and the outputs
-                                        MOD16_OUT_ANNUAL / _POTENTIAL / _COMPOSITE / _SUM_I16
-                                        (epilogues of the batch-global `_et`) */
+                                        the op-for-op code.  float32, static path: the
+                                        pipelined kernel has that guard for plain float32
+                                        drivers and OUT_SUM / _DAY_NIGHT / _COMPONENTS; with
+                                        this gate mod16_forward_raw_f32 (convert, then
+                                        mod16_forward_f32) and the outputs MOD16_OUT_ANNUAL /
+                                        _POTENTIAL / _COMPOSITE / _SUM_I16 (epilogues of the
+                                        batch-global `_et`) answer MOD16_ERR_LAYOUT */
 #define MOD16_GATE_OPEN 0x200u       /* always compute transpiration */
 #define MOD16_GATE_CLOSED 0x300u     /* transpiration = 0 */
 #define MOD16_GATE_OPEN_TRACK 0x400u /* GATE_OPEN, and OR the predicate into *gate_flag */

@@ -755,7 +755,7 @@ M16_HD typename MaskOf<V>::type step_core(const StepInV<V>& in, V tc_d, V tc_n,
 // are differences of numbers of the size of tmin_bias / vpd_off, so within rounding of a
 // ramp's zero the sign -- and with it the element's gate -- is the double code's to decide.
 // (Under a batch-global gate an element's own outputs are continuous at these points; only
-// its vote in any(g_surf > 0) is not: DESIGN.md 3.1.)
+// its vote in any(g_surf > 0) is not: DESIGN.md 3.2.)
 // A function of the raw inputs, called BEFORE the step's arithmetic: a branch inside
 // step_core splits its basic block, changes which products are fused with their sums, and
 // the kernels that have the guard then differ from the one that has not by an ulp.
@@ -770,9 +770,10 @@ M16_HD typename MaskOf<V>::type ramp_zero_need(const StepInV<V>& in, const PftCo
              vlt(vabs(uv), ramp_guard<K>() * vabs(c.vpd_off)));
 }
 
-// (The pipelined kernel calls step_core itself and has no ramp-zero guard: at its register
-// limit the extra live values cost ten instructions per pair of steps on every path.  Static
-// launches with the per-element gate take the strided kernel, see pipe_variant.)
+// (The pipelined kernel calls step_core itself and carries the ramp-zero guard only in the
+// instantiations a per-element-gate launch runs on -- forward_pipe_kernel<..., EG = true> --:
+// at its register limit the extra live values cost ten instructions per pair of steps on
+// every path, which the headline instantiation must not pay.)
 template <class V, int SEM, bool HAS_RC>
 M16_HD typename MaskOf<V>::type step_fast(const StepInV<V>& in, const PftConstV<V>& c,
                                           const PixConstV<V>& x, int gate, StepOutV<V>& o,

@@ -18,6 +18,7 @@ namespace mod16 {
            dim3 grid, cudaStream_t st);
 M16_DECL(launch_pipe_static) M16_DECL(launch_pipe_static_b)
 M16_DECL(launch_pipe_instance) M16_DECL(launch_pipe_instance_b)
+M16_DECL(launch_pipe_static_eg)
 #undef M16_DECL
 
 template <int SEM, int OUT>
@@ -156,8 +157,11 @@ static bool dense_tn(const Arr<float>& d, int64_t T, int64_t N, int esize = 4) {
 static int pipe_variant(const ForwardArgs<float>& a, uint32_t flags) {
   if (a.N % 4 != 0 || a.has_rc) return -1;
   // the per-element gate of the static path needs the guard at the zeros of the Tmin / VPD
-  // ramps (fast::ramp_zero_need in step_fast), which the pipelined kernel is built without
-  if ((flags & MOD16_SEM_MASK) == MOD16_SEM_STATIC && a.gate == GATE_ELEMENT) return -1;
+  // ramps (fast::ramp_zero_need): the pipelined kernel has it in separate instantiations, which
+  // exist for the plain float32 layouts and the three classic output modes only
+  if ((flags & MOD16_SEM_MASK) == MOD16_SEM_STATIC && a.gate == GATE_ELEMENT &&
+      (a.raw_fmt != 0 || (flags & MOD16_OUT_MASK) > MOD16_OUT_COMPONENTS))
+    return -1;
   if (a.raw_fmt != 0) {  // storage formats: the eleven per-step arrays in the format's types
     static const int order[] = {
         MOD16_D_LW_NET_DAY, MOD16_D_LW_NET_NIGHT, MOD16_D_SW_RAD_DAY, MOD16_D_SW_ALBEDO,
@@ -269,8 +273,11 @@ static int launch_pipe(ForwardArgs<float>& a, uint32_t flags, int extra, cudaStr
     M16_CUDA_CHECK(cudaGetLastError());
   }
   const bool part_b = fmt != 0 || out_mode >= 3;
+  // (the per-element gate of the static path: the instantiations with the ramp-zero guard)
+  const bool eg = is_static && a.gate == GATE_ELEMENT;
   const int rc = is_static
-      ? (part_b ? launch_pipe_static_b : launch_pipe_static)(a, src, out_mode, extra, fmt, grid, st)
+      ? (eg ? launch_pipe_static_eg : (part_b ? launch_pipe_static_b : launch_pipe_static))(
+            a, src, out_mode, extra, fmt, grid, st)
       : (part_b ? launch_pipe_instance_b : launch_pipe_instance)(a, src, out_mode, extra, fmt, grid, st);
   if (rc != MOD16_OK) return rc;
   if (a.redo_cap > 0) {

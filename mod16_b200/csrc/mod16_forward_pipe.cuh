@@ -235,7 +235,12 @@ __device__ __forceinline__ uint32_t keep_u32(uint32_t x) {
   return y;
 }
 
-template <int SEM, int OUT, int EXTRA, int FMT>
+// EG: the instantiation for the per-element gate of the static path, with the guard at the
+// zeros of the Tmin / VPD ramps (fast::ramp_zero_need).  A compile-time flag, so that the
+// instantiations every other launch uses -- the headline one among them -- do not carry it:
+// at this kernel's register limit the few extra live values cost ten instructions per pair
+// of steps on every path.
+template <int SEM, int OUT, int EXTRA, int FMT, bool EG = false>
 __global__ void __launch_bounds__(PIPE_THREADS, 1)
 forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
                     const __grid_constant__ PipeSrc src) {
@@ -453,7 +458,11 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
     fast::StepOutV<F2> r;
     M2 g_pos;
     F2 gs;
-    const M2 late = fast::step_core<F2, SEM, false>(in, tc_d, tc_n, pc, px, gate, r, g_pos, gs);
+    // (before the step: a branch inside its arithmetic would change which products are fused)
+    M2 rz = M2{false, false};
+    if (EG) rz = fast::ramp_zero_need<F2, SEM>(in, pc, gate);
+    M2 late = fast::step_core<F2, SEM, false>(in, tc_d, tc_n, pc, px, gate, r, g_pos, gs);
+    if (EG) late = fast::mor(late, rz);
     F2 res[6];
     unsigned long long q_x = 0ULL, q_y = 0ULL;   // OUT_ANNUAL: the two steps' mass, fixed point
     int g_x = -1, g_y = -1;
@@ -569,15 +578,15 @@ forward_pipe_kernel(const __grid_constant__ ForwardArgs<float> a,
   }
 }
 
-template <int SEM, int OUT, int EXTRA, int FMT>
+template <int SEM, int OUT, int EXTRA, int FMT, bool EG = false>
 static int launch_pipe_inst(const ForwardArgs<float>& a, const PipeSrc& src, dim3 grid,
                             cudaStream_t st) {
   constexpr size_t smem = (size_t)pipe_n_stages(EXTRA, FMT) * PIPE_SUB *
                           pipe_eoff(FMT, pipe_n_arr(EXTRA)) * PIPE_TILE;
   // (the attribute is per function AND per device: set before every launch, it is cheap)
-  M16_CUDA_CHECK(cudaFuncSetAttribute(forward_pipe_kernel<SEM, OUT, EXTRA, FMT>,
+  M16_CUDA_CHECK(cudaFuncSetAttribute(forward_pipe_kernel<SEM, OUT, EXTRA, FMT, EG>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  forward_pipe_kernel<SEM, OUT, EXTRA, FMT><<<grid, PIPE_THREADS, smem, st>>>(a, src);
+  forward_pipe_kernel<SEM, OUT, EXTRA, FMT, EG><<<grid, PIPE_THREADS, smem, st>>>(a, src);
   M16_CUDA_CHECK(cudaGetLastError());
   return MOD16_OK;
 }
@@ -588,10 +597,10 @@ static int launch_pipe_inst(const ForwardArgs<float>& a, const PipeSrc& src, dim
 // day / night outputs; `separate=True` with such drivers takes the strided kernel.
 // Storage formats (FMT > 0) exist for the summed and the day / night outputs of the eleven
 // per-step arrays.
-// PART splits the instantiations over two translation units per semantics (build time):
-// 0 = the float32 layouts with the three classic output modes, 1 = storage formats, loader
-// conversions and the epilogue output modes.  Returns MOD16_ERR_FLAGS for a variant of the
-// other part.
+// PART splits the instantiations over translation units (build time): 0 = the float32
+// layouts with the three classic output modes, 1 = storage formats, loader conversions and
+// the epilogue output modes, 2 = part 0 again with the ramp-zero guard (EG; static semantics,
+// per-element gate).  Returns MOD16_ERR_FLAGS for a variant of another part.
 template <int SEM, int PART>
 int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mode, int extra,
                     int fmt, dim3 grid, cudaStream_t st) {
@@ -602,6 +611,14 @@ int launch_pipe_sem(const ForwardArgs<float>& a, const PipeSrc& src, int out_mod
     M16_PIPE(0, 0, 0); M16_PIPE(0, 1, 0); M16_PIPE(0, 2, 0); M16_PIPE(0, 3, 0);
     M16_PIPE(1, 0, 0); M16_PIPE(1, 1, 0); M16_PIPE(1, 2, 0); M16_PIPE(1, 3, 0);
     M16_PIPE(2, 0, 0); M16_PIPE(2, 1, 0);
+  } else if constexpr (PART == 2) {
+#define M16_PIPE_EG(O, E) \
+  if (out_mode == O && extra == E && fmt == 0) \
+    return launch_pipe_inst<SEM, O, E, 0, true>(a, src, grid, st)
+    M16_PIPE_EG(0, 0); M16_PIPE_EG(0, 1); M16_PIPE_EG(0, 2); M16_PIPE_EG(0, 3);
+    M16_PIPE_EG(1, 0); M16_PIPE_EG(1, 1); M16_PIPE_EG(1, 2); M16_PIPE_EG(1, 3);
+    M16_PIPE_EG(2, 0); M16_PIPE_EG(2, 1);
+#undef M16_PIPE_EG
   } else {
     M16_PIPE(0, 0, 1); M16_PIPE(0, 0, 2); M16_PIPE(0, 0, 3);
     M16_PIPE(1, 0, 1); M16_PIPE(1, 0, 2); M16_PIPE(1, 0, 3);

@@ -431,8 +431,9 @@ def test_float32_kernels_at_the_discontinuities(cuda_lib, semantics):
 
     * Per-element gate: with it the zeros of the Tmin and VPD ramps are switches too (g_surf
       = 0+ turns the cuticular transpiration on, mod16/__init__.py:343-348).  The static path
-      then runs on the strided kernel, whose guards cover them (the pipelined kernel is built
-      without that guard); the instance path has no gate and stays on the pipeline.
+      then runs on instantiations of the pipelined kernel that carry a guard for them (and on
+      the strided kernel, which has it too, where the layout is not streamable); the instance
+      path has no gate.
     * Batch-global gate (the reference's `_et`): the pipelined kernel, every component.
     All against the float64 oracle on the same float32 inputs, 1e-5 relative / 1e-3 W m-2.
     '''
@@ -451,12 +452,11 @@ def test_float32_kernels_at_the_discontinuities(cuda_lib, semantics):
         parity.assert_parity(got[c], day[c], np.float32, scale, what='element gate, day %d' % c)
         parity.assert_parity(got[3 + c], night[c], np.float32, scale,
                              what='element gate, night %d' % c)
-    # day / night totals: a layout the pipeline streams -- and takes, except for the static
-    # path under the per-element gate
+    # day / night totals: a layout the pipeline streams (static path: the guard-enabled
+    # instantiation) -- the strided kernel above and this one agree with the same oracle
     td, tn = day[0] + day[1] + day[2], night[0] + night[1] + night[2]
     got = run_forward(blk, gate='element', out_mode='day_night', **kw)
-    assert _kernel(cuda_lib)[0] == (_abi.KERNEL_STRIDED if semantics == 'static'
-                                    else _abi.KERNEL_PIPE)
+    assert _kernel(cuda_lib)[0] == _abi.KERNEL_PIPE
     parity.assert_parity(got[0], td, np.float32, scale, what='element gate, day total')
     parity.assert_parity(got[1], tn, np.float32, scale, what='element gate, night total')
     if semantics == 'static':

@@ -262,11 +262,12 @@ def test_vpd_from_mixing_ratio_and_surface_pressure(cuda_lib, N):
 @pytest.mark.gpu
 def test_per_element_gate_with_stored_drivers_and_pipeline_only_outputs(cuda_lib):
     '''
-    The per-element gate of the static float32 path runs on the strided kernel (it guards the
-    zeros of the Tmin / VPD ramps), which has no storage formats and none of
-    the epilogue outputs:
-    * stored drivers in a streamable layout are converted on the device and evaluated by the
-      plain entry -- same values as the oracle's per-element gate on the stored values;
+    The per-element gate of the static float32 path needs the guard at the zeros of the Tmin /
+    VPD ramps, which the pipelined kernel carries in separate instantiations
+    for plain float32 drivers and the three classic outputs only:
+    * stored drivers are converted on the device and evaluated by the plain entry (on that
+      guard-enabled pipeline) -- same values as the oracle's per-element gate on the stored
+      values;
     * an epilogue output (here the potential terms) answers MOD16_ERR_LAYOUT;
     * the same calls with the batch-global gate stay on the fused pipeline.
     '''
@@ -279,7 +280,7 @@ def test_per_element_gate_with_stored_drivers_and_pipeline_only_outputs(cuda_lib
     (rd, rn), _ = _reference(stored, (), col, gate='element')
     got = run_forward(drv, params=col, gate='element')[0]
     k = cuda_lib.mod16_last_forward_kernel()
-    assert k & 0xff == _abi.KERNEL_STRIDED and k >> 12 == 0
+    assert k & 0xff == _abi.KERNEL_PIPE and k >> 12 == 0          # plain float32 after torch
     parity.assert_parity(got, rd + rn, np.float32, what='stored drivers, per-element gate')
     run_forward(drv, params=col, gate='global')
     k = cuda_lib.mod16_last_forward_kernel()
